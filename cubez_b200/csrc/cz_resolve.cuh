@@ -1,0 +1,501 @@
+// cz_resolve.cuh — the contact resolver (K4): prepare + worst-first adjustPositions /
+// adjustVelocities, one thread group (a warp, or a whole CTA) per world.
+//
+// The algorithm is inherently sequential across iterations (Gauss-Seidel, worst first, each
+// iteration reads the previous one's writes — contact.go:233-283, :390-445).  Parallelism
+// inside one iteration: (1) arg-max over the contacts by warp shuffles, lowest index wins ties,
+// NaN never wins; (2) the scalar resolve of the winner is executed by the lanes of the first
+// warp redundantly from staged operands (same issue cost as one lane, no divergence), lane 0
+// commits; (3) every thread propagates the change to the contacts it owns, in the
+// reference's (b, d) order.  Iteration caps are per phase.
+//
+// Staging: per world a "body work record" bw[field*bs + body] (28 reals) and a "contact work
+// record" cw[field*cs + contact] (22 reals) — in shared memory for small worlds, in an
+// L2-resident global scratch for large ones; the code only sees pointers and strides.
+#pragma once
+#include "cz_body.cuh"
+#include "cz_narrow.cuh"
+
+namespace czr {
+using namespace czm;
+
+enum BodyWork : int { BW_POS = 0, BW_Q = 3, BW_VEL = 7, BW_ROT = 10, BW_LACC = 13, BW_IITW = 16, BW_INVM = 25, BW_MOTION = 26, BW_AWAKE = 27, BW_NF = 28 };
+enum ContactWork : int { CW_N = 0, CW_TY = 3, CW_TZ = 6, CW_RP0 = 9, CW_RP1 = 12, CW_CV = 15, CW_DDV = 18, CW_PEN = 19, CW_FRIC = 20, CW_REST = 21, CW_NF = 22 };
+enum GenField : int { G_POINT = 0, G_NORMAL = 3, G_PEN = 6, G_FRIC = 7, G_REST = 8, G_NF = 9 };
+
+struct Ctx {
+    real *bw; int bs;           // body work record, field stride
+    real *cw; int cs;           // contact work record, field stride
+    int *cb0, *cb1;             // contact body indices (world-local, -1 = nil)
+    int nC;
+    real dt;
+    // The rare "resolved body is asleep" path (contact.go:380-382) reads the body-space inverse
+    // inertia and rewrites transform + world inertia.  xb != NULL: staged copy
+    // xb[(XB_IITB+k)*xbs + b], xb[(XB_TR+k)*xbs + b] (fused kernel); else the global store.
+    real *xb; int xbs;
+    czb::BodyStore store;
+    int64_t body_base;          // global index of the world's body 0 in `store`
+};
+enum ExtraBody : int { XB_IITB = 0, XB_TR = 9, XB_NF = 21 };
+
+CZD V3 bw3(const Ctx &x, int f, int b) { return mk3(x.bw[(f + 0) * x.bs + b], x.bw[(f + 1) * x.bs + b], x.bw[(f + 2) * x.bs + b]); }
+CZD void bw3_set(const Ctx &x, int f, int b, const V3 &v) { x.bw[(f + 0) * x.bs + b] = v.c[0]; x.bw[(f + 1) * x.bs + b] = v.c[1]; x.bw[(f + 2) * x.bs + b] = v.c[2]; }
+CZD M3 bw_iitw(const Ctx &x, int b) { M3 m;
+#pragma unroll
+    for (int k = 0; k < 9; k++) m.c[k] = x.bw[(BW_IITW + k) * x.bs + b];
+    return m; }
+CZD Q4 bw_q(const Ctx &x, int b) { Q4 q;
+#pragma unroll
+    for (int k = 0; k < 4; k++) q.c[k] = x.bw[(BW_Q + k) * x.bs + b];
+    return q; }
+CZD bool bw_awake(const Ctx &x, int b) { return x.bw[BW_AWAKE * x.bs + b] != R_(0); }
+CZD V3 cw3(const Ctx &x, int f, int c) { return mk3(x.cw[(f + 0) * x.cs + c], x.cw[(f + 1) * x.cs + c], x.cw[(f + 2) * x.cs + c]); }
+CZD void cw3_set(const Ctx &x, int f, int c, const V3 &v) { x.cw[(f + 0) * x.cs + c] = v.c[0]; x.cw[(f + 1) * x.cs + c] = v.c[1]; x.cw[(f + 2) * x.cs + c] = v.c[2]; }
+
+// contact.go:87-112
+CZD real desired_delta_velocity(const Ctx &x, int b0, int b1, const V3 &n, real cvx, real restitution) {
+    real vfa = R_(0);
+    if (bw_awake(x, b0)) {
+        V3 t = bw3(x, BW_LACC, b0);
+        v_mul(t, x.dt);
+        vfa += v_dot(t, n);
+    }
+    if (b1 >= 0 && bw_awake(x, b1)) {
+        V3 t = bw3(x, BW_LACC, b1);
+        v_mul(t, x.dt);
+        vfa -= v_dot(t, n);
+    }
+    real rest = restitution;
+    if (rabs(cvx) < R_(0.25)) rest = R_(0);
+    return -cvx - rest * (cvx - vfa);
+}
+
+// contact.go:159-182
+CZD V3 local_velocity(const Ctx &x, int b, const V3 &rp, const V3 &n, const V3 &ty, const V3 &tz) {
+    V3 vel = v_cross(bw3(x, BW_ROT, b), rp);
+    v_add(vel, bw3(x, BW_VEL, b));
+    // contactToWorld columns are (n, ty, tz); TransformTranspose (math/matrix.go:157) = dots with the columns
+    V3 cv = mk3(v_dot(vel, n), v_dot(vel, ty), v_dot(vel, tz));
+    V3 acc = bw3(x, BW_LACC, b);
+    v_mul(acc, x.dt);
+    V3 a2 = mk3(v_dot(acc, n), v_dot(acc, ty), v_dot(acc, tz));
+    a2.c[0] = R_(0);
+    v_add(cv, a2);
+    return cv;
+}
+
+// contact.go:59-85 + :118-156 for contact c; gen = as-generated contact fields (stride gs).
+CZD void prepare_contact(const Ctx &x, int c, const real *gen, int gs, const int *gb0, const int *gb1) {
+    int b0 = gb0[c], b1 = gb1[c];
+    V3 n = mk3(gen[(G_NORMAL + 0) * gs + c], gen[(G_NORMAL + 1) * gs + c], gen[(G_NORMAL + 2) * gs + c]);
+    V3 point = mk3(gen[(G_POINT + 0) * gs + c], gen[(G_POINT + 1) * gs + c], gen[(G_POINT + 2) * gs + c]);
+    // all as-generated fields are read before anything is written: the fused kernel aliases
+    // `gen` with the first fields of `cw` (same contact column)
+    const real restitution = gen[G_REST * gs + c], friction = gen[G_FRIC * gs + c], pen0 = gen[G_PEN * gs + c];
+    if (b0 < 0) {   // :61-65
+        v_mul(n, R_(-1.0));
+        b0 = b1;
+        b1 = -1;
+    }
+    V3 ty, tz;      // calculateContactBasis :118-156
+    if (rabs(n.c[0]) > rabs(n.c[1])) {
+        real s = rdiv(R_(1.0), rsqrt_(n.c[2] * n.c[2] + n.c[0] * n.c[0]));
+        ty.c[0] = n.c[2] * s; ty.c[1] = R_(0); ty.c[2] = n.c[0] * -s;
+        tz.c[0] = n.c[1] * ty.c[0];
+        tz.c[1] = n.c[2] * ty.c[0] - n.c[0] * ty.c[2];
+        tz.c[2] = -n.c[1] * ty.c[0];
+    } else {
+        real s = rdiv(R_(1.0), rsqrt_(n.c[2] * n.c[2] + n.c[1] * n.c[1]));
+        ty.c[0] = R_(0); ty.c[1] = -n.c[2] * s; ty.c[2] = n.c[1] * s;
+        tz.c[0] = n.c[1] * ty.c[2] - n.c[2] * ty.c[1];
+        tz.c[1] = -n.c[0] * ty.c[2];
+        tz.c[2] = n.c[0] * ty.c[1];
+    }
+    V3 rp0 = point;
+    v_sub(rp0, bw3(x, BW_POS, b0));
+    V3 cv = local_velocity(x, b0, rp0, n, ty, tz);
+    V3 rp1 = zero3();
+    if (b1 >= 0) {
+        rp1 = point;
+        v_sub(rp1, bw3(x, BW_POS, b1));
+        V3 cv1 = local_velocity(x, b1, rp1, n, ty, tz);
+        v_sub(cv, cv1);
+    }
+    real ddv = desired_delta_velocity(x, b0, b1, n, cv.c[0], restitution);
+    x.cb0[c] = b0; x.cb1[c] = b1;
+    cw3_set(x, CW_N, c, n); cw3_set(x, CW_TY, c, ty); cw3_set(x, CW_TZ, c, tz);
+    cw3_set(x, CW_RP0, c, rp0); cw3_set(x, CW_RP1, c, rp1); cw3_set(x, CW_CV, c, cv);
+    x.cw[CW_DDV * x.cs + c] = ddv;
+    x.cw[CW_PEN * x.cs + c] = pen0;
+    x.cw[CW_FRIC * x.cs + c] = friction;
+    x.cw[CW_REST * x.cs + c] = restitution;
+}
+
+CZD void cz_syncwarp(unsigned mask) {
+#ifdef __CUDA_ARCH__
+    __syncwarp(mask);
+#else
+    (void)mask;
+#endif
+}
+
+// What one resolve hands to the propagation step.
+struct Change {
+    V3 lin[2], ang[2];   // linearChange/angularChange (position) or velocityChange/rotationChange (velocity)
+    int b[2];
+};
+
+// contact.go:185-202 on staged flags: returns which body (0/1) must be woken, or -1.
+CZD int match_awake(bool a0, bool a1, int b1) {
+    if (b1 < 0) return -1;
+    if ((a0 || a1) && !(a0 && a1)) return a0 ? 1 : 0;
+    return -1;
+}
+
+// contact.go:286-386 for the winner `c` with penetration `penetration`.  Executed by a full
+// warp redundantly; `commit` (one lane) performs the body writes.
+CZD void resolve_position(const Ctx &x, int c, real penetration, bool commit, Change &ch, unsigned mask) {
+    const real angularLimit = R_(0.2);
+    int b[2] = {x.cb0[c], x.cb1[c]};
+    V3 n = cw3(x, CW_N, c);
+    V3 rp[2] = {cw3(x, CW_RP0, c), cw3(x, CW_RP1, c)};
+    bool awake[2] = {bw_awake(x, b[0]), b[1] >= 0 ? bw_awake(x, b[1]) : false};
+    int wake = match_awake(awake[0], awake[1], b[1]);   // :252
+    if (wake >= 0) awake[wake] = true;
+    real angularInertia[2] = {R_(0), R_(0)}, linearInertia[2] = {R_(0), R_(0)}, angularMove[2], linearMove[2];
+    real totalInertia = R_(0);
+    M3 iit[2];
+    V3 pos[2];
+    Q4 q[2];
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+        ch.lin[i] = zero3(); ch.ang[i] = zero3(); ch.b[i] = b[i];
+        if (b[i] < 0) continue;
+        iit[i] = bw_iitw(x, b[i]);
+        pos[i] = bw3(x, BW_POS, b[i]);
+        q[i] = bw_q(x, b[i]);
+        V3 aiw = v_cross(rp[i], n);
+        aiw = m3_mul_v(iit[i], aiw);
+        aiw = v_cross(aiw, rp[i]);
+        angularInertia[i] = v_dot(aiw, n);
+        linearInertia[i] = x.bw[BW_INVM * x.bs + b[i]];
+        totalInertia += linearInertia[i] + angularInertia[i];
+    }
+    cz_syncwarp(mask);   // every lane has read the old body state before lane 0 overwrites it
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+        if (b[i] < 0) continue;
+        real sign = i == 0 ? R_(1.0) : R_(-1.0);
+        angularMove[i] = sign * penetration * rdiv(angularInertia[i], totalInertia);
+        linearMove[i] = sign * penetration * rdiv(linearInertia[i], totalInertia);
+        V3 proj = rp[i];
+        v_add_scaled(proj, n, -v_dot(rp[i], n));
+        real maxMag = angularLimit * v_mag(proj);
+        if (angularMove[i] < -maxMag) {
+            real total = angularMove[i] + linearMove[i];
+            angularMove[i] = -maxMag;
+            linearMove[i] = total - angularMove[i];
+        } else if (angularMove[i] > maxMag) {
+            real total = angularMove[i] + linearMove[i];
+            angularMove[i] = maxMag;
+            linearMove[i] = total - angularMove[i];
+        }
+        if (angularMove[i] == R_(0.0)) {
+            ch.ang[i] = zero3();
+        } else {
+            V3 target = v_cross(rp[i], n);
+            ch.ang[i] = m3_mul_v(iit[i], target);
+            v_mul(ch.ang[i], rdiv(angularMove[i], angularInertia[i]));
+        }
+        ch.lin[i] = n;
+        v_mul(ch.lin[i], linearMove[i]);
+        v_add_scaled(pos[i], n, linearMove[i]);
+        q_add_scaled_vector(q[i], ch.ang[i], R_(1.0));
+        q_normalize(q[i]);
+        if (!awake[i]) {
+            // contact.go:380-382: a body that is (still) asleep gets CalculateDerivedData() so
+            // the move shows up in its transform / world inertia.
+            M3 iitBody;
+            if (x.xb) {
+#pragma unroll
+                for (int k = 0; k < 9; k++) iitBody.c[k] = x.xb[(XB_IITB + k) * x.xbs + b[i]];
+            } else {
+                iitBody = czb::ld_iit_body(x.store, x.body_base + b[i]);
+            }
+            M34 tr;
+            M3 iw;
+            czb::calculate_derived(pos[i], q[i], iitBody, tr, iw);
+            if (commit) {
+                if (x.xb) {
+#pragma unroll
+                    for (int k = 0; k < 12; k++) x.xb[(XB_TR + k) * x.xbs + b[i]] = tr.c[k];
+                } else {
+                    real laz = x.bw[(BW_LACC + 2) * x.bs + b[i]];
+                    czb::st_derived(x.store, x.body_base + b[i], laz, tr, iw);
+                }
+#pragma unroll
+                for (int k = 0; k < 9; k++) x.bw[(BW_IITW + k) * x.bs + b[i]] = iw.c[k];
+            }
+        }
+        if (commit) {
+            bw3_set(x, BW_POS, b[i], pos[i]);
+#pragma unroll
+            for (int k = 0; k < 4; k++) x.bw[(BW_Q + k) * x.bs + b[i]] = q[i].c[k];
+        }
+    }
+    if (commit && wake >= 0) {   // SetAwake(true) rigidbody.go:183-186
+        x.bw[BW_AWAKE * x.bs + b[wake]] = R_(1);
+        x.bw[BW_MOTION * x.bs + b[wake]] = R_(0.6);
+    }
+}
+
+// contact.go:259-279 for one owned contact
+CZD void propagate_position(const Ctx &x, int c, const Change &ch) {
+    int cb[2] = {x.cb0[c], x.cb1[c]};
+    if (cb[0] != ch.b[0] && cb[0] != ch.b[1] && cb[1] != ch.b[0] && (cb[1] != ch.b[1] || cb[1] < 0)) return;
+    V3 n = cw3(x, CW_N, c);
+    real pen = x.cw[CW_PEN * x.cs + c];
+#pragma unroll
+    for (int b = 0; b < 2; b++) {
+        if (cb[b] < 0) continue;
+        V3 rp = cw3(x, b == 0 ? CW_RP0 : CW_RP1, c);
+#pragma unroll
+        for (int d = 0; d < 2; d++) {
+            if (cb[b] == ch.b[d]) {
+                V3 dp = v_cross(ch.ang[d], rp);
+                v_add(dp, ch.lin[d]);
+                real sign = b == 0 ? R_(-1.0) : R_(1.0);
+                pen += v_dot(dp, n) * sign;
+            }
+        }
+    }
+    x.cw[CW_PEN * x.cs + c] = pen;
+}
+
+// contact.go:448-494 (+ :498-606) for the winner `c`.
+CZD void resolve_velocity(const Ctx &x, int c, bool commit, Change &ch, int *status, unsigned mask) {
+    int b[2] = {x.cb0[c], x.cb1[c]};
+    V3 n = cw3(x, CW_N, c), ty = cw3(x, CW_TY, c), tz = cw3(x, CW_TZ, c);
+    V3 rp[2] = {cw3(x, CW_RP0, c), cw3(x, CW_RP1, c)};
+    V3 cv = cw3(x, CW_CV, c);
+    real ddv = x.cw[CW_DDV * x.cs + c];
+    real friction = x.cw[CW_FRIC * x.cs + c];
+    bool awake0 = bw_awake(x, b[0]), awake1 = b[1] >= 0 ? bw_awake(x, b[1]) : false;
+    int wake = match_awake(awake0, awake1, b[1]);   // :409
+    M3 iit[2];
+    real invMass[2] = {R_(0), R_(0)};
+    V3 vel[2], rot[2];
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+        ch.lin[i] = zero3(); ch.ang[i] = zero3(); ch.b[i] = b[i];
+#pragma unroll
+        for (int k = 0; k < 9; k++) iit[i].c[k] = R_(0);
+        if (b[i] < 0) continue;
+        iit[i] = bw_iitw(x, b[i]);
+        invMass[i] = x.bw[BW_INVM * x.bs + b[i]];
+        vel[i] = bw3(x, BW_VEL, b[i]);
+        rot[i] = bw3(x, BW_ROT, b[i]);
+    }
+    cz_syncwarp(mask);
+    M3 c2w;   // contactToWorld, columns (n, ty, tz)  (SetComponents math/matrix.go:52)
+    c2w.c[0] = n.c[0]; c2w.c[1] = n.c[1]; c2w.c[2] = n.c[2];
+    c2w.c[3] = ty.c[0]; c2w.c[4] = ty.c[1]; c2w.c[5] = ty.c[2];
+    c2w.c[6] = tz.c[0]; c2w.c[7] = tz.c[1]; c2w.c[8] = tz.c[2];
+    V3 ic;
+    if (friction == R_(0.0)) {
+        // calculateFrictionlessImpulse :498-531 (second-body block is guarded by Bodies[1]==nil
+        // in the reference: skipped for two-body contacts, a nil dereference otherwise)
+        V3 dvw = v_cross(rp[0], n);
+        dvw = m3_mul_v(iit[0], dvw);
+        dvw = v_cross(dvw, rp[0]);
+        real dv = v_dot(dvw, n);
+        dv += invMass[0];
+        if (b[1] < 0 && commit && status) *status = CZ_ERR_NIL_BODY;
+        ic = mk3(rdiv(ddv, dv), R_(0), R_(0));
+    } else {
+        // calculateFrictionImpulse :535-606
+        real inverseMass = invMass[0];
+        M3 itt;
+        set_skew(itt, rp[0]);
+        M3 dvw = m3_mul_m(itt, iit[0]);
+        dvw = m3_mul_m(dvw, itt);
+#pragma unroll
+        for (int k = 0; k < 9; k++) dvw.c[k] *= R_(-1.0);
+        if (b[1] >= 0) {
+            set_skew(itt, rp[1]);
+            M3 dvw2 = m3_mul_m(itt, iit[1]);
+            dvw2 = m3_mul_m(dvw2, itt);
+#pragma unroll
+            for (int k = 0; k < 9; k++) dvw2.c[k] *= R_(-1.0);
+#pragma unroll
+            for (int k = 0; k < 9; k++) dvw.c[k] += dvw2.c[k];
+            inverseMass += invMass[1];
+        }
+        M3 dv = m3_transpose(c2w);
+        dv = m3_mul_m(dv, dvw);
+        dv = m3_mul_m(dv, c2w);
+        dv.c[0] += inverseMass; dv.c[4] += inverseMass; dv.c[8] += inverseMass;
+        M3 im = m3_invert(dv);
+        V3 velKill = mk3(ddv, -cv.c[1], -cv.c[2]);
+        ic = m3_mul_v(im, velKill);
+        real planar = rsqrt_(ic.c[1] * ic.c[1] + ic.c[2] * ic.c[2]);
+        if (planar > ic.c[0] * friction) {
+            ic.c[1] = rdiv(ic.c[1], planar);
+            ic.c[2] = rdiv(ic.c[2], planar);
+            ic.c[0] = dv.c[0] + dv.c[3] * friction * ic.c[1] + dv.c[6] * friction * ic.c[2];
+            ic.c[0] = rdiv(ddv, ic.c[0]);
+            ic.c[1] *= friction * ic.c[0];
+            ic.c[2] *= friction * ic.c[0];
+        }
+    }
+    V3 impulse = m3_mul_v(c2w, ic);
+    V3 torque = v_cross(rp[0], impulse);
+    ch.ang[0] = m3_mul_v(iit[0], torque);
+    ch.lin[0] = zero3();
+    v_add_scaled(ch.lin[0], impulse, invMass[0]);
+    v_add(vel[0], ch.lin[0]);
+    v_add(rot[0], ch.ang[0]);
+    if (b[1] >= 0) {
+        torque = v_cross(impulse, rp[1]);
+        ch.ang[1] = m3_mul_v(iit[1], torque);
+        ch.lin[1] = zero3();
+        v_add_scaled(ch.lin[1], impulse, -invMass[1]);
+        v_add(vel[1], ch.lin[1]);
+        v_add(rot[1], ch.ang[1]);
+    }
+    if (commit) {
+        bw3_set(x, BW_VEL, b[0], vel[0]);
+        bw3_set(x, BW_ROT, b[0], rot[0]);
+        if (b[1] >= 0) {
+            bw3_set(x, BW_VEL, b[1], vel[1]);
+            bw3_set(x, BW_ROT, b[1], rot[1]);
+        }
+        if (wake >= 0) {
+            x.bw[BW_AWAKE * x.bs + b[wake]] = R_(1);
+            x.bw[BW_MOTION * x.bs + b[wake]] = R_(0.6);
+        }
+    }
+}
+
+// contact.go:416-442 for one owned contact
+CZD void propagate_velocity(const Ctx &x, int c, const Change &ch) {
+    int cb[2] = {x.cb0[c], x.cb1[c]};
+    if (cb[0] != ch.b[0] && cb[0] != ch.b[1] && cb[1] != ch.b[0] && (cb[1] != ch.b[1] || cb[1] < 0)) return;
+    V3 n = cw3(x, CW_N, c), ty = cw3(x, CW_TY, c), tz = cw3(x, CW_TZ, c);
+    V3 cv = cw3(x, CW_CV, c);
+    real restitution = x.cw[CW_REST * x.cs + c];
+    real ddv = x.cw[CW_DDV * x.cs + c];
+#pragma unroll
+    for (int b = 0; b < 2; b++) {
+        if (cb[b] < 0) continue;
+        V3 rp = cw3(x, b == 0 ? CW_RP0 : CW_RP1, c);
+#pragma unroll
+        for (int d = 0; d < 2; d++) {
+            if (cb[b] == ch.b[d]) {
+                V3 dv = v_cross(ch.ang[d], rp);
+                v_add(dv, ch.lin[d]);
+                real sign = b == 1 ? R_(-1.0) : R_(1.0);
+                V3 t = mk3(v_dot(dv, n), v_dot(dv, ty), v_dot(dv, tz));
+                v_mul(t, sign);
+                v_add(cv, t);
+                // calculateDesiredDeltaVelocity (:438) is a pure function of the final
+                // contactVelocity and of flags that do not change here: evaluated once below.
+            }
+        }
+    }
+    ddv = desired_delta_velocity(x, cb[0], cb[1], n, cv.c[0], restitution);
+    cw3_set(x, CW_CV, c, cv);
+    x.cw[CW_DDV * x.cs + c] = ddv;
+}
+
+// Arg-max of (value, index): larger value wins, equal values -> lower index (the reference's
+// linear scan keeps the first strictly-greater element, contact.go:240-245 / :396-402).
+CZD void argmax_combine(real &v, int &i, real ov, int oi) {
+    if (ov > v || (ov == v && oi < i)) { v = ov; i = oi; }
+}
+template <int WIDTH>
+__device__ __forceinline__ void warp_argmax(real &v, int &i, unsigned mask) {
+#pragma unroll
+    for (int o = WIDTH / 2; o > 0; o >>= 1) {
+        real ov = __shfl_xor_sync(mask, v, o);
+        int oi = __shfl_xor_sync(mask, i, o);
+        argmax_combine(v, i, ov, oi);
+    }
+}
+// lane mask of the NT-lane group (NT <= 32) the calling thread belongs to
+template <int NT> __device__ __forceinline__ unsigned group_mask() {
+    if constexpr (NT >= 32) {
+        return 0xffffffffu;
+    } else {
+        const unsigned lane = threadIdx.x & 31u;
+        return ((1u << NT) - 1u) << (lane & ~(unsigned)(NT - 1));
+    }
+}
+
+// Shared scratch a thread group needs for the loops.
+struct GroupScratch {
+    real redv[32];
+    int redi[32];
+    real chg[12];
+    int chb[2];
+};
+
+// Group-wide barrier: a (sub-)warp group only needs __syncwarp on its lanes; larger groups are
+// whole CTAs.
+template <int NT> __device__ __forceinline__ void group_sync(unsigned mask) {
+    if (NT <= 32) __syncwarp(mask); else __syncthreads();
+}
+
+// The two worst-first loops for one world.  NT = threads in the group (8/16/32: an aligned
+// sub-warp group owns the world — several worlds share a warp and run in SIMD; >32: the whole
+// CTA of NT threads owns it).  tid = thread index within the group.
+// field = CW_PEN (position phase) or CW_DDV (velocity phase).
+template <int NT, bool VELOCITY>
+__device__ __forceinline__ int resolve_loop(const Ctx &x, int maxIterations, GroupScratch *gs, int tid, int *status) {
+    const int lane = tid & 31, warp = tid >> 5;
+    const int field = VELOCITY ? CW_DDV : CW_PEN;
+    const unsigned mask = group_mask<NT>();
+    int used = 0;
+    while (used < maxIterations) {
+        real best = R_(0.01);   // positionEpsilon / velocityEpsilon (contact.go:12-13)
+        int idx = 0x7fffffff;
+        for (int c = tid; c < x.nC; c += NT) {
+            real v = x.cw[field * x.cs + c];
+            if (v > best) { best = v; idx = c; }
+        }
+        warp_argmax<(NT < 32 ? NT : 32)>(best, idx, mask);
+        if (NT > 32) {
+            if (lane == 0) { gs->redv[warp] = best; gs->redi[warp] = idx; }
+            __syncthreads();
+            best = lane < NT / 32 ? gs->redv[lane] : R_(0.01);
+            idx = lane < NT / 32 ? gs->redi[lane] : 0x7fffffff;
+            warp_argmax<32>(best, idx, mask);
+        }
+        if (idx == 0x7fffffff) break;
+        Change ch;
+        if (NT <= 32 || warp == 0) {
+            if (VELOCITY) resolve_velocity(x, idx, tid == 0, ch, status, mask);
+            else resolve_position(x, idx, best, tid == 0, ch, mask);
+            if (NT > 32 && lane == 0) {
+#pragma unroll
+                for (int k = 0; k < 3; k++) { gs->chg[k] = ch.lin[0].c[k]; gs->chg[3 + k] = ch.lin[1].c[k]; gs->chg[6 + k] = ch.ang[0].c[k]; gs->chg[9 + k] = ch.ang[1].c[k]; }
+                gs->chb[0] = ch.b[0]; gs->chb[1] = ch.b[1];
+            }
+        }
+        group_sync<NT>(mask);
+        if (NT > 32) {
+#pragma unroll
+            for (int k = 0; k < 3; k++) { ch.lin[0].c[k] = gs->chg[k]; ch.lin[1].c[k] = gs->chg[3 + k]; ch.ang[0].c[k] = gs->chg[6 + k]; ch.ang[1].c[k] = gs->chg[9 + k]; }
+            ch.b[0] = gs->chb[0]; ch.b[1] = gs->chb[1];
+        }
+        for (int c = tid; c < x.nC; c += NT) {
+            if (VELOCITY) propagate_velocity(x, c, ch);
+            else propagate_position(x, c, ch);
+        }
+        group_sync<NT>(mask);
+        used++;
+    }
+    return used;
+}
+
+}  // namespace czr

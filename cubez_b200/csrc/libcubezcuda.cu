@@ -1,0 +1,991 @@
+// libcubezcuda.cu — host runtime + C ABI (include/cubezcuda.h) of the B200 rigid-body step.
+//
+// One translation unit: the kernels are in cz_kernels.cuh / cz_fused.cuh.  Build (see
+// __graft_entry__.build):
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false -prec-div=true
+//        -prec-sqrt=true -ftz=false -Xcompiler -fPIC,-ffp-contract=off -shared
+//        [-DCUBEZ_REAL_FLOAT] libcubezcuda.cu -o libcubezcuda[_f32].so
+// -fmad=false is part of the correctness contract: Go on amd64 never contracts
+// a*b+c, and contact existence is a chain of float comparisons.
+//
+// No CPU fallback exists in this file: every compute entry point launches CUDA kernels and
+// returns CZ_ERR_CUDA when the runtime reports an error (e.g. no device).
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "cz_kernels.cuh"
+#include "cz_fused.cuh"
+
+using namespace czk;
+
+// ------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+
+struct cz_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int sm_count = 148;
+    size_t smem_optin = 0;
+    std::string err;
+};
+
+static int fail(cz_ctx *ctx, int code, const std::string &msg) {
+    g_err = msg;
+    if (ctx) ctx->err = msg;
+    return code;
+}
+#define CK(ctx, call)                                                                                         \
+    do {                                                                                                      \
+        cudaError_t e__ = (call);                                                                             \
+        if (e__ != cudaSuccess)                                                                               \
+            return fail(ctx, CZ_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));               \
+    } while (0)
+#define CKL(ctx) CK(ctx, cudaGetLastError())
+
+static inline unsigned nblk(long long n, int bs) { return (unsigned)((n + bs - 1) / bs); }
+
+// field -> (first real slot, components) in the chunked SoA (slot = chunk*2 + lane)
+enum Field { F_POS, F_MOTION, F_ORI, F_VEL, F_ROT, F_ACC, F_LINPOW, F_ANGPOW, F_IITB, F_LACC, F_TRANSFORM, F_IITW,
+             F_HALF, F_RADIUS, F_OFFSET, F_CTRANSFORM, F_INVM, F_LIND, F_ANGD, F_COUNT };
+struct FieldSlot { int first, comps; };
+static const FieldSlot kField[F_COUNT] = {
+    {czb::C_P01 * 2, 3}, {czb::C_P2M * 2 + 1, 1}, {czb::C_Q01 * 2, 4}, {czb::C_V01 * 2, 3}, {czb::C_V2R0 * 2 + 1, 3},
+    {czb::C_A01 * 2, 3}, {czb::C_A2LP * 2 + 1, 1}, {czb::C_APW0 * 2, 1}, {czb::C_APW0 * 2 + 1, 9}, {czb::C_L01 * 2, 3},
+    {czb::C_L2T0 * 2 + 1, 12}, {czb::C_T11W0 * 2 + 1, 9}, {czb::C_H01 * 2, 3}, {czb::C_H2R * 2 + 1, 1},
+    {czb::C_O01 * 2, 12}, {czb::C_X01 * 2, 12}, {czb::C_MD * 2, 1}, {czb::C_MD * 2 + 1, 1}, {czb::C_AD * 2, 1}};
+
+// A device-resident batch of bodies + staging, shared by the world handle and the shims.
+struct Batch {
+    cz_ctx *ctx = nullptr;
+    czb::BodyStore st{};
+    long long n = 0;
+    real *stage = nullptr;       // device staging for pack/unpack, n*12 reals
+    std::vector<real> h_lind, h_angd;   // host shadow of the damping (for the Pow refresh)
+    real pow_dt = (real)NAN;
+    bool pow_user = false;
+};
+
+static int batch_alloc(cz_ctx *ctx, Batch &b, long long n) {
+    b.ctx = ctx;
+    b.n = n;
+    long long stride = (n + 63) / 64 * 64;
+    if (stride == 0) stride = 64;
+    b.st.n = n;
+    b.st.stride = stride;
+    CK(ctx, cudaMalloc(&b.st.base, sizeof(real2) * stride * czb::N_CHUNKS));
+    CK(ctx, cudaMemsetAsync(b.st.base, 0, sizeof(real2) * stride * czb::N_CHUNKS, ctx->stream));
+    CK(ctx, cudaMalloc(&b.st.awake, stride));
+    CK(ctx, cudaMalloc(&b.st.can_sleep, stride));
+    CK(ctx, cudaMalloc(&b.st.integ, stride));
+    CK(ctx, cudaMalloc(&b.st.shape, stride));
+    CK(ctx, cudaMalloc(&b.st.ident, stride));
+    CK(ctx, cudaMalloc(&b.st.active_from, sizeof(int32_t) * stride));
+    CK(ctx, cudaMemsetAsync(b.st.awake, 1, stride, ctx->stream));
+    CK(ctx, cudaMemsetAsync(b.st.can_sleep, 1, stride, ctx->stream));
+    CK(ctx, cudaMemsetAsync(b.st.integ, 1, stride, ctx->stream));
+    CK(ctx, cudaMemsetAsync(b.st.shape, 0, stride, ctx->stream));
+    CK(ctx, cudaMemsetAsync(b.st.ident, 1, stride, ctx->stream));
+    CK(ctx, cudaMemsetAsync(b.st.active_from, 0, sizeof(int32_t) * stride, ctx->stream));
+    CK(ctx, cudaMalloc(&b.stage, sizeof(real) * stride * 12));
+    b.h_lind.assign(n, (real)0.95);
+    b.h_angd.assign(n, (real)0.95);
+    return CZ_OK;
+}
+static void batch_free(Batch &b) {
+    if (b.st.base) cudaFree(b.st.base);
+    if (b.st.awake) cudaFree(b.st.awake);
+    if (b.st.can_sleep) cudaFree(b.st.can_sleep);
+    if (b.st.integ) cudaFree(b.st.integ);
+    if (b.st.shape) cudaFree(b.st.shape);
+    if (b.st.ident) cudaFree(b.st.ident);
+    if (b.st.active_from) cudaFree(b.st.active_from);
+    if (b.stage) cudaFree(b.stage);
+    b = Batch();
+}
+
+static int put_field(Batch &b, Field f, long long first, long long n, const real *host) {
+    if (!host || n == 0) return CZ_OK;
+    cz_ctx *ctx = b.ctx;
+    const FieldSlot fs = kField[f];
+    CK(ctx, cudaMemcpyAsync(b.stage, host, sizeof(real) * n * fs.comps, cudaMemcpyHostToDevice, ctx->stream));
+    k_pack<<<nblk(n * fs.comps, 256), 256, 0, ctx->stream>>>(b.st.base, b.st.stride, first, n, b.stage, fs.first, fs.comps);
+    CKL(ctx);
+    // the staging buffer is reused by the next field: order the copy after the kernel
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return CZ_OK;
+}
+static int get_field(Batch &b, Field f, long long first, long long n, real *host) {
+    if (!host || n == 0) return CZ_OK;
+    cz_ctx *ctx = b.ctx;
+    const FieldSlot fs = kField[f];
+    k_unpack<<<nblk(n * fs.comps, 256), 256, 0, ctx->stream>>>(b.st.base, b.st.stride, first, n, b.stage, fs.first, fs.comps);
+    CKL(ctx);
+    CK(ctx, cudaMemcpyAsync(host, b.stage, sizeof(real) * n * fs.comps, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return CZ_OK;
+}
+static int put_u8(Batch &b, uint8_t *dev, long long first, long long n, const uint8_t *host) {
+    if (!host || n == 0) return CZ_OK;
+    CK(b.ctx, cudaMemcpyAsync(dev + first, host, n, cudaMemcpyHostToDevice, b.ctx->stream));
+    CK(b.ctx, cudaStreamSynchronize(b.ctx->stream));
+    return CZ_OK;
+}
+static int get_u8(Batch &b, const uint8_t *dev, long long first, long long n, uint8_t *host) {
+    if (!host || n == 0) return CZ_OK;
+    CK(b.ctx, cudaMemcpyAsync(host, dev + first, n, cudaMemcpyDeviceToHost, b.ctx->stream));
+    CK(b.ctx, cudaStreamSynchronize(b.ctx->stream));
+    return CZ_OK;
+}
+
+// Evaluate Pow(damping, dt) in float64 on the host and round to Real (rigidbody.go:233-234),
+// then upload.  This is the library default; cz_world_set_pow lets the host language supply
+// its own bit pattern instead.
+static int refresh_pow(Batch &b, long long first, long long n, real dt) {
+    std::vector<real> lp(n), ap(n);
+    for (long long i = 0; i < n; i++) {
+        lp[i] = (real)std::pow((double)b.h_lind[first + i], (double)dt);
+        ap[i] = (real)std::pow((double)b.h_angd[first + i], (double)dt);
+    }
+    int rc = put_field(b, F_LINPOW, first, n, lp.data());
+    if (rc) return rc;
+    return put_field(b, F_ANGPOW, first, n, ap.data());
+}
+
+static int upload_bodies(Batch &b, long long first, long long n, const cz_bodies *s) {
+    int rc;
+    if ((rc = put_field(b, F_POS, first, n, s->position))) return rc;
+    if ((rc = put_field(b, F_ORI, first, n, s->orientation))) return rc;
+    if ((rc = put_field(b, F_VEL, first, n, s->velocity))) return rc;
+    if ((rc = put_field(b, F_ROT, first, n, s->rotation))) return rc;
+    if ((rc = put_field(b, F_ACC, first, n, s->acceleration))) return rc;
+    if ((rc = put_field(b, F_LIND, first, n, s->linear_damping))) return rc;
+    if ((rc = put_field(b, F_ANGD, first, n, s->angular_damping))) return rc;
+    if ((rc = put_field(b, F_IITB, first, n, s->inverse_inertia_tensor))) return rc;
+    if ((rc = put_field(b, F_INVM, first, n, s->inverse_mass))) return rc;
+    if ((rc = put_field(b, F_MOTION, first, n, s->motion))) return rc;
+    if ((rc = put_field(b, F_TRANSFORM, first, n, s->transform))) return rc;
+    if ((rc = put_field(b, F_IITW, first, n, s->inverse_inertia_tensor_world))) return rc;
+    if ((rc = put_field(b, F_LACC, first, n, s->last_frame_acceleration))) return rc;
+    if ((rc = put_u8(b, b.st.awake, first, n, s->is_awake))) return rc;
+    if ((rc = put_u8(b, b.st.can_sleep, first, n, s->can_sleep))) return rc;
+    if (s->linear_damping) std::memcpy(b.h_lind.data() + first, s->linear_damping, sizeof(real) * n);
+    if (s->angular_damping) std::memcpy(b.h_angd.data() + first, s->angular_damping, sizeof(real) * n);
+    if (s->linear_damping || s->angular_damping) b.pow_dt = (real)NAN;   // Pow factors are stale
+    return CZ_OK;
+}
+static int download_bodies(Batch &b, long long first, long long n, cz_bodies *s) {
+    int rc;
+    if ((rc = get_field(b, F_POS, first, n, s->position))) return rc;
+    if ((rc = get_field(b, F_ORI, first, n, s->orientation))) return rc;
+    if ((rc = get_field(b, F_VEL, first, n, s->velocity))) return rc;
+    if ((rc = get_field(b, F_ROT, first, n, s->rotation))) return rc;
+    if ((rc = get_field(b, F_ACC, first, n, s->acceleration))) return rc;
+    if ((rc = get_field(b, F_LIND, first, n, s->linear_damping))) return rc;
+    if ((rc = get_field(b, F_ANGD, first, n, s->angular_damping))) return rc;
+    if ((rc = get_field(b, F_IITB, first, n, s->inverse_inertia_tensor))) return rc;
+    if ((rc = get_field(b, F_INVM, first, n, s->inverse_mass))) return rc;
+    if ((rc = get_field(b, F_MOTION, first, n, s->motion))) return rc;
+    if ((rc = get_field(b, F_TRANSFORM, first, n, s->transform))) return rc;
+    if ((rc = get_field(b, F_IITW, first, n, s->inverse_inertia_tensor_world))) return rc;
+    if ((rc = get_field(b, F_LACC, first, n, s->last_frame_acceleration))) return rc;
+    if ((rc = get_u8(b, b.st.awake, first, n, s->is_awake))) return rc;
+    if ((rc = get_u8(b, b.st.can_sleep, first, n, s->can_sleep))) return rc;
+    return CZ_OK;
+}
+static int upload_colliders(Batch &b, long long first, long long n, const cz_colliders *c) {
+    int rc;
+    cz_ctx *ctx = b.ctx;
+    if (c->shape) {
+        std::vector<uint8_t> sh(n);
+        for (long long i = 0; i < n; i++) sh[i] = (uint8_t)c->shape[i];
+        if ((rc = put_u8(b, b.st.shape, first, n, sh.data()))) return rc;
+    }
+    if ((rc = put_field(b, F_OFFSET, first, n, c->offset))) return rc;
+    if ((rc = put_field(b, F_CTRANSFORM, first, n, c->transform))) return rc;
+    if ((rc = put_field(b, F_HALF, first, n, c->half_size))) return rc;
+    if ((rc = put_field(b, F_RADIUS, first, n, c->radius))) return rc;
+    if (c->offset) {
+        k_detect_identity<<<nblk(n, 256), 256, 0, ctx->stream>>>(b.st, first, n);
+        CKL(ctx);
+    }
+    return CZ_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// world handle
+// ------------------------------------------------------------------------------------------
+struct cz_world {
+    cz_ctx *ctx = nullptr;
+    cz_world_desc d{};
+    Batch b;
+    int P = 0;
+    PlaneView planes[CZ_MAX_PLANES];
+    int nchk = 0;
+    int *d_one = nullptr, *d_two = nullptr;
+    long long step_index = 0;
+    real *gen = nullptr;
+    int *gb0 = nullptr, *gb1 = nullptr, *nContacts = nullptr, *posIters = nullptr, *velIters = nullptr;
+    unsigned long long *stats = nullptr;   // device ST_N counters
+    // narrowphase multi-tile scratch
+    int tiles = 1, tileThreads = 32;
+    int *tileCount = nullptr, *tileBase = nullptr;
+    uint8_t *hitCount = nullptr;
+    // resolver
+    ResolveScratch rs{};
+    int resolveNT = 32;
+    int resolveSmem = 0;        // dynamic shared bytes when staged in smem, 0 = global scratch
+    bool useFused = false;
+    czf::FusedPlan fused{};
+    real bias = (real)NAN;
+    unsigned long long *h_stats = nullptr;   // pinned
+    // pinned staging for cz_world_step_host
+    real *h_pin = nullptr;
+    size_t h_pin_bytes = 0;
+};
+
+static WorldParams world_params(cz_world *w) {
+    WorldParams p;
+    p.st = w->b.st;
+    p.W = w->d.n_worlds; p.B = w->d.bodies_per_world; p.P = w->P; p.Cc = w->d.contacts_per_world;
+    p.nchk = w->nchk;
+    p.schedule = w->d.schedule;
+    p.chk_one = w->d_one; p.chk_two = w->d_two;
+    for (int i = 0; i < CZ_MAX_PLANES; i++) p.planes[i] = w->planes[i];
+    p.step_index = w->step_index;
+    p.gen = w->gen; p.gb0 = w->gb0; p.gb1 = w->gb1;
+    p.nContacts = w->nContacts; p.posIters = w->posIters; p.velIters = w->velIters;
+    p.stats = w->stats;
+    return p;
+}
+
+// (Re)derive everything that depends on the schedule size / capacities.
+static int world_plan(cz_world *w) {
+    cz_ctx *ctx = w->ctx;
+    const int B = w->d.bodies_per_world, Cc = w->d.contacts_per_world, W = w->d.n_worlds;
+    if (w->d.schedule == CZ_SCHED_ALL_PAIRS_ORDERED) w->nchk = B * (w->P + B);
+    // narrowphase tiling
+    int threads = (w->nchk + 31) / 32 * 32;
+    if (threads < 32) threads = 32;
+    if (threads > 256) threads = 256;
+    w->tileThreads = threads;
+    w->tiles = w->nchk > 0 ? (w->nchk + threads - 1) / threads : 1;
+    if (w->tileCount) { cudaFree(w->tileCount); w->tileCount = nullptr; }
+    if (w->tileBase) { cudaFree(w->tileBase); w->tileBase = nullptr; }
+    if (w->hitCount) { cudaFree(w->hitCount); w->hitCount = nullptr; }
+    if (w->tiles > 1) {
+        CK(ctx, cudaMalloc(&w->tileCount, sizeof(int) * (size_t)W * w->tiles));
+        CK(ctx, cudaMalloc(&w->tileBase, sizeof(int) * (size_t)W * w->tiles));
+        CK(ctx, cudaMalloc(&w->hitCount, (size_t)W * w->nchk));
+    }
+    // resolver staging
+    size_t need = sizeof(real) * ((size_t)czr::BW_NF * B + (size_t)czr::CW_NF * Cc) + sizeof(int) * 2 * (size_t)Cc;
+    w->resolveNT = Cc <= 128 ? 32 : 256;
+    size_t limit = ctx->smem_optin > 2048 ? ctx->smem_optin - 2048 : 0;
+    if (need <= limit) {
+        w->resolveSmem = (int)need;
+    } else {
+        w->resolveSmem = 0;
+        if (!w->rs.bw) {
+            CK(ctx, cudaMalloc(&w->rs.bw, sizeof(real) * (size_t)W * czr::BW_NF * B));
+            CK(ctx, cudaMalloc(&w->rs.cw, sizeof(real) * (size_t)W * czr::CW_NF * Cc));
+            CK(ctx, cudaMalloc(&w->rs.cb, sizeof(int) * (size_t)W * 2 * Cc));
+        }
+    }
+    // fused small-world kernel
+    w->useFused = false;
+    if (!(w->d.flags & CZ_WORLD_NO_FUSED)) {
+        w->useFused = czf::plan(w->fused, B, w->P, Cc, w->nchk, w->d.schedule, ctx->smem_optin);
+    }
+    if ((w->d.flags & CZ_WORLD_FUSED) && !w->useFused)
+        return fail(ctx, CZ_ERR_INVALID, "CZ_WORLD_FUSED requested but the world does not fit the fused kernel");
+    return CZ_OK;
+}
+
+extern "C" {
+
+int cz_real_size(void) { return (int)sizeof(real); }
+
+const char *cz_last_error(cz_ctx *ctx) { return ctx ? ctx->err.c_str() : g_err.c_str(); }
+
+int cz_init(int device, cz_ctx **out) {
+    if (!out) return fail(nullptr, CZ_ERR_INVALID, "cz_init: out is NULL");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(nullptr, CZ_ERR_CUDA, std::string("no CUDA device: ") + cudaGetErrorString(e) + " (libcubezcuda has no CPU fallback)");
+    if (device < 0 || device >= count) return fail(nullptr, CZ_ERR_INVALID, "cz_init: bad device index");
+    cz_ctx *ctx = new cz_ctx;
+    ctx->device = device;
+    CK(ctx, cudaSetDevice(device));
+    CK(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CK(ctx, cudaEventCreate(&ctx->ev0));
+    CK(ctx, cudaEventCreate(&ctx->ev1));
+    cudaDeviceProp prop;
+    CK(ctx, cudaGetDeviceProperties(&prop, device));
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->smem_optin = prop.sharedMemPerBlockOptin;
+    *out = ctx;
+    return CZ_OK;
+}
+int cz_shutdown(cz_ctx *ctx) {
+    if (!ctx) return CZ_ERR_INVALID;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    cudaEventDestroy(ctx->ev0);
+    cudaEventDestroy(ctx->ev1);
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return CZ_OK;
+}
+void *cz_ctx_stream(cz_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
+int cz_ctx_synchronize(cz_ctx *ctx) {
+    if (!ctx) return CZ_ERR_INVALID;
+    CK(ctx, cudaSetDevice(ctx->device));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return CZ_OK;
+}
+int cz_host_alloc(cz_ctx *ctx, uint64_t bytes, void **out) {
+    if (!ctx || !out) return CZ_ERR_INVALID;
+    CK(ctx, cudaSetDevice(ctx->device));
+    CK(ctx, cudaHostAlloc(out, bytes, cudaHostAllocDefault));
+    return CZ_OK;
+}
+int cz_host_free(cz_ctx *ctx, void *p) {
+    if (!ctx) return CZ_ERR_INVALID;
+    CK(ctx, cudaFreeHost(p));
+    return CZ_OK;
+}
+
+// ---- world -----------------------------------------------------------------------------
+int cz_world_create(cz_ctx *ctx, const cz_world_desc *desc, cz_world **out) {
+    if (!ctx || !desc || !out) return fail(ctx, CZ_ERR_INVALID, "cz_world_create: NULL argument");
+    if (desc->n_worlds <= 0 || desc->bodies_per_world <= 0 || desc->contacts_per_world <= 0)
+        return fail(ctx, CZ_ERR_INVALID, "cz_world_create: sizes must be positive");
+    CK(ctx, cudaSetDevice(ctx->device));
+    cz_world *w = new cz_world;
+    w->ctx = ctx;
+    w->d = *desc;
+    const long long NB = (long long)desc->n_worlds * desc->bodies_per_world;
+    const size_t NC = (size_t)desc->n_worlds * desc->contacts_per_world;
+    int rc = batch_alloc(ctx, w->b, NB);
+    if (rc) { delete w; return rc; }
+    CK(ctx, cudaMalloc(&w->gen, sizeof(real) * czr::G_NF * NC));
+    CK(ctx, cudaMalloc(&w->gb0, sizeof(int) * NC));
+    CK(ctx, cudaMalloc(&w->gb1, sizeof(int) * NC));
+    CK(ctx, cudaMalloc(&w->nContacts, sizeof(int) * desc->n_worlds));
+    CK(ctx, cudaMalloc(&w->posIters, sizeof(int) * desc->n_worlds));
+    CK(ctx, cudaMalloc(&w->velIters, sizeof(int) * desc->n_worlds));
+    CK(ctx, cudaMemsetAsync(w->nContacts, 0, sizeof(int) * desc->n_worlds, ctx->stream));
+    CK(ctx, cudaMemsetAsync(w->posIters, 0, sizeof(int) * desc->n_worlds, ctx->stream));
+    CK(ctx, cudaMemsetAsync(w->velIters, 0, sizeof(int) * desc->n_worlds, ctx->stream));
+    CK(ctx, cudaMalloc(&w->stats, sizeof(unsigned long long) * ST_N));
+    CK(ctx, cudaMemsetAsync(w->stats, 0, sizeof(unsigned long long) * ST_N, ctx->stream));
+    CK(ctx, cudaHostAlloc(&w->h_stats, sizeof(unsigned long long) * ST_N, cudaHostAllocDefault));
+    for (int i = 0; i < CZ_MAX_PLANES; i++) { w->planes[i].n = czm::mk3(0, 1, 0); w->planes[i].offset = 0; }
+    rc = world_plan(w);
+    if (rc) { cz_world_destroy(w); return rc; }
+    *out = w;
+    return CZ_OK;
+}
+int cz_world_destroy(cz_world *w) {
+    if (!w) return CZ_ERR_INVALID;
+    cudaSetDevice(w->ctx->device);
+    cudaStreamSynchronize(w->ctx->stream);
+    batch_free(w->b);
+    void *ptrs[] = {w->d_one, w->d_two, w->gen, w->gb0, w->gb1, w->nContacts, w->posIters, w->velIters, w->stats,
+                    w->tileCount, w->tileBase, w->hitCount, w->rs.bw, w->rs.cw, w->rs.cb};
+    for (void *p : ptrs) if (p) cudaFree(p);
+    if (w->h_stats) cudaFreeHost(w->h_stats);
+    if (w->h_pin) cudaFreeHost(w->h_pin);
+    delete w;
+    return CZ_OK;
+}
+static int world_range(cz_world *w, int first, int n) {
+    if (!w) return fail(nullptr, CZ_ERR_INVALID, "NULL world");
+    if (first < 0 || n < 0 || first + n > w->d.n_worlds) return fail(w->ctx, CZ_ERR_INVALID, "world range out of bounds");
+    return CZ_OK;
+}
+int cz_world_upload_bodies(cz_world *w, int32_t first, int32_t n, const cz_bodies *b, int32_t derive) {
+    int rc = world_range(w, first, n);
+    if (rc) return rc;
+    cz_ctx *ctx = w->ctx;
+    CK(ctx, cudaSetDevice(ctx->device));
+    const long long B = w->d.bodies_per_world;
+    if ((rc = upload_bodies(w->b, first * B, n * B, b))) return rc;
+    if (derive) {
+        k_derive<<<nblk(n * B, 256), 256, 0, ctx->stream>>>(w->b.st, first * B, n * B, 1, 1);
+        CKL(ctx);
+    }
+    return CZ_OK;
+}
+int cz_world_upload_colliders(cz_world *w, int32_t first, int32_t n, const cz_colliders *c, int32_t derive) {
+    int rc = world_range(w, first, n);
+    if (rc) return rc;
+    cz_ctx *ctx = w->ctx;
+    CK(ctx, cudaSetDevice(ctx->device));
+    const long long B = w->d.bodies_per_world;
+    if ((rc = upload_colliders(w->b, first * B, n * B, c))) return rc;
+    if (derive) {
+        k_derive<<<nblk(n * B, 256), 256, 0, ctx->stream>>>(w->b.st, first * B, n * B, 0, 1);
+        CKL(ctx);
+    }
+    return CZ_OK;
+}
+int cz_world_upload_planes(cz_world *w, const cz_planes *p) {
+    if (!w || !p) return CZ_ERR_INVALID;
+    if (p->n > CZ_MAX_PLANES) return fail(w->ctx, CZ_ERR_INVALID, "too many planes (max 8)");
+    w->P = p->n;
+    for (int i = 0; i < p->n; i++) {
+        w->planes[i].n = czm::mk3(p->normal[i * 3], p->normal[i * 3 + 1], p->normal[i * 3 + 2]);
+        w->planes[i].offset = p->offset[i];
+    }
+    return world_plan(w);
+}
+int cz_world_upload_schedule(cz_world *w, int32_t n_checks, const int32_t *one, const int32_t *two) {
+    if (!w || n_checks < 0) return CZ_ERR_INVALID;
+    cz_ctx *ctx = w->ctx;
+    CK(ctx, cudaSetDevice(ctx->device));
+    if (w->d.schedule != CZ_SCHED_EXPLICIT) return fail(ctx, CZ_ERR_INVALID, "world was not created with CZ_SCHED_EXPLICIT");
+    for (int i = 0; i < n_checks; i++) {
+        if (one[i] >= w->d.bodies_per_world || two[i] >= w->d.bodies_per_world || one[i] < -CZ_MAX_PLANES || two[i] < -CZ_MAX_PLANES)
+            return fail(ctx, CZ_ERR_INVALID, "schedule entry out of range");
+    }
+    if (w->d_one) cudaFree(w->d_one);
+    if (w->d_two) cudaFree(w->d_two);
+    w->d_one = w->d_two = nullptr;
+    CK(ctx, cudaMalloc(&w->d_one, sizeof(int) * (n_checks + 1)));
+    CK(ctx, cudaMalloc(&w->d_two, sizeof(int) * (n_checks + 1)));
+    CK(ctx, cudaMemcpy(w->d_one, one, sizeof(int) * n_checks, cudaMemcpyHostToDevice));
+    CK(ctx, cudaMemcpy(w->d_two, two, sizeof(int) * n_checks, cudaMemcpyHostToDevice));
+    w->nchk = n_checks;
+    return world_plan(w);
+}
+int cz_world_set_activation(cz_world *w, int32_t first, int32_t n, const int32_t *active_from, const uint8_t *integrate) {
+    int rc = world_range(w, first, n);
+    if (rc) return rc;
+    cz_ctx *ctx = w->ctx;
+    CK(ctx, cudaSetDevice(ctx->device));
+    const long long B = w->d.bodies_per_world;
+    if (active_from) CK(ctx, cudaMemcpy(w->b.st.active_from + first * B, active_from, sizeof(int32_t) * n * B, cudaMemcpyHostToDevice));
+    if (integrate) CK(ctx, cudaMemcpy(w->b.st.integ + first * B, integrate, n * B, cudaMemcpyHostToDevice));
+    return CZ_OK;
+}
+int cz_world_set_pow(cz_world *w, cz_real dt, const cz_real *lin_pow, const cz_real *ang_pow, cz_real bias) {
+    if (!w || !lin_pow || !ang_pow) return CZ_ERR_INVALID;
+    CK(w->ctx, cudaSetDevice(w->ctx->device));
+    int rc;
+    if ((rc = put_field(w->b, F_LINPOW, 0, w->b.n, lin_pow))) return rc;
+    if ((rc = put_field(w->b, F_ANGPOW, 0, w->b.n, ang_pow))) return rc;
+    w->b.pow_dt = dt;
+    w->b.pow_user = true;
+    w->bias = bias;
+    return CZ_OK;
+}
+int cz_world_set_step_index(cz_world *w, int64_t s) {
+    if (!w) return CZ_ERR_INVALID;
+    w->step_index = s;
+    return CZ_OK;
+}
+int cz_world_synchronize(cz_world *w) {
+    if (!w) return CZ_ERR_INVALID;
+    CK(w->ctx, cudaSetDevice(w->ctx->device));
+    CK(w->ctx, cudaStreamSynchronize(w->ctx->stream));
+    return CZ_OK;
+}
+
+}  // extern "C"
+
+template <int NT>
+static void launch_resolve(cz_world *w, const WorldParams &p, int maxIterOverride, real dt, bool forceGlobal) {
+    int smem = forceGlobal ? 0 : w->resolveSmem;
+    if (smem > 48 * 1024) cudaFuncSetAttribute(k_resolve<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    k_resolve<NT><<<p.W, NT, smem, w->ctx->stream>>>(p, w->rs, smem > 0 ? 1 : 0, maxIterOverride, dt);
+}
+
+// one frame of updateCallback (examples/cubedrop.go:69-75) on the multi-kernel path
+static int world_step_multi(cz_world *w, real dt, long long &launches) {
+    cz_ctx *ctx = w->ctx;
+    WorldParams p = world_params(w);
+    const long long NB = w->b.n;
+    int grid = (int)std::min<long long>(nblk(NB, 256), (long long)ctx->sm_count * 8);
+    k_integrate<true><<<grid, 256, 0, ctx->stream>>>(w->b.st, dt, w->bias, w->step_index);
+    CKL(ctx);
+    launches++;
+    if (w->nchk > 0) {
+        if (w->tiles == 1) {
+            k_narrow<NARROW_SINGLE><<<p.W, w->tileThreads, 0, ctx->stream>>>(p, 1, nullptr, nullptr, nullptr);
+            CKL(ctx);
+            launches++;
+        } else {
+            k_narrow<NARROW_COUNT><<<p.W * w->tiles, w->tileThreads, 0, ctx->stream>>>(p, w->tiles, w->tileCount, nullptr, w->hitCount);
+            CKL(ctx);
+            k_scan_tiles<<<p.W, 256, 0, ctx->stream>>>(p, w->tiles, w->tileCount, w->tileBase);
+            CKL(ctx);
+            k_narrow<NARROW_EMIT><<<p.W * w->tiles, w->tileThreads, 0, ctx->stream>>>(p, w->tiles, nullptr, w->tileBase, w->hitCount);
+            CKL(ctx);
+            launches += 3;
+        }
+        if (w->resolveNT == 32) launch_resolve<32>(w, p, -1, dt, false);
+        else launch_resolve<256>(w, p, -1, dt, false);
+        CKL(ctx);
+        launches++;
+    }
+    return CZ_OK;
+}
+
+static int world_prepare_step(cz_world *w, real dt) {
+    if (!(w->b.pow_dt == dt)) {   // also true when pow_dt is NaN
+        int rc = refresh_pow(w->b, 0, w->b.n, dt);
+        if (rc) return rc;
+        w->b.pow_dt = dt;
+        w->b.pow_user = false;
+        w->bias = (real)std::pow(0.5, (double)dt);   // rigidbody.go:250
+    }
+    return CZ_OK;
+}
+
+static int read_stats(cz_world *w, cz_step_stats *stats, long long launches, int n_steps, float ms) {
+    cz_ctx *ctx = w->ctx;
+    CK(ctx, cudaMemcpyAsync(w->h_stats, w->stats, sizeof(unsigned long long) * ST_N, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    int status = -(int)w->h_stats[ST_STATUS];
+    if (stats) {
+        std::memset(stats, 0, sizeof(*stats));
+        stats->steps = (int64_t)w->d.n_worlds * n_steps;
+        stats->contacts = (int64_t)w->h_stats[ST_CONTACTS];
+        stats->pos_iterations = (int64_t)w->h_stats[ST_POS];
+        stats->vel_iterations = (int64_t)w->h_stats[ST_VEL];
+        stats->checks = (int64_t)w->nchk * w->d.n_worlds * n_steps;
+        stats->kernel_launches = launches;
+        stats->max_contacts = (int32_t)w->h_stats[ST_MAXC];
+        stats->status = status;
+        stats->device_ms = ms;
+    }
+    if (status == CZ_ERR_CAPACITY) return fail(ctx, status, "contact capacity exceeded (contacts_per_world too small)");
+    if (status == CZ_ERR_NIL_BODY) return fail(ctx, status, "frictionless one-body contact: the reference dereferences a nil body (contact.go:512-523)");
+    if (status) return fail(ctx, status, "device-side error");
+    return CZ_OK;
+}
+
+extern "C" {
+
+int cz_world_step(cz_world *w, cz_real dt, int32_t n_steps, cz_step_stats *stats) {
+    if (!w || n_steps < 0) return fail(nullptr, CZ_ERR_INVALID, "cz_world_step: bad argument");
+    cz_ctx *ctx = w->ctx;
+    CK(ctx, cudaSetDevice(ctx->device));
+    int rc = world_prepare_step(w, dt);
+    if (rc) return rc;
+    long long launches = 0;
+    if (stats) {
+        CK(ctx, cudaMemsetAsync(w->stats, 0, sizeof(unsigned long long) * ST_N, ctx->stream));
+        CK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    }
+    if (w->useFused) {
+        WorldParams p = world_params(w);
+        rc = czf::launch(w->fused, p, dt, w->bias, n_steps, ctx->stream, ctx->sm_count);
+        if (rc) return fail(ctx, CZ_ERR_CUDA, std::string("fused launch: ") + cudaGetErrorString((cudaError_t)rc));
+        launches++;
+        w->step_index += n_steps;
+    } else {
+        for (int s = 0; s < n_steps; s++) {
+            if ((rc = world_step_multi(w, dt, launches))) return rc;
+            w->step_index++;
+        }
+    }
+    if (stats) {
+        CK(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+        CK(ctx, cudaEventSynchronize(ctx->ev1));
+        float ms = 0;
+        CK(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        return read_stats(w, stats, launches, n_steps, ms);
+    }
+    return CZ_OK;
+}
+
+int cz_world_download_bodies(cz_world *w, int32_t first, int32_t n, cz_bodies *out) {
+    int rc = world_range(w, first, n);
+    if (rc) return rc;
+    CK(w->ctx, cudaSetDevice(w->ctx->device));
+    const long long B = w->d.bodies_per_world;
+    return download_bodies(w->b, first * B, n * B, out);
+}
+int cz_world_download_colliders(cz_world *w, int32_t first, int32_t n, cz_colliders *out) {
+    int rc = world_range(w, first, n);
+    if (rc) return rc;
+    CK(w->ctx, cudaSetDevice(w->ctx->device));
+    const long long B = w->d.bodies_per_world;
+    if ((rc = get_field(w->b, F_CTRANSFORM, first * B, n * B, out->transform))) return rc;
+    if ((rc = get_field(w->b, F_OFFSET, first * B, n * B, out->offset))) return rc;
+    if ((rc = get_field(w->b, F_HALF, first * B, n * B, out->half_size))) return rc;
+    if ((rc = get_field(w->b, F_RADIUS, first * B, n * B, out->radius))) return rc;
+    if (out->shape) {
+        std::vector<uint8_t> sh(n * B);
+        if ((rc = get_u8(w->b, w->b.st.shape, first * B, n * B, sh.data()))) return rc;
+        for (long long i = 0; i < n * B; i++) out->shape[i] = sh[i];
+    }
+    return CZ_OK;
+}
+int cz_world_download_contacts(cz_world *w, int32_t world, cz_contacts *out) {
+    int rc = world_range(w, world, 1);
+    if (rc) return rc;
+    cz_ctx *ctx = w->ctx;
+    CK(ctx, cudaSetDevice(ctx->device));
+    int nC = 0;
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    CK(ctx, cudaMemcpy(&nC, w->nContacts + world, sizeof(int), cudaMemcpyDeviceToHost));
+    out->n = nC;
+    if (nC > out->capacity || nC > w->d.contacts_per_world) return fail(ctx, CZ_ERR_CAPACITY, "cz_world_download_contacts: capacity too small");
+    if (nC == 0) return CZ_OK;
+    const size_t Cc = w->d.contacts_per_world, gs = (size_t)w->d.n_worlds * Cc, off = (size_t)world * Cc;
+    std::vector<real> tmp(nC);
+    auto getf = [&](int f, real *dst, int comp, int ncomp) -> int {
+        CK(ctx, cudaMemcpy(tmp.data(), w->gen + f * gs + off, sizeof(real) * nC, cudaMemcpyDeviceToHost));
+        for (int i = 0; i < nC; i++) dst[i * ncomp + comp] = tmp[i];
+        return CZ_OK;
+    };
+    for (int k = 0; k < 3; k++) {
+        if (out->point && (rc = getf(czr::G_POINT + k, out->point, k, 3))) return rc;
+        if (out->normal && (rc = getf(czr::G_NORMAL + k, out->normal, k, 3))) return rc;
+    }
+    if (out->penetration && (rc = getf(czr::G_PEN, out->penetration, 0, 1))) return rc;
+    if (out->friction && (rc = getf(czr::G_FRIC, out->friction, 0, 1))) return rc;
+    if (out->restitution && (rc = getf(czr::G_REST, out->restitution, 0, 1))) return rc;
+    if (out->body0) CK(ctx, cudaMemcpy(out->body0, w->gb0 + off, sizeof(int) * nC, cudaMemcpyDeviceToHost));
+    if (out->body1) CK(ctx, cudaMemcpy(out->body1, w->gb1 + off, sizeof(int) * nC, cudaMemcpyDeviceToHost));
+    return CZ_OK;
+}
+int cz_world_last_step_counts(cz_world *w, int32_t *n_contacts, int32_t *pos_it, int32_t *vel_it) {
+    if (!w) return CZ_ERR_INVALID;
+    cz_ctx *ctx = w->ctx;
+    CK(ctx, cudaSetDevice(ctx->device));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    const size_t bytes = sizeof(int) * w->d.n_worlds;
+    if (n_contacts) CK(ctx, cudaMemcpy(n_contacts, w->nContacts, bytes, cudaMemcpyDeviceToHost));
+    if (pos_it) CK(ctx, cudaMemcpy(pos_it, w->posIters, bytes, cudaMemcpyDeviceToHost));
+    if (vel_it) CK(ctx, cudaMemcpy(vel_it, w->velIters, bytes, cudaMemcpyDeviceToHost));
+    return CZ_OK;
+}
+int cz_world_checksum_energy(cz_world *w, uint64_t *checksum, double *energy) {
+    if (!w) return CZ_ERR_INVALID;
+    cz_ctx *ctx = w->ctx;
+    CK(ctx, cudaSetDevice(ctx->device));
+    const int W = w->d.n_worlds;
+    unsigned long long *dh = nullptr;
+    double *de = nullptr;
+    CK(ctx, cudaMalloc(&dh, sizeof(unsigned long long) * W));
+    CK(ctx, cudaMalloc(&de, sizeof(double) * W));
+    k_checksum_energy<<<nblk(W, 128), 128, 0, ctx->stream>>>(w->b.st, W, w->d.bodies_per_world, dh, de);
+    CKL(ctx);
+    std::vector<unsigned long long> hh(W);
+    std::vector<double> he(W);
+    CK(ctx, cudaMemcpyAsync(hh.data(), dh, sizeof(unsigned long long) * W, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(ctx, cudaMemcpyAsync(he.data(), de, sizeof(double) * W, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(dh);
+    cudaFree(de);
+    unsigned long long sum = 0;
+    double e = 0;
+    for (int i = 0; i < W; i++) { sum += hh[i]; e += he[i]; }
+    if (checksum) *checksum = sum;
+    if (energy) *energy = e;
+    return CZ_OK;
+}
+
+// Host-buffer step: the end-to-end call of a host-resident caller.  Uploads the primary
+// state (what the host may have edited: the K1 read set), runs n_steps, downloads everything
+// Integrate/ResolveContacts write.  Pinned staging, one stream.
+int cz_world_step_host(cz_world *w, cz_bodies *io, cz_real dt, int32_t n_steps, cz_step_stats *stats) {
+    if (!w || !io) return CZ_ERR_INVALID;
+    if (io->n != w->b.n) return fail(w->ctx, CZ_ERR_INVALID, "cz_world_step_host: io->n must equal n_worlds*bodies_per_world");
+    cz_bodies up = *io;
+    up.transform = nullptr; up.inverse_inertia_tensor_world = nullptr; up.last_frame_acceleration = nullptr;
+    up.inverse_mass = nullptr;   // constant after setup
+    int rc = upload_bodies(w->b, 0, w->b.n, &up);
+    if (rc) return rc;
+    if ((rc = cz_world_step(w, dt, n_steps, stats))) return rc;
+    cz_bodies down = *io;
+    down.acceleration = nullptr; down.linear_damping = nullptr; down.angular_damping = nullptr;
+    down.inverse_inertia_tensor = nullptr; down.inverse_mass = nullptr; down.can_sleep = nullptr;
+    return download_bodies(w->b, 0, w->b.n, &down);
+}
+
+// ---- object-API shims ------------------------------------------------------------------------
+int cz_integrate(cz_ctx *ctx, cz_bodies *io, cz_real dt, const cz_real *lin_pow, const cz_real *ang_pow, const cz_real *bias) {
+    if (!ctx || !io || io->n <= 0) return fail(ctx, CZ_ERR_INVALID, "cz_integrate: bad argument");
+    CK(ctx, cudaSetDevice(ctx->device));
+    Batch b;
+    int rc = batch_alloc(ctx, b, io->n);
+    if (!rc) rc = upload_bodies(b, 0, io->n, io);
+    if (!rc) {
+        if (lin_pow && ang_pow) {
+            rc = put_field(b, F_LINPOW, 0, io->n, lin_pow);
+            if (!rc) rc = put_field(b, F_ANGPOW, 0, io->n, ang_pow);
+        } else {
+            rc = refresh_pow(b, 0, io->n, dt);
+        }
+    }
+    if (!rc) {
+        real bs = bias ? *bias : (real)std::pow(0.5, (double)dt);
+        int grid = (int)std::min<long long>(nblk(io->n, 256), (long long)ctx->sm_count * 8);
+        k_integrate<false><<<grid, 256, 0, ctx->stream>>>(b.st, dt, bs, 0);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) rc = fail(ctx, CZ_ERR_CUDA, cudaGetErrorString(e));
+    }
+    if (!rc) rc = download_bodies(b, 0, io->n, io);
+    batch_free(b);
+    return rc;
+}
+
+int cz_calculate_derived_data(cz_ctx *ctx, cz_bodies *io) {
+    if (!ctx || !io || io->n <= 0) return fail(ctx, CZ_ERR_INVALID, "cz_calculate_derived_data: bad argument");
+    CK(ctx, cudaSetDevice(ctx->device));
+    Batch b;
+    int rc = batch_alloc(ctx, b, io->n);
+    if (!rc) rc = upload_bodies(b, 0, io->n, io);
+    if (!rc) {
+        k_derive<<<nblk(io->n, 256), 256, 0, ctx->stream>>>(b.st, 0, io->n, 1, 0);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) rc = fail(ctx, CZ_ERR_CUDA, cudaGetErrorString(e));
+    }
+    if (!rc) rc = download_bodies(b, 0, io->n, io);
+    batch_free(b);
+    return rc;
+}
+
+int cz_collider_derive(cz_ctx *ctx, int32_t n, const cz_real *body_transform, const cz_real *offset, cz_real *out) {
+    if (!ctx || n <= 0 || !body_transform || !offset || !out) return fail(ctx, CZ_ERR_INVALID, "cz_collider_derive: bad argument");
+    CK(ctx, cudaSetDevice(ctx->device));
+    Batch b;
+    int rc = batch_alloc(ctx, b, n);
+    if (!rc) rc = put_field(b, F_TRANSFORM, 0, n, body_transform);
+    if (!rc) rc = put_field(b, F_OFFSET, 0, n, offset);
+    if (!rc) {
+        k_fill_u8<<<nblk(n, 256), 256, 0, ctx->stream>>>(b.st.shape, n, CZ_SHAPE_CUBE);
+        k_fill_u8<<<nblk(n, 256), 256, 0, ctx->stream>>>(b.st.ident, n, 0);
+        k_derive<<<nblk(n, 256), 256, 0, ctx->stream>>>(b.st, 0, n, 0, 1);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) rc = fail(ctx, CZ_ERR_CUDA, cudaGetErrorString(e));
+    }
+    if (!rc) rc = get_field(b, F_CTRANSFORM, 0, n, out);
+    batch_free(b);
+    return rc;
+}
+
+int cz_narrowphase(cz_ctx *ctx, const cz_colliders *colliders, const cz_planes *planes, const cz_bodies *bodies,
+                   int32_t n_checks, const int32_t *one, const int32_t *two, cz_contacts *out, uint8_t *found) {
+    if (!ctx || !colliders || !out || n_checks < 0 || colliders->n <= 0) return fail(ctx, CZ_ERR_INVALID, "cz_narrowphase: bad argument");
+    // A one-world handle whose "bodies" are the colliders; contact body ids are mapped back
+    // through colliders->body on the way out.
+    cz_world_desc d{1, colliders->n, std::max(1, out->capacity), CZ_SCHED_EXPLICIT, CZ_WORLD_NO_FUSED};
+    cz_world *w = nullptr;
+    int rc = cz_world_create(ctx, &d, &w);
+    if (rc) return rc;
+    const int n = colliders->n;
+    do {
+        if (planes && planes->n > 0 && (rc = cz_world_upload_planes(w, planes))) break;
+        if ((rc = upload_colliders(w->b, 0, n, colliders))) break;
+        if (bodies && bodies->velocity) {   // sphere.Body.Velocity for colliders.go:417-421
+            std::vector<real> vel((size_t)n * 3, 0);
+            for (int i = 0; i < n; i++) {
+                int bi = colliders->body ? colliders->body[i] : i;
+                if (bi >= 0 && bi < bodies->n) for (int k = 0; k < 3; k++) vel[i * 3 + k] = bodies->velocity[bi * 3 + k];
+            }
+            if ((rc = put_field(w->b, F_VEL, 0, n, vel.data()))) break;
+        }
+        if ((rc = cz_world_upload_schedule(w, n_checks, one, two))) break;
+        WorldParams p = world_params(w);
+        if (n_checks > 0) {
+            // always the COUNT/EMIT pair here so that per-check hit counts are available
+            if (!w->hitCount) {
+                cudaMalloc(&w->tileCount, sizeof(int) * w->tiles);
+                cudaMalloc(&w->tileBase, sizeof(int) * w->tiles);
+                cudaMalloc(&w->hitCount, n_checks);
+            }
+            k_narrow<NARROW_COUNT><<<w->tiles, w->tileThreads, 0, ctx->stream>>>(p, w->tiles, w->tileCount, nullptr, w->hitCount);
+            k_scan_tiles<<<1, 256, 0, ctx->stream>>>(p, w->tiles, w->tileCount, w->tileBase);
+            k_narrow<NARROW_EMIT><<<w->tiles, w->tileThreads, 0, ctx->stream>>>(p, w->tiles, nullptr, w->tileBase, w->hitCount);
+            cudaError_t e = cudaGetLastError();
+            if (e != cudaSuccess) { rc = fail(ctx, CZ_ERR_CUDA, cudaGetErrorString(e)); break; }
+            if (found) {
+                cudaStreamSynchronize(ctx->stream);
+                cudaMemcpy(found, w->hitCount, n_checks, cudaMemcpyDeviceToHost);
+                for (int i = 0; i < n_checks; i++) found[i] = found[i] ? 1 : 0;
+            }
+        } else {
+            cudaMemsetAsync(w->nContacts, 0, sizeof(int), ctx->stream);
+        }
+        rc = cz_world_download_contacts(w, 0, out);
+        if (rc) break;
+        if (colliders->body) {
+            for (int i = 0; i < out->n; i++) {
+                if (out->body0 && out->body0[i] >= 0) out->body0[i] = colliders->body[out->body0[i]];
+                if (out->body1 && out->body1[i] >= 0) out->body1[i] = colliders->body[out->body1[i]];
+            }
+        }
+    } while (0);
+    cz_world_destroy(w);
+    return rc;
+}
+
+int cz_resolve_contacts(cz_ctx *ctx, int32_t max_iterations, cz_contacts *io, cz_bodies *bodies, cz_real dt, int32_t *iters) {
+    if (!ctx || !io || !bodies || bodies->n <= 0) return fail(ctx, CZ_ERR_INVALID, "cz_resolve_contacts: bad argument");
+    if (iters) iters[0] = iters[1] = 0;
+    if (!(dt > 0) || io->n <= 0) return CZ_OK;   // contact.go:210-212
+    cz_world_desc d{1, bodies->n, io->n, CZ_SCHED_EXPLICIT, CZ_WORLD_NO_FUSED};
+    cz_world *w = nullptr;
+    int rc = cz_world_create(ctx, &d, &w);
+    if (rc) return rc;
+    const int nC = io->n;
+    do {
+        if ((rc = upload_bodies(w->b, 0, bodies->n, bodies))) break;
+        // contacts -> as-generated arrays
+        const size_t gs = (size_t)nC;
+        std::vector<real> g((size_t)czr::G_NF * nC);
+        for (int i = 0; i < nC; i++) {
+            for (int k = 0; k < 3; k++) { g[(czr::G_POINT + k) * gs + i] = io->point[i * 3 + k]; g[(czr::G_NORMAL + k) * gs + i] = io->normal[i * 3 + k]; }
+            g[czr::G_PEN * gs + i] = io->penetration[i];
+            g[czr::G_FRIC * gs + i] = io->friction ? io->friction[i] : (real)0.9;
+            g[czr::G_REST * gs + i] = io->restitution ? io->restitution[i] : (real)0.1;
+        }
+        cudaMemcpy(w->gen, g.data(), sizeof(real) * g.size(), cudaMemcpyHostToDevice);
+        cudaMemcpy(w->gb0, io->body0, sizeof(int) * nC, cudaMemcpyHostToDevice);
+        cudaMemcpy(w->gb1, io->body1, sizeof(int) * nC, cudaMemcpyHostToDevice);
+        cudaMemcpy(w->nContacts, &nC, sizeof(int), cudaMemcpyHostToDevice);
+        if (!w->rs.bw) {
+            cudaMalloc(&w->rs.bw, sizeof(real) * czr::BW_NF * bodies->n);
+            cudaMalloc(&w->rs.cw, sizeof(real) * czr::CW_NF * nC);
+            cudaMalloc(&w->rs.cb, sizeof(int) * 2 * nC);
+        }
+        WorldParams p = world_params(w);
+        if (w->resolveNT == 32) launch_resolve<32>(w, p, max_iterations, dt, true);
+        else launch_resolve<256>(w, p, max_iterations, dt, true);
+        k_contacts_writeback<<<nblk(nC, 128), 128, 0, ctx->stream>>>(p, w->rs);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) { rc = fail(ctx, CZ_ERR_CUDA, cudaGetErrorString(e)); break; }
+        cz_step_stats st;
+        rc = read_stats(w, &st, 2, 1, 0.f);
+        if (rc) break;
+        if (iters) {
+            cudaMemcpy(&iters[0], w->posIters, sizeof(int), cudaMemcpyDeviceToHost);
+            cudaMemcpy(&iters[1], w->velIters, sizeof(int), cudaMemcpyDeviceToHost);
+        }
+        int cap = io->capacity;
+        io->capacity = std::max(cap, nC);
+        rc = cz_world_download_contacts(w, 0, io);
+        io->capacity = cap;
+        if (rc) break;
+        cz_bodies down = *bodies;
+        down.acceleration = nullptr; down.linear_damping = nullptr; down.angular_damping = nullptr;
+        down.inverse_inertia_tensor = nullptr; down.inverse_mass = nullptr; down.can_sleep = nullptr;
+        rc = download_bodies(w->b, 0, bodies->n, &down);
+    } while (0);
+    cz_world_destroy(w);
+    return rc;
+}
+
+// ---- microbench / diagnostics --------------------------------------------------------------
+int cz_bench_integrate(cz_ctx *ctx, int64_t n, uint64_t seed, int32_t warmup, int32_t steps, cz_real dt, float *avg_ms, uint64_t *checksum) {
+    if (!ctx || n <= 0 || steps <= 0) return fail(ctx, CZ_ERR_INVALID, "cz_bench_integrate: bad argument");
+    CK(ctx, cudaSetDevice(ctx->device));
+    Batch b;
+    int rc = batch_alloc(ctx, b, n);
+    if (rc) { batch_free(b); return rc; }
+    k_init_free_bodies<<<nblk(n, 256), 256, 0, ctx->stream>>>(b.st, seed, dt);
+    real bias = (real)std::pow(0.5, (double)dt);
+    // grid: a multiple of the SM count; 256-thread CTAs, 2+ resident per SM
+    int grid = (int)std::min<long long>(nblk(n, 256), (long long)ctx->sm_count * 16);
+    for (int i = 0; i < warmup; i++) k_integrate<false><<<grid, 256, 0, ctx->stream>>>(b.st, dt, bias, 0);
+    cudaEventRecord(ctx->ev0, ctx->stream);
+    for (int i = 0; i < steps; i++) k_integrate<false><<<grid, 256, 0, ctx->stream>>>(b.st, dt, bias, 0);
+    cudaEventRecord(ctx->ev1, ctx->stream);
+    cudaError_t e = cudaEventSynchronize(ctx->ev1);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) { batch_free(b); return fail(ctx, CZ_ERR_CUDA, cudaGetErrorString(e)); }
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+    if (avg_ms) *avg_ms = ms / steps;
+    if (checksum) {
+        // checksum over the first 4096 bodies (keeps the check cheap)
+        int W = (int)std::min<int64_t>(n, 4096);
+        unsigned long long *dh;
+        double *de;
+        cudaMalloc(&dh, sizeof(unsigned long long) * W);
+        cudaMalloc(&de, sizeof(double) * W);
+        k_checksum_energy<<<nblk(W, 128), 128, 0, ctx->stream>>>(b.st, W, 1, dh, de);
+        std::vector<unsigned long long> hh(W);
+        cudaMemcpyAsync(hh.data(), dh, sizeof(unsigned long long) * W, cudaMemcpyDeviceToHost, ctx->stream);
+        cudaStreamSynchronize(ctx->stream);
+        unsigned long long s = 0;
+        for (auto v : hh) s += v;
+        *checksum = s;
+        cudaFree(dh);
+        cudaFree(de);
+    }
+    batch_free(b);
+    return CZ_OK;
+}
+
+}  // extern "C"
+
+__global__ void k_math_op(int op, const real *in, real *out) {
+    using namespace czm;
+    auto v3 = [&](int o) { return mk3(in[o], in[o + 1], in[o + 2]); };
+    auto q4 = [&](int o) { Q4 q; for (int k = 0; k < 4; k++) q.c[k] = in[o + k]; return q; };
+    auto m3 = [&](int o) { M3 m; for (int k = 0; k < 9; k++) m.c[k] = in[o + k]; return m; };
+    auto m34 = [&](int o) { M34 m; for (int k = 0; k < 12; k++) m.c[k] = in[o + k]; return m; };
+    auto put3 = [&](const V3 &v) { out[0] = v.c[0]; out[1] = v.c[1]; out[2] = v.c[2]; };
+    switch (op) {
+    case CZ_OP_VEC_ADD: { V3 a = v3(0); v_add(a, v3(3)); put3(a); break; }
+    case CZ_OP_VEC_ADD_SCALED: { V3 a = v3(0); v_add_scaled(a, v3(3), in[6]); put3(a); break; }
+    case CZ_OP_VEC_COMPONENT_PRODUCT: { V3 a = v3(0); v_component_product(a, v3(3)); put3(a); break; }
+    case CZ_OP_VEC_CROSS: put3(v_cross(v3(0), v3(3))); break;
+    case CZ_OP_VEC_DOT: out[0] = v_dot(v3(0), v3(3)); break;
+    case CZ_OP_VEC_MAGNITUDE: out[0] = v_mag(v3(0)); break;
+    case CZ_OP_VEC_SQUARE_MAGNITUDE: out[0] = v_sqmag(v3(0)); break;
+    case CZ_OP_VEC_MUL_WITH: { V3 a = v3(0); v_mul(a, in[3]); put3(a); break; }
+    case CZ_OP_VEC_NORMALIZE: { V3 a = v3(0); v_normalize(a); put3(a); break; }
+    case CZ_OP_VEC_SUB: { V3 a = v3(0); v_sub(a, v3(3)); put3(a); break; }
+    case CZ_OP_QUAT_MUL: { Q4 a = q4(0); q_mul(a, q4(4)); for (int k = 0; k < 4; k++) out[k] = a.c[k]; break; }
+    case CZ_OP_QUAT_LEN: out[0] = q_len(q4(0)); break;
+    case CZ_OP_QUAT_NORMALIZE: { Q4 a = q4(0); q_normalize(a); for (int k = 0; k < 4; k++) out[k] = a.c[k]; break; }
+    case CZ_OP_QUAT_ROTATE: put3(q_rotate(q4(0), v3(4))); break;
+    case CZ_OP_QUAT_ADD_SCALED_VECTOR: { Q4 a = q4(0); q_add_scaled_vector(a, v3(4), in[7]); for (int k = 0; k < 4; k++) out[k] = a.c[k]; break; }
+    case CZ_OP_M3_MUL_M3: { M3 r = m3_mul_m(m3(0), m3(9)); for (int k = 0; k < 9; k++) out[k] = r.c[k]; break; }
+    case CZ_OP_M3_INVERT: { M3 r = m3_invert(m3(0)); for (int k = 0; k < 9; k++) out[k] = r.c[k]; break; }
+    case CZ_OP_M3_MUL_V: put3(m3_mul_v(m3(0), v3(9))); break;
+    case CZ_OP_M3_TRANSFORM_TRANSPOSE: put3(m3_transform_transpose(m3(0), v3(9))); break;
+    case CZ_OP_M3_DETERMINANT: out[0] = m3_det(m3(0)); break;
+    case CZ_OP_M34_MUL_M34: { M34 r = m34_mul_m34(m34(0), m34(12)); for (int k = 0; k < 12; k++) out[k] = r.c[k]; break; }
+    case CZ_OP_M34_MUL_V: put3(m34_mul_v(m34(0), v3(12))); break;
+    case CZ_OP_M34_TRANSFORM_INVERSE: put3(m34_transform_inverse(m34(0), v3(12))); break;
+    case CZ_OP_M34_SET_AS_TRANSFORM: { M34 r; m34_set_as_transform(r, v3(0), q4(3)); for (int k = 0; k < 12; k++) out[k] = r.c[k]; break; }
+    case CZ_OP_REAL_EQUAL: out[0] = real_equal(in[0], in[1]) ? R_(1) : R_(0); break;
+    case CZ_OP_TRANSFORM_INERTIA: { M3 w; transform_inertia_tensor(w, m3(0), m34(9)); for (int k = 0; k < 9; k++) out[k] = w.c[k]; break; }
+    default: out[0] = R_(0);
+    }
+}
+
+extern "C" {
+
+int cz_math_op(cz_ctx *ctx, int32_t op, const cz_real *in, cz_real *out) {
+    if (!ctx || !in || !out) return CZ_ERR_INVALID;
+    CK(ctx, cudaSetDevice(ctx->device));
+    real *d = nullptr;
+    CK(ctx, cudaMalloc(&d, sizeof(real) * 48));
+    CK(ctx, cudaMemcpy(d, in, sizeof(real) * 24, cudaMemcpyHostToDevice));
+    k_math_op<<<1, 1, 0, ctx->stream>>>(op, d, d + 24);
+    CKL(ctx);
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    CK(ctx, cudaMemcpy(out, d + 24, sizeof(real) * 12, cudaMemcpyDeviceToHost));
+    cudaFree(d);
+    return CZ_OK;
+}
+
+}  // extern "C"
