@@ -1,0 +1,259 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the cubez B200 hot path (contract: see README/DESIGN.md).
+
+Workload (BASELINE.json configs[3], "batched RL-style"): 65 536 independent, perturbed 8-cube
+cubedrop worlds PER GPU (weak scaling; worlds never exchange data), 600-frame episodes at
+dt = 1/60, float64.  World k starts at frame (k mod 600) of its episode and is reset to its
+initial state when the episode ends, so every timed frame sees the same stationary mix of
+free fall / impact / settling / sleeping worlds, whatever --steps is.  One "step" = one frame
+of updateCallback (examples/cubedrop.go:69-75) for every world of the job.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+  (N > 1: launched by torchrun, one rank per GPU; NCCL only for the end-of-run reduce)
+
+Prints ONE JSON line on rank 0.  `value` = world-steps/s with state resident on the GPU;
+`e2e` = the same through cz_world_step_host with pinned HOST buffers (H2D + D2H every step);
+`roofline` = the dominant kernel of this workload (fused world step); `roofline_k1` = the
+HBM-bound integrate+derive kernel on 16 Mi free bodies (cfg5); `cpu_baseline` = the CPU oracle
+("port" of the Go loops; Go itself can not run in this image) on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+EPISODE = 600
+DT = 1.0 / 60.0
+WORLDS_PER_GPU = int(os.environ.get("CUBEZ_BENCH_WORLDS", 65536))
+BODIES_PER_WORLD = 8
+K1_BODIES = 1 << 24
+K1_BYTES_F64 = 531          # algorithmic bytes per awake body-step
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        sm = [float(s[0]) for s in self.samples if s and s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if len(s) > 1 and s[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for s in self.samples if len(s) >= 7 for i in range(4) if s[3 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(self.samples)}
+
+
+def cpu_oracle_sample(n_worlds: int, n_threads: int):
+    """World-steps/s of the CPU oracle on full 600-frame episodes of the first n_worlds worlds
+    (the stationary population's average cost per frame equals the episode average)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from cubez_b200 import scenes
+    from oracle_lib import OracleWorld     # the checker; allowed here as the CPU baseline only
+    sc = scenes.batched_cubedrop(n_worlds=n_worlds)
+    w = OracleWorld.from_scene(sc)
+    t0 = time.perf_counter()
+    w.step(DT, EPISODE, n_threads=n_threads)
+    dt = time.perf_counter() - t0
+    w.close()
+    return n_worlds * EPISODE / dt, dt
+
+
+def run_reference(args, rank):
+    """--impl reference: the reference's CPU implementation of the path on the host cores.
+    Go can not be built here, so this is the line-by-line C++ restatement (oracle/), AoS
+    structs and per-contact heap allocation kept, worlds partitioned over all host threads."""
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    per_step_worlds = threads * 8
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    for _ in range(args.warmup):
+        cpu_oracle_sample(per_step_worlds, threads)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_oracle_sample(per_step_worlds, threads)
+    el = time.perf_counter() - t0
+    value = per_step_worlds * EPISODE * args.steps / el
+    line = {
+        "impl": "reference", "metric": "world_steps_per_s", "value": value, "unit": "world-steps/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * el / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "cfg4 batched RL-style cubedrop-8, 600-frame episodes (CPU sample)", "dt": DT,
+                   "bodies_per_world": BODIES_PER_WORLD},
+        "cpu_baseline": {"value": value, "unit": "world-steps/s", "cores": threads, "kind": "port",
+                         "sample": f"each step = {per_step_worlds} worlds x {EPISODE} frames on {threads} threads (C++ restatement of the Go loops; no Go toolchain in this image)"},
+        "e2e": {"value": value, "unit": "world-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "body_steps_per_s": value * BODIES_PER_WORLD,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=120)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--worlds", type=int, default=WORLDS_PER_GPU, help="worlds per GPU")
+    ap.add_argument("--e2e-steps", type=int, default=10)
+    ap.add_argument("--no-k1", action="store_true", help="skip the cfg5 integrate roofline run")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", 0))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    world_size = int(os.environ.get("WORLD_SIZE", 1))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: libcubezcuda has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world_size > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    from cubez_b200 import _abi, scenes
+    from cubez_b200.api import BatchedWorld, Context
+    from cubez_b200.sharding import reduce_run
+
+    W = args.worlds
+    first_world = rank * W                      # weak scaling: every rank owns W worlds with distinct global ids
+    ctx = Context.get(local_rank, "f64")
+    scene = scenes.batched_cubedrop(_abi.F64, n_worlds=W, first_world=first_world)
+    contact_cap = int(os.environ.get("CUBEZ_BENCH_CONTACT_CAP", 64))
+    world = BatchedWorld.from_scene(scene, device=local_rank, contacts_per_world=contact_cap, ctx=ctx)
+    phase0 = ((first_world + np.arange(W, dtype=np.int64)) % EPISODE).astype(np.int32)
+    world.set_episodes(EPISODE, phase0)
+    world.step(DT, EPISODE, stats=True)         # pre-roll (setup, untimed): the population becomes stationary
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world_size > 1:
+            dist.barrier()
+        world.synchronize()
+
+    # ---- device-resident arm --------------------------------------------------------------
+    world.step(DT, args.warmup, stats=True)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    t0 = time.perf_counter()
+    st = world.step(DT, args.steps, stats=True)         # K frames, CUDA events on the launching stream inside
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    dev_ms = float(st["device_ms"])
+    cks, energy = world.checksum_energy()
+    red = reduce_run(cks, energy, {"contacts": st["contacts"], "pos_iterations": st["pos_iterations"],
+                                   "vel_iterations": st["vel_iterations"], "launches": st["kernel_launches"]}, dev_ms, dev)
+    max_ms = red["max_ms"]
+    total_world_steps = W * world_size * args.steps
+    value = total_world_steps / (max_ms * 1e-3)
+
+    # ---- end-to-end arm: host buffers through cz_world_step_host ------------------------------
+    host = world.download()
+    nb = W * BODIES_PER_WORLD
+    h2d = nb * (28 * 8 + 2)                      # primary state the host may have edited (K1 read set)
+    d2h = nb * (38 * 8 + 1)                      # everything the frame writes
+    world.step_host(host, DT, 1)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        world.step_host(host, DT, 1)
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / args.e2e_steps
+    if world_size > 1:
+        t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    e2e_value = W * world_size / (e2e_ms * 1e-3)
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+
+    # ---- roofline of the dominant kernel (fused world step) ---------------------------------
+    peak, peak_kind = measured_peaks()
+    # algorithmic HBM bytes of one k_world_fused launch: stage 41 chunks (16 B) + 5 flag/int fields per body in,
+    # 25 chunks + 1 flag out; independent of the number of frames (state stays in shared memory)
+    fused_bytes = nb * (41 * 16 + 8 + 25 * 16 + 1)
+    roofline = {"bound": "hbm", "kernel": "k_world_fused", "achieved": fused_bytes / (dev_ms * 1e-3) / 1e9, "peak": peak,
+                "unit": "GB/s", "frac": fused_bytes / (dev_ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_kind": peak_kind,
+                "note": "not HBM-bound by design: state is shared-memory resident across frames; the kernel is FP64-issue/latency bound (see profiles/)"}
+    roofline_k1 = None
+    if rank == 0 and not args.no_k1:
+        world.close()
+        ms, _ = ctx.bench_integrate(K1_BODIES, warmup=3, steps=50, dt=DT)
+        ach = K1_BODIES * K1_BYTES_F64 / (ms * 1e-3) / 1e9
+        roofline_k1 = {"bound": "hbm", "kernel": "k_integrate<false> (Integrate+CalculateDerivedData, cfg5: 16Mi free bodies f64)",
+                       "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_kind": peak_kind,
+                       "ms_per_launch": ms, "body_steps_per_s": K1_BODIES / (ms * 1e-3), "bytes_per_body": K1_BYTES_F64}
+
+    if rank == 0:
+        cpu_value, cpu_s = cpu_oracle_sample(256, 1)
+        line = {
+            "metric": "world_steps_per_s", "value": value, "unit": "world-steps/s", "n_gpus": world_size, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": max_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "cfg4 batched RL-style: independent perturbed 8-cube cubedrop worlds, 600-frame episodes, phases staggered uniformly, reset at episode end",
+                       "worlds_per_gpu": W, "bodies_per_world": BODIES_PER_WORLD, "dt": DT, "contact_capacity": contact_cap,
+                       "parallelism": f"worlds sharded over {world_size} GPU(s), no per-step collective",
+                       "l2": "state (%.0f MB/GPU) larger than L2; frames of one call run from shared memory" % (nb * 84 * 16 / 1e6)},
+            "body_steps_per_s": value * BODIES_PER_WORLD,
+            "e2e": {"value": e2e_value, "unit": "world-steps/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_ms, "api": "cz_world_step_host (pinned staging, 1 frame per call)"},
+            "gpu_launches": int(red["counters"]["launches"]),
+            "clocks": sampler.summary(),
+            "roofline": roofline,
+            "roofline_k1": roofline_k1,
+            "cpu_baseline": {"value": cpu_value, "unit": "world-steps/s", "cores": 1, "kind": "port",
+                             "sample": f"256 worlds x {EPISODE} frames, 1 thread, {cpu_s:.1f} s (C++ restatement of the Go loops)"},
+            "checksum": hex(red["checksum"]), "energy": red["energy"],
+            "contacts_per_world_step": red["counters"]["contacts"] / total_world_steps,
+            "vel_iterations_per_world_step": red["counters"]["vel_iterations"] / total_world_steps,
+            "pos_iterations_per_world_step": red["counters"]["pos_iterations"] / total_world_steps,
+            "wall_ms_timed_region": wall_ms,
+        }
+        print(json.dumps(line), flush=True)
+    if world_size > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

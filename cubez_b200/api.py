@@ -192,6 +192,11 @@ class BatchedWorld:
     def set_step_index(self, s: int):
         self.ctx.check(self.lib.cz_world_set_step_index(self.h, s))
 
+    def set_episodes(self, length: int, phase0=None):
+        """RL-style episodes: snapshot now; world k is at frame phase0[k] and resets on wrap."""
+        ph = np.zeros(self.n_worlds, dtype=np.int32) if phase0 is None else np.ascontiguousarray(phase0, dtype=np.int32)
+        self.ctx.check(self.lib.cz_world_set_episodes(self.h, length, ph.ctypes.data_as(C.POINTER(C.c_int32))))
+
     # ---- stepping --------------------------------------------------------------------
     def step(self, dt, n_steps: int = 1, stats: bool = True) -> Optional[dict]:
         st = CzStepStats()

@@ -28,7 +28,16 @@ struct WorldParams {
     int *gb0, *gb1;           // [W*Cc]
     int *nContacts, *posIters, *velIters;   // [W]
     unsigned long long *stats;   // [0] contacts [1] pos iters [2] vel iters [3] checks [4] max contacts [5] status
+    // RL-style episodes: world w is restored from `snap` at the start of every frame where
+    // (phase0[w] + step - episodeStep0) % episodeLen == 0
+    int episodeLen;
+    long long episodeStep0;
+    const int *phase0;
+    BodyStore snap;
 };
+CZD bool episode_wraps(const WorldParams &p, int w, long long step) {
+    return p.episodeLen > 0 && (p.phase0[w] + (step - p.episodeStep0)) % p.episodeLen == 0;
+}
 enum { ST_CONTACTS = 0, ST_POS = 1, ST_VEL = 2, ST_CHECKS = 3, ST_MAXC = 4, ST_STATUS = 5, ST_N = 8 };
 
 CZD int cz_popc(unsigned v) {
@@ -105,6 +114,17 @@ __global__ void __launch_bounds__(256, 2) k_integrate(BodyStore s, real dt, real
             st_m34(s, C_X01, i, m34_mul_m34(tr, off));
         }
     }
+}
+
+// Episode reset (multi-kernel path): restore the bodies of every world whose phase wraps.
+__global__ void k_episode_reset(WorldParams p) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= p.st.n) return;
+    int w = (int)(i / p.B);
+    if (!episode_wraps(p, w, p.step_index)) return;
+#pragma unroll 4
+    for (int k = 0; k < czb::N_CHUNKS; k++) p.st.st(k, i, p.snap.ld(k, i));
+    p.st.awake[i] = p.snap.awake[i];
 }
 
 // CalculateDerivedData for n bodies + collider transforms (upload with derive=1, and the
@@ -328,7 +348,7 @@ __global__ void __launch_bounds__(256) k_narrow(WorldParams p, int tiles, int *t
         if (slot < p.Cc) store_gen(gen, gs, gb0, gb1, slot, e.gc);
     } else {
         ColliderView c = load_collider(p.st, base + e.cubeLocal, e.cubeLocal);
-#pragma unroll
+#pragma unroll 1
         for (int v = 0; v < 8; v++) {
             if (e.mask & (1u << v)) {
                 GenContact gc;
@@ -366,9 +386,11 @@ __global__ void __launch_bounds__(256) k_scan_tiles(WorldParams p, int tiles, co
 // Work records live in dynamic shared memory when they fit (useSmem), otherwise in the global
 // scratch `gscratch` (L2-resident for the sizes involved).
 // --------------------------------------------------------------------------------------
+// contact work reals per contact in k_resolve's staging: 18 cold + pen, ddv, fric, rest
+#define CW_NREAL (czr::CW_NCOLD + 4)
 struct ResolveScratch {
     real *bw;   // [W][BW_NF*B]
-    real *cw;   // [W][CW_NF*Cc]
+    real *cw;   // [W][CW_NREAL*Cc]
     int *cb;    // [W][2*Cc]
 };
 
@@ -411,24 +433,31 @@ __global__ void __launch_bounds__(NT) k_resolve(WorldParams p, ResolveScratch rs
         return;
     }
     Ctx x;
-    x.bs = p.B; x.cs = p.Cc; x.nC = nC; x.dt = dt; x.store = p.st; x.body_base = (long long)w * p.B;
+    x.bs = p.B; x.nC = nC; x.dt = dt; x.store = p.st; x.body_base = (long long)w * p.B;
     x.xb = nullptr; x.xbs = 0;
+    real *cwbase;
     if (useSmem) {
         x.bw = (real *)smem_raw;
-        x.cw = x.bw + BW_NF * p.B;
-        x.cb0 = (int *)(x.cw + CW_NF * p.Cc);
-        x.cb1 = x.cb0 + p.Cc;
+        cwbase = x.bw + BW_NF * p.B;
+        x.cb0 = (int *)(cwbase + CW_NREAL * p.Cc);
     } else {
         x.bw = rs.bw + (long long)w * BW_NF * p.B;
-        x.cw = rs.cw + (long long)w * CW_NF * p.Cc;
+        cwbase = rs.cw + (long long)w * CW_NREAL * p.Cc;
         x.cb0 = rs.cb + (long long)w * 2 * p.Cc;
-        x.cb1 = x.cb0 + p.Cc;
     }
+    x.cb1 = x.cb0 + p.Cc;
+    x.cold = cwbase; x.cfs = p.Cc; x.ccs = 1;                 // SoA
+    x.pen = cwbase + (size_t)CW_NCOLD * p.Cc; x.ddv = x.pen + p.Cc; x.fric = x.ddv + p.Cc; x.rest = x.fric + p.Cc;
     for (int b = tid; b < p.B; b += NT) load_body_work(x, p.st, x.body_base + b, b);
     __syncthreads();
     const long long gstride = (long long)p.W * p.Cc;
-    for (int c = tid; c < nC; c += NT)
-        prepare_contact(x, c, p.gen + (long long)w * p.Cc, (int)gstride, p.gb0 + (long long)w * p.Cc, p.gb1 + (long long)w * p.Cc);
+    GenView g;
+    g.pn = p.gen + (long long)w * p.Cc; g.fs = (int)gstride; g.cs = 1;
+    g.pen = p.gen + G_PEN * gstride + (long long)w * p.Cc;
+    g.fric = p.gen + G_FRIC * gstride + (long long)w * p.Cc;
+    g.rest = p.gen + G_REST * gstride + (long long)w * p.Cc;
+    g.b0 = p.gb0 + (long long)w * p.Cc; g.b1 = p.gb1 + (long long)w * p.Cc;
+    for (int c = tid; c < nC; c += NT) prepare_contact(x, c, g);
     __syncthreads();
     int maxIter = maxIterOverride >= 0 ? maxIterOverride : nC * 8;   // cubedrop.go:73
     int status = 0;
@@ -456,7 +485,7 @@ __global__ void k_contacts_writeback(WorldParams p, ResolveScratch rs) {
     long long gs = (long long)p.W * p.Cc;
 #pragma unroll
     for (int k = 0; k < 3; k++) p.gen[(G_NORMAL + k) * gs + c] = rs.cw[(CW_N + k) * p.Cc + c];
-    p.gen[G_PEN * gs + c] = rs.cw[CW_PEN * p.Cc + c];
+    p.gen[G_PEN * gs + c] = rs.cw[CW_NCOLD * p.Cc + c];
     p.gb0[c] = rs.cb[c];
     p.gb1[c] = rs.cb[p.Cc + c];
 }

@@ -27,6 +27,13 @@ __host__ __device__ __forceinline__ real2 make_real2(real a, real b) { return ma
 // arithmetic on the CPU (test infrastructure only; the product library never calls them on
 // the host).
 #define CZD __host__ __device__ __forceinline__
+// Out-of-line on the device: every inlined IEEE division / square root is ~20 SASS instructions
+// plus a slow-path stub, and the fused world kernel is instruction-cache bound (see profiles/).
+#ifdef __CUDA_ARCH__
+#define CZD_OUTLINE __device__ __noinline__
+#else
+#define CZD_OUTLINE __host__ __device__ __forceinline__
+#endif
 #define R_(x) ((real)(x))
 
 namespace czm {
@@ -38,7 +45,7 @@ namespace czm {
 // math/math.go:91-98: RealAbs / RealSqrt go through float64 and round back; for IEEE types
 // that is the same value as the native op (sqrt: 53 >= 2*24+2 bits).
 CZD real rabs(real a) { return (real)fabs((double)a); }
-CZD real rsqrt_(real a) {
+CZD_OUTLINE real rsqrt_(real a) {
 #ifdef __CUDA_ARCH__
 #ifdef CUBEZ_REAL_FLOAT
     return __fsqrt_rn(a);
@@ -49,7 +56,7 @@ CZD real rsqrt_(real a) {
     return (real)sqrt((double)a);
 #endif
 }
-CZD real rdiv(real a, real b) {
+CZD_OUTLINE real rdiv(real a, real b) {
 #ifdef __CUDA_ARCH__
 #ifdef CUBEZ_REAL_FLOAT
     return __fdiv_rn(a, b);
@@ -69,7 +76,7 @@ CZD real real_inf() {
 }
 
 // math/math.go:64-78
-CZD bool real_equal(real a, real b) {
+CZD_OUTLINE bool real_equal(real a, real b) {
     if (a == b) return true;
     real diff = rabs(a - b);
     if (a * b == R_(0) || diff < CZ_MIN_NORMAL) {

@@ -9,9 +9,11 @@
 // commits; (3) every thread propagates the change to the contacts it owns, in the
 // reference's (b, d) order.  Iteration caps are per phase.
 //
-// Staging: per world a "body work record" bw[field*bs + body] (28 reals) and a "contact work
-// record" cw[field*cs + contact] (22 reals) — in shared memory for small worlds, in an
-// L2-resident global scratch for large ones; the code only sees pointers and strides.
+// Staging: per world a "body work record" bw[field*bs + body] (28 reals) and a contact work
+// record split into hot fields (penetration, desired delta-v, body ids: scanned every
+// iteration — shared memory) and cold fields (18 reals: only the winner and its neighbours
+// are touched — shared memory when it fits, else an L2-resident global scratch).  The code
+// only sees pointers and strides.
 #pragma once
 #include "cz_body.cuh"
 #include "cz_narrow.cuh"
@@ -20,23 +22,38 @@ namespace czr {
 using namespace czm;
 
 enum BodyWork : int { BW_POS = 0, BW_Q = 3, BW_VEL = 7, BW_ROT = 10, BW_LACC = 13, BW_IITW = 16, BW_INVM = 25, BW_MOTION = 26, BW_AWAKE = 27, BW_NF = 28 };
-enum ContactWork : int { CW_N = 0, CW_TY = 3, CW_TZ = 6, CW_RP0 = 9, CW_RP1 = 12, CW_CV = 15, CW_DDV = 18, CW_PEN = 19, CW_FRIC = 20, CW_REST = 21, CW_NF = 22 };
+// Contact work record.  "Cold" fields (read only for the winner and for the contacts that
+// share a body with it): normal, the two tangents, the two relative positions, the contact
+// velocity.  "Hot" fields (scanned by every arg-max): penetration, desiredDeltaVelocity, body ids.
+enum ContactCold : int { CW_N = 0, CW_TY = 3, CW_TZ = 6, CW_RP0 = 9, CW_RP1 = 12, CW_CV = 15, CW_NCOLD = 18 };
+// as-generated contact: point and normal live in cold slots 0..5 until prepare overwrites them
 enum GenField : int { G_POINT = 0, G_NORMAL = 3, G_PEN = 6, G_FRIC = 7, G_REST = 8, G_NF = 9 };
 
 struct Ctx {
-    real *bw; int bs;           // body work record, field stride
-    real *cw; int cs;           // contact work record, field stride
+    real *bw; int bs;           // body work record bw[field*bs + body]
+    real *cold;                 // cold contact fields: cold[field*cfs + contact*ccs]
+    int cfs, ccs;               //   SoA: cfs = capacity, ccs = 1;  AoS: cfs = 1, ccs = CW_NCOLD
+    real *pen, *ddv;            // hot: Penetration, desiredDeltaVelocity  [contact]
+    real *fric, *rest;          // per-contact Friction / Restitution, or NULL: the constants 0.9 / 0.1
     int *cb0, *cb1;             // contact body indices (world-local, -1 = nil)
     int nC;
     real dt;
     // The rare "resolved body is asleep" path (contact.go:380-382) reads the body-space inverse
     // inertia and rewrites transform + world inertia.  xb != NULL: staged copy
-    // xb[(XB_IITB+k)*xbs + b], xb[(XB_TR+k)*xbs + b] (fused kernel); else the global store.
+    // xb[(XB_IITB+k)*xbs + b], xb[(XB_TR+k)*xbs + b]; else the global store.
     real *xb; int xbs;
     czb::BodyStore store;
     int64_t body_base;          // global index of the world's body 0 in `store`
 };
 enum ExtraBody : int { XB_IITB = 0, XB_TR = 9, XB_NF = 21 };
+
+// as-generated contacts handed to prepare_contact (may alias the cold record, see above)
+struct GenView {
+    real *pn; int fs, cs;       // point/normal: pn[(G_POINT+k)*fs + c*cs]
+    real *pen;                  // [contact]
+    real *fric, *rest;          // [contact] or NULL (0.9 / 0.1)
+    int *b0, *b1;
+};
 
 CZD V3 bw3(const Ctx &x, int f, int b) { return mk3(x.bw[(f + 0) * x.bs + b], x.bw[(f + 1) * x.bs + b], x.bw[(f + 2) * x.bs + b]); }
 CZD void bw3_set(const Ctx &x, int f, int b, const V3 &v) { x.bw[(f + 0) * x.bs + b] = v.c[0]; x.bw[(f + 1) * x.bs + b] = v.c[1]; x.bw[(f + 2) * x.bs + b] = v.c[2]; }
@@ -49,8 +66,16 @@ CZD Q4 bw_q(const Ctx &x, int b) { Q4 q;
     for (int k = 0; k < 4; k++) q.c[k] = x.bw[(BW_Q + k) * x.bs + b];
     return q; }
 CZD bool bw_awake(const Ctx &x, int b) { return x.bw[BW_AWAKE * x.bs + b] != R_(0); }
-CZD V3 cw3(const Ctx &x, int f, int c) { return mk3(x.cw[(f + 0) * x.cs + c], x.cw[(f + 1) * x.cs + c], x.cw[(f + 2) * x.cs + c]); }
-CZD void cw3_set(const Ctx &x, int f, int c, const V3 &v) { x.cw[(f + 0) * x.cs + c] = v.c[0]; x.cw[(f + 1) * x.cs + c] = v.c[1]; x.cw[(f + 2) * x.cs + c] = v.c[2]; }
+CZD V3 cw3(const Ctx &x, int f, int c) {
+    const real *p = x.cold + (size_t)f * x.cfs + (size_t)c * x.ccs;
+    return mk3(p[0], p[x.cfs], p[2 * x.cfs]);
+}
+CZD void cw3_set(const Ctx &x, int f, int c, const V3 &v) {
+    real *p = x.cold + (size_t)f * x.cfs + (size_t)c * x.ccs;
+    p[0] = v.c[0]; p[x.cfs] = v.c[1]; p[2 * x.cfs] = v.c[2];
+}
+CZD real ctx_friction(const Ctx &x, int c) { return x.fric ? x.fric[c] : R_(0.9); }
+CZD real ctx_restitution(const Ctx &x, int c) { return x.rest ? x.rest[c] : R_(0.1); }
 
 // contact.go:87-112
 CZD real desired_delta_velocity(const Ctx &x, int b0, int b1, const V3 &n, real cvx, real restitution) {
@@ -84,14 +109,14 @@ CZD V3 local_velocity(const Ctx &x, int b, const V3 &rp, const V3 &n, const V3 &
     return cv;
 }
 
-// contact.go:59-85 + :118-156 for contact c; gen = as-generated contact fields (stride gs).
-CZD void prepare_contact(const Ctx &x, int c, const real *gen, int gs, const int *gb0, const int *gb1) {
-    int b0 = gb0[c], b1 = gb1[c];
-    V3 n = mk3(gen[(G_NORMAL + 0) * gs + c], gen[(G_NORMAL + 1) * gs + c], gen[(G_NORMAL + 2) * gs + c]);
-    V3 point = mk3(gen[(G_POINT + 0) * gs + c], gen[(G_POINT + 1) * gs + c], gen[(G_POINT + 2) * gs + c]);
-    // all as-generated fields are read before anything is written: the fused kernel aliases
-    // `gen` with the first fields of `cw` (same contact column)
-    const real restitution = gen[G_REST * gs + c], friction = gen[G_FRIC * gs + c], pen0 = gen[G_PEN * gs + c];
+// contact.go:59-85 + :118-156 for contact c.  All as-generated fields are read before anything
+// is written: `g` may alias the cold record (same contact column).
+CZD void prepare_contact(const Ctx &x, int c, const GenView &g) {
+    int b0 = g.b0[c], b1 = g.b1[c];
+    const real *gp = g.pn + (size_t)c * g.cs;
+    V3 point = mk3(gp[(G_POINT + 0) * g.fs], gp[(G_POINT + 1) * g.fs], gp[(G_POINT + 2) * g.fs]);
+    V3 n = mk3(gp[(G_NORMAL + 0) * g.fs], gp[(G_NORMAL + 1) * g.fs], gp[(G_NORMAL + 2) * g.fs]);
+    const real restitution = g.rest ? g.rest[c] : R_(0.1), friction = g.fric ? g.fric[c] : R_(0.9), pen0 = g.pen[c];
     if (b0 < 0) {   // :61-65
         v_mul(n, R_(-1.0));
         b0 = b1;
@@ -125,10 +150,10 @@ CZD void prepare_contact(const Ctx &x, int c, const real *gen, int gs, const int
     x.cb0[c] = b0; x.cb1[c] = b1;
     cw3_set(x, CW_N, c, n); cw3_set(x, CW_TY, c, ty); cw3_set(x, CW_TZ, c, tz);
     cw3_set(x, CW_RP0, c, rp0); cw3_set(x, CW_RP1, c, rp1); cw3_set(x, CW_CV, c, cv);
-    x.cw[CW_DDV * x.cs + c] = ddv;
-    x.cw[CW_PEN * x.cs + c] = pen0;
-    x.cw[CW_FRIC * x.cs + c] = friction;
-    x.cw[CW_REST * x.cs + c] = restitution;
+    x.ddv[c] = ddv;
+    x.pen[c] = pen0;
+    if (x.fric) x.fric[c] = friction;
+    if (x.rest) x.rest[c] = restitution;
 }
 
 CZD void cz_syncwarp(unsigned mask) {
@@ -254,7 +279,7 @@ CZD void propagate_position(const Ctx &x, int c, const Change &ch) {
     int cb[2] = {x.cb0[c], x.cb1[c]};
     if (cb[0] != ch.b[0] && cb[0] != ch.b[1] && cb[1] != ch.b[0] && (cb[1] != ch.b[1] || cb[1] < 0)) return;
     V3 n = cw3(x, CW_N, c);
-    real pen = x.cw[CW_PEN * x.cs + c];
+    real pen = x.pen[c];
 #pragma unroll
     for (int b = 0; b < 2; b++) {
         if (cb[b] < 0) continue;
@@ -269,7 +294,7 @@ CZD void propagate_position(const Ctx &x, int c, const Change &ch) {
             }
         }
     }
-    x.cw[CW_PEN * x.cs + c] = pen;
+    x.pen[c] = pen;
 }
 
 // contact.go:448-494 (+ :498-606) for the winner `c`.
@@ -278,8 +303,8 @@ CZD void resolve_velocity(const Ctx &x, int c, bool commit, Change &ch, int *sta
     V3 n = cw3(x, CW_N, c), ty = cw3(x, CW_TY, c), tz = cw3(x, CW_TZ, c);
     V3 rp[2] = {cw3(x, CW_RP0, c), cw3(x, CW_RP1, c)};
     V3 cv = cw3(x, CW_CV, c);
-    real ddv = x.cw[CW_DDV * x.cs + c];
-    real friction = x.cw[CW_FRIC * x.cs + c];
+    real ddv = x.ddv[c];
+    real friction = ctx_friction(x, c);
     bool awake0 = bw_awake(x, b[0]), awake1 = b[1] >= 0 ? bw_awake(x, b[1]) : false;
     int wake = match_awake(awake0, awake1, b[1]);   // :409
     M3 iit[2];
@@ -383,8 +408,8 @@ CZD void propagate_velocity(const Ctx &x, int c, const Change &ch) {
     if (cb[0] != ch.b[0] && cb[0] != ch.b[1] && cb[1] != ch.b[0] && (cb[1] != ch.b[1] || cb[1] < 0)) return;
     V3 n = cw3(x, CW_N, c), ty = cw3(x, CW_TY, c), tz = cw3(x, CW_TZ, c);
     V3 cv = cw3(x, CW_CV, c);
-    real restitution = x.cw[CW_REST * x.cs + c];
-    real ddv = x.cw[CW_DDV * x.cs + c];
+    real restitution = ctx_restitution(x, c);
+    real ddv;
 #pragma unroll
     for (int b = 0; b < 2; b++) {
         if (cb[b] < 0) continue;
@@ -405,7 +430,7 @@ CZD void propagate_velocity(const Ctx &x, int c, const Change &ch) {
     }
     ddv = desired_delta_velocity(x, cb[0], cb[1], n, cv.c[0], restitution);
     cw3_set(x, CW_CV, c, cv);
-    x.cw[CW_DDV * x.cs + c] = ddv;
+    x.ddv[c] = ddv;
 }
 
 // Arg-max of (value, index): larger value wins, equal values -> lower index (the reference's
@@ -453,14 +478,14 @@ template <int NT> __device__ __forceinline__ void group_sync(unsigned mask) {
 template <int NT, bool VELOCITY>
 __device__ __forceinline__ int resolve_loop(const Ctx &x, int maxIterations, GroupScratch *gs, int tid, int *status) {
     const int lane = tid & 31, warp = tid >> 5;
-    const int field = VELOCITY ? CW_DDV : CW_PEN;
+    const real *hot = VELOCITY ? x.ddv : x.pen;
     const unsigned mask = group_mask<NT>();
     int used = 0;
     while (used < maxIterations) {
         real best = R_(0.01);   // positionEpsilon / velocityEpsilon (contact.go:12-13)
         int idx = 0x7fffffff;
         for (int c = tid; c < x.nC; c += NT) {
-            real v = x.cw[field * x.cs + c];
+            real v = hot[c];
             if (v > best) { best = v; idx = c; }
         }
         warp_argmax<(NT < 32 ? NT : 32)>(best, idx, mask);

@@ -174,9 +174,16 @@ static int upload_bodies(Batch &b, long long first, long long n, const cz_bodies
     if ((rc = put_field(b, F_LACC, first, n, s->last_frame_acceleration))) return rc;
     if ((rc = put_u8(b, b.st.awake, first, n, s->is_awake))) return rc;
     if ((rc = put_u8(b, b.st.can_sleep, first, n, s->can_sleep))) return rc;
-    if (s->linear_damping) std::memcpy(b.h_lind.data() + first, s->linear_damping, sizeof(real) * n);
-    if (s->angular_damping) std::memcpy(b.h_angd.data() + first, s->angular_damping, sizeof(real) * n);
-    if (s->linear_damping || s->angular_damping) b.pow_dt = (real)NAN;   // Pow factors are stale
+    bool dampingChanged = false;
+    if (s->linear_damping && std::memcmp(b.h_lind.data() + first, s->linear_damping, sizeof(real) * n) != 0) {
+        std::memcpy(b.h_lind.data() + first, s->linear_damping, sizeof(real) * n);
+        dampingChanged = true;
+    }
+    if (s->angular_damping && std::memcmp(b.h_angd.data() + first, s->angular_damping, sizeof(real) * n) != 0) {
+        std::memcpy(b.h_angd.data() + first, s->angular_damping, sizeof(real) * n);
+        dampingChanged = true;
+    }
+    if (dampingChanged) b.pow_dt = (real)NAN;   // Pow factors are stale
     return CZ_OK;
 }
 static int download_bodies(Batch &b, long long first, long long n, cz_bodies *s) {
@@ -242,7 +249,13 @@ struct cz_world {
     int resolveSmem = 0;        // dynamic shared bytes when staged in smem, 0 = global scratch
     bool useFused = false;
     czf::FusedPlan fused{};
+    unsigned int *d_next = nullptr;   // dynamic world counter of the fused kernel
     real bias = (real)NAN;
+    // episodes
+    int episodeLen = 0;
+    long long episodeStep0 = 0;
+    int *d_phase0 = nullptr;
+    Batch snap;
     unsigned long long *h_stats = nullptr;   // pinned
     // pinned staging for cz_world_step_host
     real *h_pin = nullptr;
@@ -261,6 +274,7 @@ static WorldParams world_params(cz_world *w) {
     p.gen = w->gen; p.gb0 = w->gb0; p.gb1 = w->gb1;
     p.nContacts = w->nContacts; p.posIters = w->posIters; p.velIters = w->velIters;
     p.stats = w->stats;
+    p.episodeLen = w->episodeLen; p.episodeStep0 = w->episodeStep0; p.phase0 = w->d_phase0; p.snap = w->snap.st;
     return p;
 }
 
@@ -284,7 +298,7 @@ static int world_plan(cz_world *w) {
         CK(ctx, cudaMalloc(&w->hitCount, (size_t)W * w->nchk));
     }
     // resolver staging
-    size_t need = sizeof(real) * ((size_t)czr::BW_NF * B + (size_t)czr::CW_NF * Cc) + sizeof(int) * 2 * (size_t)Cc;
+    size_t need = sizeof(real) * ((size_t)czr::BW_NF * B + (size_t)CW_NREAL * Cc) + sizeof(int) * 2 * (size_t)Cc;
     w->resolveNT = Cc <= 128 ? 32 : 256;
     size_t limit = ctx->smem_optin > 2048 ? ctx->smem_optin - 2048 : 0;
     if (need <= limit) {
@@ -293,17 +307,20 @@ static int world_plan(cz_world *w) {
         w->resolveSmem = 0;
         if (!w->rs.bw) {
             CK(ctx, cudaMalloc(&w->rs.bw, sizeof(real) * (size_t)W * czr::BW_NF * B));
-            CK(ctx, cudaMalloc(&w->rs.cw, sizeof(real) * (size_t)W * czr::CW_NF * Cc));
+            CK(ctx, cudaMalloc(&w->rs.cw, sizeof(real) * (size_t)W * CW_NREAL * Cc));
             CK(ctx, cudaMalloc(&w->rs.cb, sizeof(int) * (size_t)W * 2 * Cc));
         }
     }
     // fused small-world kernel
     w->useFused = false;
     if (!(w->d.flags & CZ_WORLD_NO_FUSED)) {
-        w->useFused = czf::plan(w->fused, B, w->P, Cc, w->nchk, w->d.schedule, ctx->smem_optin);
+        if (w->fused.cold) { cudaFree(w->fused.cold); w->fused.cold = nullptr; }
+        w->useFused = czf::plan(w->fused, B, w->P, Cc, w->nchk, w->d.schedule, ctx->smem_optin, ctx->sm_count);
+        if (w->useFused) {
+            CK(ctx, cudaMalloc(&w->fused.cold, sizeof(real) * w->fused.coldReals * (size_t)w->fused.grid * w->fused.groupsPerBlock));
+            if (!w->d_next) CK(ctx, cudaMalloc(&w->d_next, sizeof(unsigned int)));
+        }
     }
-    if ((w->d.flags & CZ_WORLD_FUSED) && !w->useFused)
-        return fail(ctx, CZ_ERR_INVALID, "CZ_WORLD_FUSED requested but the world does not fit the fused kernel");
     return CZ_OK;
 }
 
@@ -399,8 +416,10 @@ int cz_world_destroy(cz_world *w) {
     cudaSetDevice(w->ctx->device);
     cudaStreamSynchronize(w->ctx->stream);
     batch_free(w->b);
+    if (w->snap.st.base) batch_free(w->snap);
+    if (w->d_phase0) cudaFree(w->d_phase0);
     void *ptrs[] = {w->d_one, w->d_two, w->gen, w->gb0, w->gb1, w->nContacts, w->posIters, w->velIters, w->stats,
-                    w->tileCount, w->tileBase, w->hitCount, w->rs.bw, w->rs.cw, w->rs.cb};
+                    w->tileCount, w->tileBase, w->hitCount, w->rs.bw, w->rs.cw, w->rs.cb, w->fused.cold, w->d_next};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (w->h_stats) cudaFreeHost(w->h_stats);
     if (w->h_pin) cudaFreeHost(w->h_pin);
@@ -483,6 +502,10 @@ int cz_world_set_pow(cz_world *w, cz_real dt, const cz_real *lin_pow, const cz_r
     int rc;
     if ((rc = put_field(w->b, F_LINPOW, 0, w->b.n, lin_pow))) return rc;
     if ((rc = put_field(w->b, F_ANGPOW, 0, w->b.n, ang_pow))) return rc;
+    if (w->snap.st.base) {
+        if ((rc = put_field(w->snap, F_LINPOW, 0, w->b.n, lin_pow))) return rc;
+        if ((rc = put_field(w->snap, F_ANGPOW, 0, w->b.n, ang_pow))) return rc;
+    }
     w->b.pow_dt = dt;
     w->b.pow_user = true;
     w->bias = bias;
@@ -491,6 +514,33 @@ int cz_world_set_pow(cz_world *w, cz_real dt, const cz_real *lin_pow, const cz_r
 int cz_world_set_step_index(cz_world *w, int64_t s) {
     if (!w) return CZ_ERR_INVALID;
     w->step_index = s;
+    return CZ_OK;
+}
+int cz_world_set_episodes(cz_world *w, int32_t length, const int32_t *phase0) {
+    if (!w) return CZ_ERR_INVALID;
+    cz_ctx *ctx = w->ctx;
+    CK(ctx, cudaSetDevice(ctx->device));
+    if (length <= 0) { w->episodeLen = 0; return CZ_OK; }
+    const int W = w->d.n_worlds;
+    if (phase0) for (int i = 0; i < W; i++) if (phase0[i] < 0 || phase0[i] >= length) return fail(ctx, CZ_ERR_INVALID, "phase0 out of range");
+    if (!w->snap.st.base) {
+        int rc = batch_alloc(ctx, w->snap, w->b.n);
+        if (rc) return rc;
+    }
+    if (!w->d_phase0) CK(ctx, cudaMalloc(&w->d_phase0, sizeof(int) * W));
+    if (phase0) CK(ctx, cudaMemcpyAsync(w->d_phase0, phase0, sizeof(int) * W, cudaMemcpyHostToDevice, ctx->stream));
+    else CK(ctx, cudaMemsetAsync(w->d_phase0, 0, sizeof(int) * W, ctx->stream));
+    const long long stride = w->b.st.stride;
+    CK(ctx, cudaMemcpyAsync(w->snap.st.base, w->b.st.base, sizeof(real2) * stride * czb::N_CHUNKS, cudaMemcpyDeviceToDevice, ctx->stream));
+    CK(ctx, cudaMemcpyAsync(w->snap.st.awake, w->b.st.awake, stride, cudaMemcpyDeviceToDevice, ctx->stream));
+    CK(ctx, cudaMemcpyAsync(w->snap.st.can_sleep, w->b.st.can_sleep, stride, cudaMemcpyDeviceToDevice, ctx->stream));
+    CK(ctx, cudaMemcpyAsync(w->snap.st.integ, w->b.st.integ, stride, cudaMemcpyDeviceToDevice, ctx->stream));
+    CK(ctx, cudaMemcpyAsync(w->snap.st.shape, w->b.st.shape, stride, cudaMemcpyDeviceToDevice, ctx->stream));
+    CK(ctx, cudaMemcpyAsync(w->snap.st.ident, w->b.st.ident, stride, cudaMemcpyDeviceToDevice, ctx->stream));
+    CK(ctx, cudaMemcpyAsync(w->snap.st.active_from, w->b.st.active_from, sizeof(int32_t) * stride, cudaMemcpyDeviceToDevice, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    w->episodeLen = length;
+    w->episodeStep0 = w->step_index;
     return CZ_OK;
 }
 int cz_world_synchronize(cz_world *w) {
@@ -515,6 +565,11 @@ static int world_step_multi(cz_world *w, real dt, long long &launches) {
     WorldParams p = world_params(w);
     const long long NB = w->b.n;
     int grid = (int)std::min<long long>(nblk(NB, 256), (long long)ctx->sm_count * 8);
+    if (w->episodeLen > 0) {
+        k_episode_reset<<<nblk(NB, 256), 256, 0, ctx->stream>>>(p);
+        CKL(ctx);
+        launches++;
+    }
     k_integrate<true><<<grid, 256, 0, ctx->stream>>>(w->b.st, dt, w->bias, w->step_index);
     CKL(ctx);
     launches++;
@@ -544,6 +599,10 @@ static int world_prepare_step(cz_world *w, real dt) {
     if (!(w->b.pow_dt == dt)) {   // also true when pow_dt is NaN
         int rc = refresh_pow(w->b, 0, w->b.n, dt);
         if (rc) return rc;
+        if (w->snap.st.base) {   // the episode snapshot carries the Pow factors too
+            w->snap.h_lind = w->b.h_lind; w->snap.h_angd = w->b.h_angd;
+            if ((rc = refresh_pow(w->snap, 0, w->snap.n, dt))) return rc;
+        }
         w->b.pow_dt = dt;
         w->b.pow_user = false;
         w->bias = (real)std::pow(0.5, (double)dt);   // rigidbody.go:250
@@ -580,6 +639,8 @@ int cz_world_step(cz_world *w, cz_real dt, int32_t n_steps, cz_step_stats *stats
     if (!w || n_steps < 0) return fail(nullptr, CZ_ERR_INVALID, "cz_world_step: bad argument");
     cz_ctx *ctx = w->ctx;
     CK(ctx, cudaSetDevice(ctx->device));
+    if ((w->d.flags & CZ_WORLD_FUSED) && !w->useFused)
+        return fail(ctx, CZ_ERR_INVALID, "CZ_WORLD_FUSED requested but the world does not fit the fused kernel");
     int rc = world_prepare_step(w, dt);
     if (rc) return rc;
     long long launches = 0;
@@ -589,7 +650,7 @@ int cz_world_step(cz_world *w, cz_real dt, int32_t n_steps, cz_step_stats *stats
     }
     if (w->useFused) {
         WorldParams p = world_params(w);
-        rc = czf::launch(w->fused, p, dt, w->bias, n_steps, ctx->stream, ctx->sm_count);
+        rc = czf::launch(w->fused, p, dt, w->bias, n_steps, w->d_next, ctx->stream);
         if (rc) return fail(ctx, CZ_ERR_CUDA, std::string("fused launch: ") + cudaGetErrorString((cudaError_t)rc));
         launches++;
         w->step_index += n_steps;
@@ -860,7 +921,7 @@ int cz_resolve_contacts(cz_ctx *ctx, int32_t max_iterations, cz_contacts *io, cz
         cudaMemcpy(w->nContacts, &nC, sizeof(int), cudaMemcpyHostToDevice);
         if (!w->rs.bw) {
             cudaMalloc(&w->rs.bw, sizeof(real) * czr::BW_NF * bodies->n);
-            cudaMalloc(&w->rs.cw, sizeof(real) * czr::CW_NF * nC);
+            cudaMalloc(&w->rs.cw, sizeof(real) * CW_NREAL * nC);
             cudaMalloc(&w->rs.cb, sizeof(int) * 2 * nC);
         }
         WorldParams p = world_params(w);

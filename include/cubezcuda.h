@@ -229,6 +229,10 @@ int cz_world_set_activation(cz_world *w, int32_t first_world, int32_t n_worlds, 
 /* Override the Pow factors (rigidbody.go:233,234,250) for duration dt with host-language values. */
 int cz_world_set_pow(cz_world *w, cz_real dt, const cz_real *lin_pow, const cz_real *ang_pow, cz_real bias);
 int cz_world_set_step_index(cz_world *w, int64_t step_index);
+/* RL-style episodes (new API): snapshot the current device state as the episode start; world k
+ * is at frame phase0[k] (0 <= phase0[k] < length) of its episode now and is restored to the
+ * snapshot at the start of every frame on which its phase wraps to 0.  length <= 0 disables. */
+int cz_world_set_episodes(cz_world *w, int32_t length, const int32_t *phase0);
 /* n_steps frames of updateCallback (examples/cubedrop.go:69-75). Asynchronous unless stats != NULL. */
 int cz_world_step(cz_world *w, cz_real dt, int32_t n_steps, cz_step_stats *stats);
 int cz_world_synchronize(cz_world *w);

@@ -872,6 +872,12 @@ template <class R> struct World {
     int schedule = SCHED_ALL_PAIRS_ORDERED;
     std::vector<int32_t> checkOne, checkTwo; // explicit schedule; >=0 collider index, <0 plane -(p+1)
     int64_t stepIndex = 0;
+    // RL-style episodes (no reference counterpart): restore `episodeStart` whenever the
+    // world's phase wraps to 0
+    int episodeLength = 0, episodePhase0 = 0;
+    int64_t episodeStep0 = 0;
+    std::vector<Body<R>> episodeBodies;
+    std::vector<Collider<R>> episodeColliders;
     // outputs of the last step
     std::vector<ContactRecord<R>> lastContacts;
     int posIters = 0, velIters = 0, status = 0;
@@ -882,6 +888,10 @@ template <class R> struct World {
 
     void step(R dt) {
         const int n = (int)bodies.size();
+        if (episodeLength > 0 && (episodePhase0 + (stepIndex - episodeStep0)) % episodeLength == 0) {
+            bodies = episodeBodies;
+            colliders = episodeColliders;
+        }
         fix_pointers();
         // updateObjects — cubedrop.go:29-39 / ballistic.go:27-44
         for (int i = 0; i < n; i++) {

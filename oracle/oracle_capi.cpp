@@ -297,6 +297,18 @@ int czo_world_set_activation(void *h, int32_t first, int32_t n, const int32_t *a
         }
     return 0;
 }
+int czo_world_set_episodes(void *h, int32_t length, const int32_t *phase0) {
+    OracleWorlds *w = (OracleWorlds *)h;
+    for (size_t i = 0; i < w->worlds.size(); i++) {
+        World<R> &wd = w->worlds[i];
+        wd.episodeLength = length;
+        wd.episodePhase0 = phase0 ? phase0[i] : 0;
+        wd.episodeStep0 = wd.stepIndex;
+        wd.episodeBodies = wd.bodies;
+        wd.episodeColliders = wd.colliders;
+    }
+    return 0;
+}
 int czo_world_set_step_index(void *h, int64_t s) { for (auto &wd : ((OracleWorlds *)h)->worlds) wd.stepIndex = s; return 0; }
 
 // n_threads > 1 partitions the worlds over std::threads (worlds are independent).

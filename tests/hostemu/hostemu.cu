@@ -41,13 +41,13 @@ void get(HostStore &h, int first, int comps, real *dst, long long n) {
 }
 
 template <bool VELOCITY> int host_loop(const Ctx &x, int maxIter, int *status) {
-    const int field = VELOCITY ? CW_DDV : CW_PEN;
+    const real *hot = VELOCITY ? x.ddv : x.pen;
     int used = 0;
     while (used < maxIter) {
         real best = R_(0.01);
         int idx = 0x7fffffff;
         for (int c = 0; c < x.nC; c++) {
-            real v = x.cw[field * x.cs + c];
+            real v = hot[c];
             if (v > best) { best = v; idx = c; }
         }
         if (idx == 0x7fffffff) break;
@@ -101,7 +101,7 @@ int cze_run(cz_bodies *io, const cz_colliders *col, const cz_planes *planes, int
     p.schedule = schedule; p.chk_one = one; p.chk_two = two;
     p.nchk = schedule == CZ_SCHED_ALL_PAIRS_ORDERED ? B * (p.P + B) : n_checks;
     for (int i = 0; i < p.P; i++) { p.planes[i].n = mk3(planes->normal[i * 3], planes->normal[i * 3 + 1], planes->normal[i * 3 + 2]); p.planes[i].offset = planes->offset[i]; }
-    std::vector<real> gen((size_t)G_NF * contact_cap), bw((size_t)BW_NF * B), cw((size_t)CW_NF * contact_cap);
+    std::vector<real> gen((size_t)G_NF * contact_cap), bw((size_t)BW_NF * B), cw((size_t)CW_NREAL * contact_cap);
     std::vector<int> gb0(contact_cap), gb1(contact_cap), cb(2 * (size_t)contact_cap);
     int lastC = 0;
     for (int s = 0; s < n_steps; s++) {
@@ -168,10 +168,17 @@ int cze_run(cz_bodies *io, const cz_colliders *col, const cz_planes *planes, int
         // K4
         if (nC > 0) {
             Ctx x;
-            x.bw = bw.data(); x.bs = B; x.cw = cw.data(); x.cs = contact_cap; x.cb0 = cb.data(); x.cb1 = cb.data() + contact_cap;
+            x.bw = bw.data(); x.bs = B; x.cb0 = cb.data(); x.cb1 = cb.data() + contact_cap;
+            // cold fields laid out AoS here (the fused kernel's layout); k_resolve uses SoA
+            x.cold = cw.data(); x.cfs = 1; x.ccs = CW_NCOLD;
+            x.pen = cw.data() + (size_t)CW_NCOLD * contact_cap; x.ddv = x.pen + contact_cap; x.fric = x.ddv + contact_cap; x.rest = x.fric + contact_cap;
             x.nC = nC; x.dt = dt; x.xb = nullptr; x.xbs = 0; x.store = h.st; x.body_base = 0;
+            GenView g;
+            g.pn = gen.data(); g.fs = contact_cap; g.cs = 1; g.pen = gen.data() + (size_t)G_PEN * contact_cap;
+            g.fric = gen.data() + (size_t)G_FRIC * contact_cap; g.rest = gen.data() + (size_t)G_REST * contact_cap;
+            g.b0 = gb0.data(); g.b1 = gb1.data();
             for (int b = 0; b < B; b++) load_body_work(x, h.st, b, b);
-            for (int c = 0; c < nC; c++) prepare_contact(x, c, gen.data(), contact_cap, gb0.data(), gb1.data());
+            for (int c = 0; c < nC; c++) prepare_contact(x, c, g);
             int status = 0;
             out_pos[s] = host_loop<false>(x, nC * 8, &status);
             out_vel[s] = host_loop<true>(x, nC * 8, &status);

@@ -45,6 +45,7 @@ def load(prec: str = "f64") -> C.CDLL:
         "czo_world_upload_schedule": ([VP, C.c_int32, P32, P32], C.c_int),
         "czo_world_set_activation": ([VP, C.c_int32, C.c_int32, P32, PU8], C.c_int),
         "czo_world_set_step_index": ([VP, C.c_int64], C.c_int),
+        "czo_world_set_episodes": ([VP, C.c_int32, P32], C.c_int),
         "czo_world_step": ([VP, R, C.c_int32, C.c_int32, C.POINTER(CzStepStats)], C.c_int),
         "czo_world_download_bodies": ([VP, C.c_int32, C.c_int32, PB], C.c_int),
         "czo_world_download_colliders": ([VP, C.c_int32, C.c_int32, PC], C.c_int),
@@ -171,6 +172,10 @@ class OracleWorld:
 
     def set_step_index(self, s: int):
         self.lib.czo_world_set_step_index(self.h, s)
+
+    def set_episodes(self, length: int, phase0=None):
+        ph = np.zeros(self.n_worlds, dtype=np.int32) if phase0 is None else np.ascontiguousarray(phase0, dtype=np.int32)
+        self.lib.czo_world_set_episodes(self.h, length, ph.ctypes.data_as(C.POINTER(C.c_int32)))
 
     def step(self, dt, n_steps: int = 1, n_threads: int = 1) -> dict:
         st = CzStepStats()

@@ -1,0 +1,174 @@
+"""GPU: the batched-world handle vs golden fixtures and vs the oracle — contact sets
+(pair sequence, counts) bit-exact per step, state bit-exact, on both the multi-kernel path
+and the fused small-world kernel, f64 and f32."""
+import os
+
+import numpy as np
+import pytest
+
+import hostemu_lib as he
+from cubez_b200 import _abi, scenes
+from golden_cases import CASES, STATE_FIELDS, check_against_golden, load_golden
+from oracle_lib import OracleWorld
+
+pytestmark = pytest.mark.gpu
+PATHS = {"multi": (_abi.WORLD_NO_FUSED, None), "fused32": (_abi.WORLD_FUSED, "32"), "fused16": (_abi.WORLD_FUSED, "16"),
+         "fused8": (_abi.WORLD_FUSED, "8")}
+
+
+def make_world(scene, path, **kw):
+    from cubez_b200.api import BatchedWorld
+    flags, g = PATHS[path]
+    if g:
+        os.environ["CUBEZ_FUSED_G"] = g
+    try:
+        return BatchedWorld.from_scene(scene, flags=flags, **kw)
+    finally:
+        os.environ.pop("CUBEZ_FUSED_G", None)
+
+
+@pytest.mark.parametrize("path", sorted(PATHS))
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_world_matches_golden(name, path):
+    make, n = CASES[name]
+    scene = make()
+    w = make_world(scene, path)
+    check_against_golden(w, scene, load_golden(name), n, he.pair_hash)
+    w.close()
+
+
+@pytest.mark.parametrize("path", ["multi", "fused8"])
+def test_cubedrop_600_steps_vs_oracle(path):
+    """cfg1 full length: contact sets compared every step for all 600 steps."""
+    scene = scenes.cubedrop()
+    gpu, cpu = make_world(scene, path), OracleWorld.from_scene(scene)
+    for s in range(600):
+        gpu.step(scene.dt, 1); cpu.step(scene.dt, 1)
+        assert gpu.contact_pairs(0) == cpu.contact_pairs(0), s
+        if s % 50 == 0:
+            gc, cc = gpu.contacts(0), cpu.contacts(0)
+            for f in ("point", "normal", "penetration"):
+                assert np.array_equal(gc.valid(f), cc.valid(f)), (s, f)
+    g, c = gpu.download(), cpu.download()
+    for f in STATE_FIELDS + ("transform", "inverse_inertia_tensor_world", "last_frame_acceleration"):
+        assert np.array_equal(getattr(g, f), getattr(c, f)), f
+    assert not g.is_awake.any()            # everything has gone to sleep
+    gpu.close()
+
+
+@pytest.mark.parametrize("path", ["multi", "fused32"])
+def test_ballistic_full_600_steps_vs_oracle(path):
+    """cfg2: 64 bullets spawned over time, explicit 4 226-check schedule, static backboard."""
+    scene = scenes.ballistic()
+    gpu, cpu = make_world(scene, path), OracleWorld.from_scene(scene)
+    for s in range(0, 600, 4):
+        gs, cs = gpu.step(scene.dt, 4), cpu.step(scene.dt, 4)
+        assert gs["contacts"] == cs["contacts"] and gs["vel_iterations"] == cs["vel_iterations"] and gs["pos_iterations"] == cs["pos_iterations"], s
+        assert gpu.contact_pairs(0) == cpu.contact_pairs(0), s
+    g, c = gpu.download(), cpu.download()
+    for f in STATE_FIELDS:
+        assert np.array_equal(getattr(g, f), getattr(c, f)), f
+    assert gpu.checksum_energy()[0] == cpu.checksum_energy()[0]
+    gpu.close()
+
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+def test_batched_worlds_multi_step_calls_and_checksum(prec):
+    """cfg4 shape (512 worlds): n_steps per call, parity on every world, checksum equality, and
+    shard invariance (two half-size handles == one full handle)."""
+    p = _abi.precision(prec)
+    scene = scenes.batched_cubedrop(p, n_worlds=512)
+    gpu, cpu = make_world(scene, "fused8"), OracleWorld.from_scene(scene)
+    for s in range(0, 240, 40):
+        gs, cs = gpu.step(scene.dt, 40), cpu.step(scene.dt, 40, n_threads=8)
+        for k in ("contacts", "pos_iterations", "vel_iterations", "max_contacts"):
+            assert gs[k] == cs[k], (s, k, gs[k], cs[k])
+        gc, cc = gpu.last_counts(), cpu.last_counts()
+        for a, b in zip(gc, cc):
+            assert np.array_equal(a, b)
+    g, c = gpu.download(), cpu.download()
+    for f in STATE_FIELDS:
+        assert np.array_equal(getattr(g, f), getattr(c, f)), f
+    total = gpu.checksum_energy()
+    assert total[0] == cpu.checksum_energy()[0]
+    assert abs(total[1] - cpu.checksum_energy()[1]) <= 1e-9 * abs(total[1])
+    gpu.close()
+    # shards
+    acc = 0
+    for first in (0, 256):
+        sh = scenes.batched_cubedrop(p, n_worlds=256, first_world=first)
+        w = make_world(sh, "fused8")
+        w.step(sh.dt, 240, stats=False)
+        acc = (acc + w.checksum_energy()[0]) % (1 << 64)
+        w.close()
+    assert acc == total[0]
+
+
+def test_pile_small_all_pairs_multi_tile():
+    """cfg3 shape at 6x6x6 = 216 bodies: 46 872 checks per step -> multi-tile count/scan/emit
+    narrowphase and the CTA-wide resolver with global scratch."""
+    scene = scenes.pile(side=6)
+    gpu, cpu = make_world(scene, "multi"), OracleWorld.from_scene(scene)
+    for s in range(0, 120, 10):
+        gs, cs = gpu.step(scene.dt, 10), cpu.step(scene.dt, 10)
+        assert gs["contacts"] == cs["contacts"] and gs["pos_iterations"] == cs["pos_iterations"] and gs["vel_iterations"] == cs["vel_iterations"], s
+        assert gpu.contact_pairs(0) == cpu.contact_pairs(0), s
+    g, c = gpu.download(), cpu.download()
+    for f in STATE_FIELDS:
+        assert np.array_equal(getattr(g, f), getattr(c, f)), f
+    gpu.close()
+
+
+def test_contact_capacity_overflow_is_an_error():
+    from cubez_b200._abi import CubezError
+    scene = scenes.cubedrop()
+    for path in ("multi", "fused8"):
+        w = make_world(scene, path, contacts_per_world=16)
+        with pytest.raises(CubezError) as e:
+            w.step(scene.dt, 200)
+        assert e.value.code == _abi.CZ_ERR_CAPACITY
+        w.close()
+
+
+def test_upload_download_roundtrip_and_step_host():
+    """cz_world_step_host (host buffers in/out) == device-resident stepping."""
+    scene = scenes.batched_cubedrop(n_worlds=64)
+    a, b = make_world(scene, "fused8"), make_world(scene, "fused8")
+    host = a.download()
+    for s in range(100):
+        a.step_host(host, scene.dt, 1)
+        b.step(scene.dt, 1, stats=False)
+    ref = b.download()
+    for f in STATE_FIELDS + ("transform", "inverse_inertia_tensor_world", "last_frame_acceleration"):
+        assert np.array_equal(getattr(host, f), getattr(ref, f)), f
+    a.close(); b.close()
+
+
+def test_set_pow_override_matches_default():
+    scene = scenes.cubedrop()
+    a, b = make_world(scene, "multi"), make_world(scene, "multi")
+    dt = scene.dt
+    lp = np.power(scene.bodies.linear_damping.astype(np.float64), dt)
+    ap = np.power(scene.bodies.angular_damping.astype(np.float64), dt)
+    a.set_pow(dt, lp, ap, 0.5 ** dt)
+    a.step(dt, 100); b.step(dt, 100)
+    assert a.checksum_energy()[0] == b.checksum_energy()[0]
+    a.close(); b.close()
+
+
+@pytest.mark.parametrize("path", ["multi", "fused8", "fused32"])
+def test_episode_reset_staggered_phases(path):
+    """RL-style episodes: worlds at staggered phases, restored to the snapshot on wrap."""
+    scene = scenes.batched_cubedrop(n_worlds=24)
+    gpu, cpu = make_world(scene, path), OracleWorld.from_scene(scene)
+    L = 130
+    phase0 = (np.arange(24) * 7) % L
+    gpu.set_episodes(L, phase0); cpu.set_episodes(L, phase0)
+    for s in range(0, 300, 25):
+        gs, cs = gpu.step(scene.dt, 25), cpu.step(scene.dt, 25)
+        for k in ("contacts", "pos_iterations", "vel_iterations"):
+            assert gs[k] == cs[k], (s, k)
+    g, c = gpu.download(), cpu.download()
+    for f in STATE_FIELDS:
+        assert np.array_equal(getattr(g, f), getattr(c, f)), f
+    gpu.close()
