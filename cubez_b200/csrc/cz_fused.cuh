@@ -51,10 +51,11 @@ struct FusedPlan {
     size_t coldReals;    // per group
 };
 
-static inline size_t world_bytes(int B, int Cc) {
+static inline size_t world_bytes(int B, int Cc, int nchk) {
     size_t reals = (size_t)FB_NF * B + 2 * (size_t)Cc;
     size_t ints = 2 * (size_t)Cc + 2 * (size_t)B;
-    size_t bytes = reals * sizeof(real) + ints * sizeof(int);
+    size_t shorts = 2 * (size_t)nchk;          // per-check info + the queue of checks that need a full pair test
+    size_t bytes = reals * sizeof(real) + ints * sizeof(int) + shorts * sizeof(unsigned short) + (size_t)nchk;
     return (bytes + 15) / 16 * 16;
 }
 
@@ -66,8 +67,8 @@ static inline int env_int(const char *name, int dflt) {
 // Decide whether (and how) a world shape runs on the fused kernel.
 static inline bool plan(FusedPlan &fp, int B, int P, int Cc, int nchk, int schedule, size_t smemOptin, int smCount) {
     (void)P; (void)schedule;
-    if (B > 64 || nchk > 8192 || nchk <= 0) return false;
-    const size_t wb = world_bytes(B, Cc);
+    if (B > 64 || nchk > 1024 || nchk <= 0) return false;
+    const size_t wb = world_bytes(B, Cc, nchk);
     const size_t perSM = 227 * 1024;
     if (wb > smemOptin) return false;
     int G = B <= 8 ? 8 : (B <= 16 ? 16 : 32);
@@ -98,7 +99,7 @@ static inline bool plan(FusedPlan &fp, int B, int P, int Cc, int nchk, int sched
     fp.smemBytes = smem;
     fp.keepContacts = env_int("CUBEZ_FUSED_KEEP_CONTACTS", 1);
     fp.lockstep = env_int("CUBEZ_FUSED_LOCKSTEP", 1);
-    fp.coldReals = (size_t)Cc * czr::CW_NCOLD;
+    fp.coldReals = (size_t)Cc * czr::CW_NCOLD + (size_t)nchk * 8;   // + staging of pair-test contacts
     fp.cold = nullptr;
     return true;
 }
@@ -110,6 +111,9 @@ struct Staged {
     int *cb0, *cb1;       // [Cc]
     int *flags, *active;  // [B]
     real *cold;           // global scratch, AoS [contact][CW_NCOLD]
+    real *pairGen;        // global scratch: contact of queued pair test q, [q][8]
+    unsigned short *info, *queue;   // [nchk] per-check vertex mask / queue slot; queue of check ids
+    unsigned char *cnt;   // [nchk] contacts produced by check k
 };
 
 __device__ __forceinline__ ColliderView staged_collider(const Staged &s, int i) {
@@ -205,7 +209,7 @@ __global__ void __launch_bounds__(128, MINB) k_world_fused(WorldParams p, FusedP
     using namespace czr;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int grp = threadIdx.x / G, tid = threadIdx.x % G;
-    const unsigned mask = group_mask<G>();
+    const unsigned mask = 0xffffffffu;   // all collectives are warp-wide with width G: the groups of a warp stay converged
     const int B = p.B, Cc = p.Cc;
     Staged s;
     unsigned char *base = smem_raw + (size_t)grp * fp.worldBytes;
@@ -216,7 +220,11 @@ __global__ void __launch_bounds__(128, MINB) k_world_fused(WorldParams p, FusedP
     s.cb1 = s.cb0 + Cc;
     s.flags = s.cb1 + Cc;
     s.active = s.flags + B;
+    s.info = (unsigned short *)(s.active + B);
+    s.queue = s.info + p.nchk;
+    s.cnt = (unsigned char *)(s.queue + p.nchk);
     s.cold = fp.cold + ((size_t)blockIdx.x * fp.groupsPerBlock + grp) * fp.coldReals;
+    s.pairGen = s.cold + (size_t)Cc * CW_NCOLD;
     const BodyStore &st = p.st;
 
     Ctx x;
@@ -239,7 +247,7 @@ __global__ void __launch_bounds__(128, MINB) k_world_fused(WorldParams p, FusedP
         const bool live = wu < (unsigned)p.W;
         if (LOCKSTEP) {
             if (!__syncthreads_or(live ? 1 : 0)) break;     // every group of the CTA is out of worlds
-        } else if (!live) {
+        } else if (!__any_sync(mask, live ? 1 : 0)) {
             break;
         }
         const int w = live ? (int)wu : 0;
@@ -258,8 +266,8 @@ __global__ void __launch_bounds__(128, MINB) k_world_fused(WorldParams p, FusedP
 #pragma unroll
                     for (int k = czb::C_L2T0; k <= czb::C_T11W0; k++) st.st(k, gbase + b, p.snap.ld(k, gbase + b));
                 }
-                __syncwarp(mask);
             }
+            __syncwarp(mask);   // (warp-wide collectives only at warp-uniform points)
             // ---- updateObjects: Integrate + collider derive (cubedrop.go:29-39) ---------
             for (int b = live ? tid : B; b < B; b += G) {
                 const int fl = s.flags[b];
@@ -304,34 +312,117 @@ __global__ void __launch_bounds__(128, MINB) k_world_fused(WorldParams p, FusedP
             __syncwarp(mask);
             if (LOCKSTEP) __syncthreads();
 
-            // ---- generateContacts with order-preserving compaction ---------------------------
-            int nC = 0;
-            for (int k0 = live ? 0 : p.nchk; k0 < p.nchk; k0 += G) {
+            // ---- generateContacts (cubedrop.go:42-67), three passes --------------------------------
+            // A: every check gets its cheap test: plane checks are evaluated (vertex mask), pair
+            //    checks that survive the bounding-sphere rejection are queued.  B: the queued pair
+            //    tests (15-axis SAT etc.) run densely, one per lane — in a spread scene only a few
+            //    of the all-pairs checks reach this pass, and running them in place left ~3 of 32
+            //    lanes busy.  C: order-preserving emission in check order (the reference's append
+            //    order): prefix scan of the per-check contact counts.
+            int nQ = 0;
+            const unsigned gshift = (threadIdx.x & 31u) & ~(unsigned)(G - 1);
+            const unsigned gbits = G == 32 ? 0xffffffffu : ((1u << G) - 1u);
+            for (int k0 = 0; k0 < p.nchk; k0 += G) {
                 const int k = k0 + tid;
-                CheckEval e;
-                e.count = 0; e.kind = 0; e.mask = 0;
+                bool need = false;
+                if (live && k < p.nchk) {
+                    int a = 0, b2 = 0;
+                    unsigned cnt = 0, info = 0;
+                    if (decode_check(p, k, a, b2) && !(a < 0 && b2 < 0) && (a < 0 || staged_active(s, a, step)) && (b2 < 0 || staged_active(s, b2, step))) {
+                        if (a < 0 || b2 < 0) {
+                            const int ci = a < 0 ? b2 : a, pi = a < 0 ? -a - 1 : -b2 - 1;
+                            ColliderView c = staged_collider(s, ci);
+                            if (c.shape == CZ_SHAPE_SPHERE) {
+                                GenContact gc;
+                                cnt = czn::sphere_halfspace(c, p.planes[pi], gc) ? 1u : 0u;
+                            } else if (c.shape == CZ_SHAPE_CUBE) {
+                                info = czn::cube_halfspace_mask(c, p.planes[pi]);
+                                cnt = (unsigned)cz_popc(info);
+                            }
+                        } else {
+                            // bounding-sphere rejection needs only the centres and sizes
+                            ColliderView one, two;
+                            one.shape = s.flags[a] & FF_SHAPE_MASK; two.shape = s.flags[b2] & FF_SHAPE_MASK;
+#pragma unroll
+                            for (int j = 0; j < 3; j++) {
+                                one.t.c[9 + j] = s.fb[(FB_CTR + 9 + j) * B + a]; two.t.c[9 + j] = s.fb[(FB_CTR + 9 + j) * B + b2];
+                                one.half.c[j] = s.fb[(FB_HALF + j) * B + a]; two.half.c[j] = s.fb[(FB_HALF + j) * B + b2];
+                            }
+                            one.radius = s.fb[FB_RADIUS * B + a]; two.radius = s.fb[FB_RADIUS * B + b2];
+                            need = !czn::bounding_reject(one, two);
+                        }
+                    }
+                    s.cnt[k] = (unsigned char)cnt;
+                    s.info[k] = (unsigned short)info;
+                }
+                const unsigned ball = (__ballot_sync(mask, need) >> gshift) & gbits;
+                if (need) s.queue[nQ + __popc(ball & ((1u << tid) - 1u))] = (unsigned short)k;
+                nQ += __popc(ball);
+            }
+            __syncwarp(mask);
+            for (int q = tid; q < nQ; q += G) {   // pass B: dense pair tests
+                const int k = s.queue[q];
                 int a = 0, b2 = 0;
-                if (k < p.nchk && decode_check(p, k, a, b2)) eval_check_staged(p, s, step, a, b2, e);
-                int incl = e.count;
+                decode_check(p, k, a, b2);
+                ColliderView one = staged_collider(s, a), two = staged_collider(s, b2);
+                V3 v1 = zero3(), v2 = zero3();
+                if (one.shape != two.shape) { v1 = bw3(x, BW_VEL, a); v2 = bw3(x, BW_VEL, b2); }
+                GenContact gc;
+                const bool hit = czn::check_pair(one, two, v1, v2, gc);
+                s.cnt[k] = hit ? 1 : 0;
+                s.info[k] = (unsigned short)q;
+                if (hit) {
+                    real *r = s.pairGen + (size_t)q * 8;
+#pragma unroll
+                    for (int j = 0; j < 3; j++) { r[j] = gc.point.c[j]; r[3 + j] = gc.normal.c[j]; }
+                    r[6] = gc.pen;
+                    r[7] = (real)(gc.b0 * 128 + (gc.b1 + 1));   // bodies (one,two) may be swapped by the test
+                }
+            }
+            __syncwarp(mask);
+            int nC = 0;
+            for (int k0 = 0; k0 < p.nchk; k0 += G) {   // pass C: ordered emission (uniform trip count: warp-wide scan)
+                const int k = k0 + tid;
+                const int cnt = (live && k < p.nchk) ? (int)s.cnt[k] : 0;
+                int incl = cnt;
 #pragma unroll
                 for (int o = 1; o < G; o <<= 1) {
                     int t = __shfl_up_sync(mask, incl, o, G);
                     if (tid >= o) incl += t;
                 }
                 const int total = __shfl_sync(mask, incl, G - 1, G);
-                int slot = nC + incl - e.count;
-                if (e.kind == 1) {
-                    if (slot < Cc) stage_gen(s, slot, e.gc);
-                } else if (e.kind == 2) {
-                    ColliderView c = staged_collider(s, e.cubeLocal);
-#pragma unroll 1
-                    for (int v = 0; v < 8; v++) {
-                        if (e.mask & (1u << v)) {
+                int slot = nC + incl - cnt;
+                if (cnt > 0) {
+                    int a = 0, b2 = 0;
+                    decode_check(p, k, a, b2);
+                    if (a < 0 || b2 < 0) {
+                        const int ci = a < 0 ? b2 : a, pi = a < 0 ? -a - 1 : -b2 - 1;
+                        ColliderView c = staged_collider(s, ci);
+                        if (c.shape == CZ_SHAPE_SPHERE) {
                             GenContact gc;
-                            czn::cube_halfspace_contact(c, p.planes[e.plane], v, gc);
+                            czn::sphere_halfspace(c, p.planes[pi], gc);
                             if (slot < Cc) stage_gen(s, slot, gc);
-                            slot++;
+                        } else {
+                            const unsigned vm = s.info[k];
+#pragma unroll 1
+                            for (int v = 0; v < 8; v++) {
+                                if (vm & (1u << v)) {
+                                    GenContact gc;
+                                    czn::cube_halfspace_contact(c, p.planes[pi], v, gc);
+                                    if (slot < Cc) stage_gen(s, slot, gc);
+                                    slot++;
+                                }
+                            }
                         }
+                    } else if (slot < Cc) {
+                        const real *r = s.pairGen + (size_t)s.info[k] * 8;
+                        GenContact gc;
+#pragma unroll
+                        for (int j = 0; j < 3; j++) { gc.point.c[j] = r[j]; gc.normal.c[j] = r[3 + j]; }
+                        gc.pen = r[6];
+                        const int code = (int)r[7];
+                        gc.b0 = code / 128; gc.b1 = code % 128 - 1;
+                        stage_gen(s, slot, gc);
                     }
                 }
                 nC += total;
@@ -356,24 +447,20 @@ __global__ void __launch_bounds__(128, MINB) k_world_fused(WorldParams p, FusedP
                     p.gb0[(long long)w * Cc + c] = s.cb0[c];
                     p.gb1[(long long)w * Cc + c] = s.cb1[c];
                 }
-                __syncwarp(mask);
             }
+            __syncwarp(mask);
             // ---- ResolveContacts(8*len) (cubedrop.go:72-74) -----------------------------------
             if (LOCKSTEP) __syncthreads();
             int st2 = 0;
-            if (nC > 0) {
-                x.nC = nC;
-                for (int c = tid; c < nC; c += G) prepare_contact(x, c, gv);
-                __syncwarp(mask);
-                lastPos = resolve_loop<G, false>(x, nC * 8, nullptr, tid, &st2);
-            }
+            x.nC = nC;
+            for (int c = tid; c < nC; c += G) prepare_contact(x, c, gv);
+            __syncwarp(mask);
+            lastPos = resolve_loop<G, false>(x, nC > 0, nC * 8, tid, &st2);
             if (LOCKSTEP) __syncthreads();
-            if (nC > 0) {
-                lastVel = resolve_loop<G, true>(x, nC * 8, nullptr, tid, &st2);
-                if (st2) status = st2;
-                accPos += (unsigned long long)lastPos;
-                accVel += (unsigned long long)lastVel;
-            }
+            lastVel = resolve_loop<G, true>(x, nC > 0, nC * 8, tid, &st2);
+            if (st2) status = st2;
+            accPos += (unsigned long long)lastPos;
+            accVel += (unsigned long long)lastVel;
             __syncwarp(mask);
         }
 

@@ -461,9 +461,16 @@ __global__ void __launch_bounds__(NT) k_resolve(WorldParams p, ResolveScratch rs
     __syncthreads();
     int maxIter = maxIterOverride >= 0 ? maxIterOverride : nC * 8;   // cubedrop.go:73
     int status = 0;
-    int pi = resolve_loop<NT, false>(x, maxIter, &gs, tid, &status);
-    __syncthreads();
-    int vi = resolve_loop<NT, true>(x, maxIter, &gs, tid, &status);
+    int pi, vi;
+    if (NT == 32) {
+        pi = resolve_loop<32, false>(x, true, maxIter, tid, &status);
+        __syncthreads();
+        vi = resolve_loop<32, true>(x, true, maxIter, tid, &status);
+    } else {
+        pi = resolve_loop_cta<(NT > 32 ? NT : 64), false>(x, maxIter, &gs, tid, &status);
+        __syncthreads();
+        vi = resolve_loop_cta<(NT > 32 ? NT : 64), true>(x, maxIter, &gs, tid, &status);
+    }
     __syncthreads();
     for (int b = tid; b < p.B; b += NT) store_body_work(x, p.st, x.body_base + b, b);
     if (tid == 0) {

@@ -156,14 +156,6 @@ CZD void prepare_contact(const Ctx &x, int c, const GenView &g) {
     if (x.rest) x.rest[c] = restitution;
 }
 
-CZD void cz_syncwarp(unsigned mask) {
-#ifdef __CUDA_ARCH__
-    __syncwarp(mask);
-#else
-    (void)mask;
-#endif
-}
-
 // What one resolve hands to the propagation step.
 struct Change {
     V3 lin[2], ang[2];   // linearChange/angularChange (position) or velocityChange/rotationChange (velocity)
@@ -177,9 +169,20 @@ CZD int match_awake(bool a0, bool a1, int b1) {
     return -1;
 }
 
-// contact.go:286-386 for the winner `c` with penetration `penetration`.  Executed by a full
-// warp redundantly; `commit` (one lane) performs the body writes.
-CZD void resolve_position(const Ctx &x, int c, real penetration, bool commit, Change &ch, unsigned mask) {
+// What a resolve must write back to the bodies; committed by one lane after the whole group
+// has finished reading the old state.
+struct PosCommit {
+    int b[2];
+    V3 pos[2];
+    Q4 q[2];
+    bool asleep[2];   // body is (still) asleep: CalculateDerivedData() follows (contact.go:380-382)
+    int wake;         // body slot woken by matchAwakeState, or -1
+};
+
+// contact.go:286-386 for the winner `c` with penetration `penetration`.  Pure: reads the staged
+// state, returns the change (for the propagation) and the values to commit.  Executed by every
+// lane of the group redundantly (same issue cost as one lane, no divergence).
+CZD void resolve_position(const Ctx &x, int c, real penetration, Change &ch, PosCommit &pc) {
     const real angularLimit = R_(0.2);
     int b[2] = {x.cb0[c], x.cb1[c]};
     V3 n = cw3(x, CW_N, c);
@@ -187,18 +190,18 @@ CZD void resolve_position(const Ctx &x, int c, real penetration, bool commit, Ch
     bool awake[2] = {bw_awake(x, b[0]), b[1] >= 0 ? bw_awake(x, b[1]) : false};
     int wake = match_awake(awake[0], awake[1], b[1]);   // :252
     if (wake >= 0) awake[wake] = true;
+    pc.wake = wake;
     real angularInertia[2] = {R_(0), R_(0)}, linearInertia[2] = {R_(0), R_(0)}, angularMove[2], linearMove[2];
     real totalInertia = R_(0);
     M3 iit[2];
-    V3 pos[2];
-    Q4 q[2];
 #pragma unroll
     for (int i = 0; i < 2; i++) {
         ch.lin[i] = zero3(); ch.ang[i] = zero3(); ch.b[i] = b[i];
+        pc.b[i] = b[i]; pc.asleep[i] = false;
         if (b[i] < 0) continue;
         iit[i] = bw_iitw(x, b[i]);
-        pos[i] = bw3(x, BW_POS, b[i]);
-        q[i] = bw_q(x, b[i]);
+        pc.pos[i] = bw3(x, BW_POS, b[i]);
+        pc.q[i] = bw_q(x, b[i]);
         V3 aiw = v_cross(rp[i], n);
         aiw = m3_mul_v(iit[i], aiw);
         aiw = v_cross(aiw, rp[i]);
@@ -206,7 +209,6 @@ CZD void resolve_position(const Ctx &x, int c, real penetration, bool commit, Ch
         linearInertia[i] = x.bw[BW_INVM * x.bs + b[i]];
         totalInertia += linearInertia[i] + angularInertia[i];
     }
-    cz_syncwarp(mask);   // every lane has read the old body state before lane 0 overwrites it
 #pragma unroll
     for (int i = 0; i < 2; i++) {
         if (b[i] < 0) continue;
@@ -234,43 +236,48 @@ CZD void resolve_position(const Ctx &x, int c, real penetration, bool commit, Ch
         }
         ch.lin[i] = n;
         v_mul(ch.lin[i], linearMove[i]);
-        v_add_scaled(pos[i], n, linearMove[i]);
-        q_add_scaled_vector(q[i], ch.ang[i], R_(1.0));
-        q_normalize(q[i]);
-        if (!awake[i]) {
-            // contact.go:380-382: a body that is (still) asleep gets CalculateDerivedData() so
-            // the move shows up in its transform / world inertia.
+        v_add_scaled(pc.pos[i], n, linearMove[i]);
+        q_add_scaled_vector(pc.q[i], ch.ang[i], R_(1.0));
+        q_normalize(pc.q[i]);
+        pc.asleep[i] = !awake[i];
+    }
+}
+
+// The body writes of applyPositionChange (one lane).  A body that is (still) asleep gets
+// CalculateDerivedData() so the move shows up in its transform / world inertia (:380-382).
+CZD void commit_position(const Ctx &x, PosCommit &pc) {
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+        const int b = pc.b[i];
+        if (b < 0) continue;
+        if (pc.asleep[i]) {
             M3 iitBody;
             if (x.xb) {
 #pragma unroll
-                for (int k = 0; k < 9; k++) iitBody.c[k] = x.xb[(XB_IITB + k) * x.xbs + b[i]];
+                for (int k = 0; k < 9; k++) iitBody.c[k] = x.xb[(XB_IITB + k) * x.xbs + b];
             } else {
-                iitBody = czb::ld_iit_body(x.store, x.body_base + b[i]);
+                iitBody = czb::ld_iit_body(x.store, x.body_base + b);
             }
             M34 tr;
             M3 iw;
-            czb::calculate_derived(pos[i], q[i], iitBody, tr, iw);
-            if (commit) {
-                if (x.xb) {
+            czb::calculate_derived(pc.pos[i], pc.q[i], iitBody, tr, iw);
+            if (x.xb) {
 #pragma unroll
-                    for (int k = 0; k < 12; k++) x.xb[(XB_TR + k) * x.xbs + b[i]] = tr.c[k];
-                } else {
-                    real laz = x.bw[(BW_LACC + 2) * x.bs + b[i]];
-                    czb::st_derived(x.store, x.body_base + b[i], laz, tr, iw);
-                }
-#pragma unroll
-                for (int k = 0; k < 9; k++) x.bw[(BW_IITW + k) * x.bs + b[i]] = iw.c[k];
+                for (int k = 0; k < 12; k++) x.xb[(XB_TR + k) * x.xbs + b] = tr.c[k];
+            } else {
+                real laz = x.bw[(BW_LACC + 2) * x.bs + b];
+                czb::st_derived(x.store, x.body_base + b, laz, tr, iw);
             }
-        }
-        if (commit) {
-            bw3_set(x, BW_POS, b[i], pos[i]);
 #pragma unroll
-            for (int k = 0; k < 4; k++) x.bw[(BW_Q + k) * x.bs + b[i]] = q[i].c[k];
+            for (int k = 0; k < 9; k++) x.bw[(BW_IITW + k) * x.bs + b] = iw.c[k];
         }
+        bw3_set(x, BW_POS, b, pc.pos[i]);
+#pragma unroll
+        for (int k = 0; k < 4; k++) x.bw[(BW_Q + k) * x.bs + b] = pc.q[i].c[k];
     }
-    if (commit && wake >= 0) {   // SetAwake(true) rigidbody.go:183-186
-        x.bw[BW_AWAKE * x.bs + b[wake]] = R_(1);
-        x.bw[BW_MOTION * x.bs + b[wake]] = R_(0.6);
+    if (pc.wake >= 0) {   // SetAwake(true) rigidbody.go:183-186
+        x.bw[BW_AWAKE * x.bs + pc.b[pc.wake]] = R_(1);
+        x.bw[BW_MOTION * x.bs + pc.b[pc.wake]] = R_(0.6);
     }
 }
 
@@ -298,7 +305,14 @@ CZD void propagate_position(const Ctx &x, int c, const Change &ch) {
 }
 
 // contact.go:448-494 (+ :498-606) for the winner `c`.
-CZD void resolve_velocity(const Ctx &x, int c, bool commit, Change &ch, int *status, unsigned mask) {
+struct VelCommit {
+    int b[2];
+    V3 vel[2], rot[2];
+    int wake;
+    int status;
+};
+
+CZD void resolve_velocity(const Ctx &x, int c, Change &ch, VelCommit &vc) {
     int b[2] = {x.cb0[c], x.cb1[c]};
     V3 n = cw3(x, CW_N, c), ty = cw3(x, CW_TY, c), tz = cw3(x, CW_TZ, c);
     V3 rp[2] = {cw3(x, CW_RP0, c), cw3(x, CW_RP1, c)};
@@ -306,22 +320,21 @@ CZD void resolve_velocity(const Ctx &x, int c, bool commit, Change &ch, int *sta
     real ddv = x.ddv[c];
     real friction = ctx_friction(x, c);
     bool awake0 = bw_awake(x, b[0]), awake1 = b[1] >= 0 ? bw_awake(x, b[1]) : false;
-    int wake = match_awake(awake0, awake1, b[1]);   // :409
+    vc.wake = match_awake(awake0, awake1, b[1]);   // :409
+    vc.status = 0;
     M3 iit[2];
     real invMass[2] = {R_(0), R_(0)};
-    V3 vel[2], rot[2];
 #pragma unroll
     for (int i = 0; i < 2; i++) {
-        ch.lin[i] = zero3(); ch.ang[i] = zero3(); ch.b[i] = b[i];
+        ch.lin[i] = zero3(); ch.ang[i] = zero3(); ch.b[i] = b[i]; vc.b[i] = b[i];
 #pragma unroll
         for (int k = 0; k < 9; k++) iit[i].c[k] = R_(0);
         if (b[i] < 0) continue;
         iit[i] = bw_iitw(x, b[i]);
         invMass[i] = x.bw[BW_INVM * x.bs + b[i]];
-        vel[i] = bw3(x, BW_VEL, b[i]);
-        rot[i] = bw3(x, BW_ROT, b[i]);
+        vc.vel[i] = bw3(x, BW_VEL, b[i]);
+        vc.rot[i] = bw3(x, BW_ROT, b[i]);
     }
-    cz_syncwarp(mask);
     M3 c2w;   // contactToWorld, columns (n, ty, tz)  (SetComponents math/matrix.go:52)
     c2w.c[0] = n.c[0]; c2w.c[1] = n.c[1]; c2w.c[2] = n.c[2];
     c2w.c[3] = ty.c[0]; c2w.c[4] = ty.c[1]; c2w.c[5] = ty.c[2];
@@ -335,7 +348,7 @@ CZD void resolve_velocity(const Ctx &x, int c, bool commit, Change &ch, int *sta
         dvw = v_cross(dvw, rp[0]);
         real dv = v_dot(dvw, n);
         dv += invMass[0];
-        if (b[1] < 0 && commit && status) *status = CZ_ERR_NIL_BODY;
+        if (b[1] < 0) vc.status = CZ_ERR_NIL_BODY;
         ic = mk3(rdiv(ddv, dv), R_(0), R_(0));
     } else {
         // calculateFrictionImpulse :535-606
@@ -378,27 +391,29 @@ CZD void resolve_velocity(const Ctx &x, int c, bool commit, Change &ch, int *sta
     ch.ang[0] = m3_mul_v(iit[0], torque);
     ch.lin[0] = zero3();
     v_add_scaled(ch.lin[0], impulse, invMass[0]);
-    v_add(vel[0], ch.lin[0]);
-    v_add(rot[0], ch.ang[0]);
+    v_add(vc.vel[0], ch.lin[0]);
+    v_add(vc.rot[0], ch.ang[0]);
     if (b[1] >= 0) {
         torque = v_cross(impulse, rp[1]);
         ch.ang[1] = m3_mul_v(iit[1], torque);
         ch.lin[1] = zero3();
         v_add_scaled(ch.lin[1], impulse, -invMass[1]);
-        v_add(vel[1], ch.lin[1]);
-        v_add(rot[1], ch.ang[1]);
+        v_add(vc.vel[1], ch.lin[1]);
+        v_add(vc.rot[1], ch.ang[1]);
     }
-    if (commit) {
-        bw3_set(x, BW_VEL, b[0], vel[0]);
-        bw3_set(x, BW_ROT, b[0], rot[0]);
-        if (b[1] >= 0) {
-            bw3_set(x, BW_VEL, b[1], vel[1]);
-            bw3_set(x, BW_ROT, b[1], rot[1]);
-        }
-        if (wake >= 0) {
-            x.bw[BW_AWAKE * x.bs + b[wake]] = R_(1);
-            x.bw[BW_MOTION * x.bs + b[wake]] = R_(0.6);
-        }
+}
+
+// The body writes of applyVelocityChange (AddVelocity / AddRotation, contact.go:478-490) (one lane).
+CZD void commit_velocity(const Ctx &x, const VelCommit &vc) {
+    bw3_set(x, BW_VEL, vc.b[0], vc.vel[0]);
+    bw3_set(x, BW_ROT, vc.b[0], vc.rot[0]);
+    if (vc.b[1] >= 0) {
+        bw3_set(x, BW_VEL, vc.b[1], vc.vel[1]);
+        bw3_set(x, BW_ROT, vc.b[1], vc.rot[1]);
+    }
+    if (vc.wake >= 0) {
+        x.bw[BW_AWAKE * x.bs + vc.b[vc.wake]] = R_(1);
+        x.bw[BW_MOTION * x.bs + vc.b[vc.wake]] = R_(0.6);
     }
 }
 
@@ -447,17 +462,57 @@ __device__ __forceinline__ void warp_argmax(real &v, int &i, unsigned mask) {
         argmax_combine(v, i, ov, oi);
     }
 }
-// lane mask of the NT-lane group (NT <= 32) the calling thread belongs to
-template <int NT> __device__ __forceinline__ unsigned group_mask() {
-    if constexpr (NT >= 32) {
-        return 0xffffffffu;
-    } else {
-        const unsigned lane = threadIdx.x & 31u;
-        return ((1u << NT) - 1u) << (lane & ~(unsigned)(NT - 1));
+// The worst-first loop of one phase for worlds owned by (sub-)warp groups of NT <= 32 lanes.
+// Called by all 32 lanes of a warp together: the 32/NT worlds of the warp iterate in lock step
+// (a world that is done idles) so every collective uses the full-warp mask and the groups stay
+// converged — sub-warp masks make the hardware run each group's instruction stream separately.
+// `enabled` and every branch condition are uniform within a group.
+template <int NT, bool VELOCITY>
+__device__ __forceinline__ int resolve_loop(const Ctx &x, bool enabled, int maxIterations, int tid, int *status) {
+    static_assert(NT <= 32, "warp-level loop");
+    const real *hot = VELOCITY ? x.ddv : x.pen;
+    const unsigned full = 0xffffffffu;
+    bool done = !enabled || maxIterations <= 0;
+    int used = 0;
+    while (true) {
+        real best = R_(0.01);   // positionEpsilon / velocityEpsilon (contact.go:12-13)
+        int idx = 0x7fffffff;
+        if (!done) {
+            for (int c = tid; c < x.nC; c += NT) {
+                real v = hot[c];
+                if (v > best) { best = v; idx = c; }
+            }
+        }
+        warp_argmax<NT>(best, idx, full);
+        if (idx == 0x7fffffff) done = true;
+        if (__all_sync(full, done)) break;
+        Change ch;
+        PosCommit pc;
+        VelCommit vc;
+        if (!done) {
+            if (VELOCITY) resolve_velocity(x, idx, ch, vc);
+            else resolve_position(x, idx, best, ch, pc);
+        }
+        __syncwarp();   // every lane has read the old body state before one lane overwrites it
+        if (!done && tid == 0) {
+            if (VELOCITY) { commit_velocity(x, vc); if (vc.status) *status = vc.status; }
+            else commit_position(x, pc);
+        }
+        __syncwarp();
+        if (!done) {
+            for (int c = tid; c < x.nC; c += NT) {
+                if (VELOCITY) propagate_velocity(x, c, ch);
+                else propagate_position(x, c, ch);
+            }
+            used++;
+            if (used >= maxIterations) done = true;
+        }
+        __syncwarp();
     }
+    return used;
 }
 
-// Shared scratch a thread group needs for the loops.
+// Shared scratch of the CTA-wide loop.
 struct GroupScratch {
     real redv[32];
     int redi[32];
@@ -465,59 +520,52 @@ struct GroupScratch {
     int chb[2];
 };
 
-// Group-wide barrier: a (sub-)warp group only needs __syncwarp on its lanes; larger groups are
-// whole CTAs.
-template <int NT> __device__ __forceinline__ void group_sync(unsigned mask) {
-    if (NT <= 32) __syncwarp(mask); else __syncthreads();
-}
-
-// The two worst-first loops for one world.  NT = threads in the group (8/16/32: an aligned
-// sub-warp group owns the world — several worlds share a warp and run in SIMD; >32: the whole
-// CTA of NT threads owns it).  tid = thread index within the group.
-// field = CW_PEN (position phase) or CW_DDV (velocity phase).
+// The same loop for one world owned by a whole CTA of NT threads (large worlds).  Only the first
+// warp runs the scalar resolve; the change is broadcast through shared memory.
 template <int NT, bool VELOCITY>
-__device__ __forceinline__ int resolve_loop(const Ctx &x, int maxIterations, GroupScratch *gs, int tid, int *status) {
+__device__ __forceinline__ int resolve_loop_cta(const Ctx &x, int maxIterations, GroupScratch *gs, int tid, int *status) {
     const int lane = tid & 31, warp = tid >> 5;
     const real *hot = VELOCITY ? x.ddv : x.pen;
-    const unsigned mask = group_mask<NT>();
+    const unsigned full = 0xffffffffu;
     int used = 0;
     while (used < maxIterations) {
-        real best = R_(0.01);   // positionEpsilon / velocityEpsilon (contact.go:12-13)
+        real best = R_(0.01);
         int idx = 0x7fffffff;
         for (int c = tid; c < x.nC; c += NT) {
             real v = hot[c];
             if (v > best) { best = v; idx = c; }
         }
-        warp_argmax<(NT < 32 ? NT : 32)>(best, idx, mask);
-        if (NT > 32) {
-            if (lane == 0) { gs->redv[warp] = best; gs->redi[warp] = idx; }
-            __syncthreads();
-            best = lane < NT / 32 ? gs->redv[lane] : R_(0.01);
-            idx = lane < NT / 32 ? gs->redi[lane] : 0x7fffffff;
-            warp_argmax<32>(best, idx, mask);
-        }
+        warp_argmax<32>(best, idx, full);
+        if (lane == 0) { gs->redv[warp] = best; gs->redi[warp] = idx; }
+        __syncthreads();
+        best = lane < NT / 32 ? gs->redv[lane] : R_(0.01);
+        idx = lane < NT / 32 ? gs->redi[lane] : 0x7fffffff;
+        warp_argmax<32>(best, idx, full);
         if (idx == 0x7fffffff) break;
         Change ch;
-        if (NT <= 32 || warp == 0) {
-            if (VELOCITY) resolve_velocity(x, idx, tid == 0, ch, status, mask);
-            else resolve_position(x, idx, best, tid == 0, ch, mask);
-            if (NT > 32 && lane == 0) {
+        if (warp == 0) {
+            PosCommit pc;
+            VelCommit vc;
+            if (VELOCITY) resolve_velocity(x, idx, ch, vc);
+            else resolve_position(x, idx, best, ch, pc);
+            __syncwarp();
+            if (lane == 0) {
+                if (VELOCITY) { commit_velocity(x, vc); if (vc.status) *status = vc.status; }
+                else commit_position(x, pc);
 #pragma unroll
                 for (int k = 0; k < 3; k++) { gs->chg[k] = ch.lin[0].c[k]; gs->chg[3 + k] = ch.lin[1].c[k]; gs->chg[6 + k] = ch.ang[0].c[k]; gs->chg[9 + k] = ch.ang[1].c[k]; }
                 gs->chb[0] = ch.b[0]; gs->chb[1] = ch.b[1];
             }
         }
-        group_sync<NT>(mask);
-        if (NT > 32) {
+        __syncthreads();
 #pragma unroll
-            for (int k = 0; k < 3; k++) { ch.lin[0].c[k] = gs->chg[k]; ch.lin[1].c[k] = gs->chg[3 + k]; ch.ang[0].c[k] = gs->chg[6 + k]; ch.ang[1].c[k] = gs->chg[9 + k]; }
-            ch.b[0] = gs->chb[0]; ch.b[1] = gs->chb[1];
-        }
+        for (int k = 0; k < 3; k++) { ch.lin[0].c[k] = gs->chg[k]; ch.lin[1].c[k] = gs->chg[3 + k]; ch.ang[0].c[k] = gs->chg[6 + k]; ch.ang[1].c[k] = gs->chg[9 + k]; }
+        ch.b[0] = gs->chb[0]; ch.b[1] = gs->chb[1];
         for (int c = tid; c < x.nC; c += NT) {
             if (VELOCITY) propagate_velocity(x, c, ch);
             else propagate_position(x, c, ch);
         }
-        group_sync<NT>(mask);
+        __syncthreads();
         used++;
     }
     return used;

@@ -52,8 +52,16 @@ template <bool VELOCITY> int host_loop(const Ctx &x, int maxIter, int *status) {
         }
         if (idx == 0x7fffffff) break;
         Change ch;
-        if (VELOCITY) resolve_velocity(x, idx, true, ch, status, 0u);
-        else resolve_position(x, idx, best, true, ch, 0u);
+        if (VELOCITY) {
+            VelCommit vc;
+            resolve_velocity(x, idx, ch, vc);
+            commit_velocity(x, vc);
+            if (vc.status) *status = vc.status;
+        } else {
+            PosCommit pc;
+            resolve_position(x, idx, best, ch, pc);
+            commit_position(x, pc);
+        }
         for (int c = 0; c < x.nC; c++) {
             if (VELOCITY) propagate_velocity(x, c, ch);
             else propagate_position(x, c, ch);
