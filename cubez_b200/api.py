@@ -115,6 +115,27 @@ class Context:
         contacts.take(cst)
         return int(iters[0]), int(iters[1])
 
+    def pinned_bodies(self, n: int) -> Bodies:
+        """A Bodies record whose arrays live in page-locked host memory (cz_host_alloc): the
+        zero-copy views a cgo caller would get with unsafe.Slice over C-allocated buffers.  Used
+        with BatchedWorld.step_host so the H2D / D2H copies are truly asynchronous."""
+        b = Bodies.__new__(Bodies)
+        b.n, b.prec, b.a = int(n), self.prec, {}
+        isz = np.dtype(self.prec.dtype).itemsize
+        total = sum(max(1, n * max(comp, 1)) * (1 if comp == 0 else isz) + 64 for _, comp in _abi.BODY_FIELDS)
+        raw = C.c_void_p()
+        self.check(self.lib.cz_host_alloc(self.h, total, C.byref(raw)))
+        buf = (C.c_uint8 * total).from_address(raw.value)
+        b._pinned = (raw, buf)
+        off = 0
+        for name, comp in _abi.BODY_FIELDS:
+            dt = np.uint8 if comp == 0 else self.prec.dtype
+            cnt = n * max(comp, 1)
+            arr = np.frombuffer(buf, dtype=dt, count=cnt, offset=off)
+            b.a[name] = arr.reshape((n,) if comp in (0, 1) else (n, comp))
+            off += (cnt * np.dtype(dt).itemsize + 63) // 64 * 64
+        return b
+
     def bench_integrate(self, n: int, seed: int = 5, warmup: int = 3, steps: int = 100, dt: float = 1.0 / 60.0):
         ms = C.c_float()
         cks = C.c_uint64()
@@ -213,9 +234,9 @@ class BatchedWorld:
         self.ctx.check(self.lib.cz_world_synchronize(self.h))
 
     # ---- downloads -------------------------------------------------------------------
-    def download(self, first_world: int = 0, n_worlds: Optional[int] = None, fields=None) -> Bodies:
+    def download(self, first_world: int = 0, n_worlds: Optional[int] = None, fields=None, out: Optional[Bodies] = None) -> Bodies:
         n = self.n_worlds - first_world if n_worlds is None else n_worlds
-        out = Bodies(n * self.B, self.prec, fields=fields)
+        out = out if out is not None else Bodies(n * self.B, self.prec, fields=fields)
         st = out.struct()
         self.ctx.check(self.lib.cz_world_download_bodies(self.h, first_world, n, C.byref(st)))
         return out

@@ -85,7 +85,7 @@ static inline bool plan(FusedPlan &fp, int B, int P, int Cc, int nchk, int sched
     if (bps < 1) bps = 1;
     int maxByThreads = 2048 / threads;
     if (bps > maxByThreads) bps = maxByThreads;
-    int minb = env_int("CUBEZ_FUSED_MINB", 3);     // register budget: 65536 / (128 * MINB) per thread
+    int minb = env_int("CUBEZ_FUSED_MINB", 2);     // register budget: 65536 / (128 * MINB) per thread
     if (minb < 2) minb = 2;
     if (minb > 4) minb = 4;
     if (bps > minb * (128 / threads)) bps = minb * (128 / threads);
@@ -244,13 +244,13 @@ __global__ void __launch_bounds__(128, MINB) k_world_fused(WorldParams p, FusedP
         unsigned int wu = 0;
         if (tid == 0) wu = atomicAdd(nextWorld, 1u);
         wu = __shfl_sync(mask, wu, 0, G);
-        const bool live = wu < (unsigned)p.W;
+        const bool live = wu < (unsigned)p.wCount;
         if (LOCKSTEP) {
             if (!__syncthreads_or(live ? 1 : 0)) break;     // every group of the CTA is out of worlds
         } else if (!__any_sync(mask, live ? 1 : 0)) {
             break;
         }
-        const int w = live ? (int)wu : 0;
+        const int w = live ? p.wFirst + (int)wu : 0;
         const long long gbase = (long long)w * B;
         x.body_base = gbase;
         if (live) stage_world<G>(s, st, gbase, B, tid);
@@ -504,10 +504,10 @@ __global__ void __launch_bounds__(128, MINB) k_world_fused(WorldParams p, FusedP
 
 // returns 0 or a cudaError_t
 static inline int launch(const FusedPlan &fp, const WorldParams &p, real dt, real bias, int nSteps, unsigned int *nextWorld, cudaStream_t stream) {
-    cudaError_t e = cudaMemsetAsync(nextWorld, 0, sizeof(unsigned int), stream);
+    cudaError_t e = cudaMemsetAsync(nextWorld, 0, sizeof(unsigned int), stream);   // stream-ordered before the launch
     if (e != cudaSuccess) return (int)e;
     int grid = fp.grid;
-    const int needed = (p.W + fp.groupsPerBlock - 1) / fp.groupsPerBlock;
+    const int needed = (p.wCount + fp.groupsPerBlock - 1) / fp.groupsPerBlock;
     if (grid > needed) grid = needed;
 #define CZF_LAUNCH(GG, MB, LS)                                                                                        \
     do {                                                                                                            \

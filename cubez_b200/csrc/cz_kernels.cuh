@@ -19,6 +19,7 @@ using czn::PlaneView;
 struct WorldParams {
     BodyStore st;
     int W, B, P, Cc;          // worlds, bodies per world, planes, contact capacity per world
+    int wFirst, wCount;       // world range a fused launch works on (chunked host pipeline)
     int nchk;                 // checks per world
     int schedule;
     const int *chk_one, *chk_two;   // explicit schedule (shared by all worlds)
@@ -172,6 +173,55 @@ __global__ void k_unpack(const real2 *base, long long stride, long long first_bo
     int sl = first_slot + (int)(t % comps);
     dst[t] = ((const real *)(base + (long long)(sl >> 1) * stride))[2 * (first_body + i) + (sl & 1)];
 }
+// ---- one-kernel pack / unpack of the per-frame host state (cz_world_step_host) ----------------
+// Inputs: everything the host may have edited (the K1 read set); outputs: everything a frame
+// writes.  Arrays are the ABI's flat "array of small vectors", device copies of the host's.
+struct HostIn { const real *pos, *ori, *vel, *rot, *acc, *iitb, *motion; const uint8_t *awake, *can_sleep; };
+struct HostOut { real *pos, *ori, *vel, *rot, *motion, *lacc, *tr, *iitw; uint8_t *awake; };
+
+__global__ void k_pack_all(czb::BodyStore s, long long first, long long n, HostIn h) {
+    using namespace czb;
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const long long i = first + t;
+    s.st(C_P01, i, make_real2(h.pos[i * 3], h.pos[i * 3 + 1]));
+    s.st(C_P2M, i, make_real2(h.pos[i * 3 + 2], h.motion[i]));
+    s.st(C_Q01, i, make_real2(h.ori[i * 4], h.ori[i * 4 + 1]));
+    s.st(C_Q23, i, make_real2(h.ori[i * 4 + 2], h.ori[i * 4 + 3]));
+    s.st(C_V01, i, make_real2(h.vel[i * 3], h.vel[i * 3 + 1]));
+    s.st(C_V2R0, i, make_real2(h.vel[i * 3 + 2], h.rot[i * 3]));
+    s.st(C_R12, i, make_real2(h.rot[i * 3 + 1], h.rot[i * 3 + 2]));
+    s.st(C_A01, i, make_real2(h.acc[i * 3], h.acc[i * 3 + 1]));
+    s.st(C_A2LP, i, make_real2(h.acc[i * 3 + 2], s.ld(C_A2LP, i).y));        // keeps linPow
+    s.st(C_APW0, i, make_real2(s.ld(C_APW0, i).x, h.iitb[i * 9]));           // keeps angPow
+    s.st(C_I12, i, make_real2(h.iitb[i * 9 + 1], h.iitb[i * 9 + 2]));
+    s.st(C_I34, i, make_real2(h.iitb[i * 9 + 3], h.iitb[i * 9 + 4]));
+    s.st(C_I56, i, make_real2(h.iitb[i * 9 + 5], h.iitb[i * 9 + 6]));
+    s.st(C_I78, i, make_real2(h.iitb[i * 9 + 7], h.iitb[i * 9 + 8]));
+    s.awake[i] = h.awake[i];
+    s.can_sleep[i] = h.can_sleep[i];
+}
+__global__ void k_unpack_all(czb::BodyStore s, long long first, long long n, HostOut h) {
+    using namespace czb;
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const long long i = first + t;
+    V3 pos = ld_position(s, i), vel = ld_velocity(s, i), rot = ld_rotation(s, i), la = ld_last_acc(s, i);
+    Q4 q = ld_orientation(s, i);
+    M34 tr = ld_transform(s, i);
+    M3 iw = ld_iit_world(s, i);
+#pragma unroll
+    for (int k = 0; k < 3; k++) { h.pos[i * 3 + k] = pos.c[k]; h.vel[i * 3 + k] = vel.c[k]; h.rot[i * 3 + k] = rot.c[k]; h.lacc[i * 3 + k] = la.c[k]; }
+#pragma unroll
+    for (int k = 0; k < 4; k++) h.ori[i * 4 + k] = q.c[k];
+#pragma unroll
+    for (int k = 0; k < 12; k++) h.tr[i * 12 + k] = tr.c[k];
+#pragma unroll
+    for (int k = 0; k < 9; k++) h.iitw[i * 9 + k] = iw.c[k];
+    h.motion[i] = s.ld(C_P2M, i).y;
+    h.awake[i] = s.awake[i];
+}
+
 __global__ void k_fill_u8(uint8_t *p, long long n, uint8_t v) {
     long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t < n) p[t] = v;

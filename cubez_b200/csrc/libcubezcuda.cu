@@ -257,7 +257,18 @@ struct cz_world {
     int *d_phase0 = nullptr;
     Batch snap;
     unsigned long long *h_stats = nullptr;   // pinned
-    // pinned staging for cz_world_step_host
+    // chunked pipeline of cz_world_step_host: H2D | pack + step + unpack | D2H on three streams
+    struct HostPipe {
+        bool ready = false;
+        int chunks = 1;
+        cudaStream_t sUp = nullptr, sDown = nullptr, sComp2 = nullptr;   // sComp2: odd chunks, so kernel tails overlap
+        std::vector<cudaEvent_t> evUp, evComp;
+        cudaEvent_t evBegin = nullptr, evDownDone = nullptr;
+        real *dIn = nullptr, *dOut = nullptr;        // per-field device staging
+        uint8_t *dFlags = nullptr;                   // awake_in, can_sleep_in, awake_out
+        unsigned int *dNext = nullptr;               // per-chunk world counters
+        real *cold2 = nullptr;                       // second cold-contact scratch: odd chunks run concurrently with even ones
+    } pipe;
     real *h_pin = nullptr;
     size_t h_pin_bytes = 0;
 };
@@ -266,6 +277,7 @@ static WorldParams world_params(cz_world *w) {
     WorldParams p;
     p.st = w->b.st;
     p.W = w->d.n_worlds; p.B = w->d.bodies_per_world; p.P = w->P; p.Cc = w->d.contacts_per_world;
+    p.wFirst = 0; p.wCount = w->d.n_worlds;
     p.nchk = w->nchk;
     p.schedule = w->d.schedule;
     p.chk_one = w->d_one; p.chk_two = w->d_two;
@@ -423,6 +435,13 @@ int cz_world_destroy(cz_world *w) {
     for (void *p : ptrs) if (p) cudaFree(p);
     if (w->h_stats) cudaFreeHost(w->h_stats);
     if (w->h_pin) cudaFreeHost(w->h_pin);
+    if (w->pipe.ready) {
+        cudaStreamDestroy(w->pipe.sUp); cudaStreamDestroy(w->pipe.sDown); cudaStreamDestroy(w->pipe.sComp2);
+        for (auto e : w->pipe.evUp) cudaEventDestroy(e);
+        for (auto e : w->pipe.evComp) cudaEventDestroy(e);
+        cudaEventDestroy(w->pipe.evBegin); cudaEventDestroy(w->pipe.evDownDone);
+        cudaFree(w->pipe.dIn); cudaFree(w->pipe.dOut); cudaFree(w->pipe.dFlags); cudaFree(w->pipe.dNext); if (w->pipe.cold2) cudaFree(w->pipe.cold2);
+    }
     delete w;
     return CZ_OK;
 }
@@ -759,22 +778,127 @@ int cz_world_checksum_energy(cz_world *w, uint64_t *checksum, double *energy) {
     return CZ_OK;
 }
 
-// Host-buffer step: the end-to-end call of a host-resident caller.  Uploads the primary
-// state (what the host may have edited: the K1 read set), runs n_steps, downloads everything
-// Integrate/ResolveContacts write.  Pinned staging, one stream.
+// Host-buffer step: the end-to-end call of a host-resident caller.  Uploads the primary state
+// (what the host may have edited: the K1 read set), runs n_steps, downloads everything
+// Integrate/ResolveContacts write.  For worlds on the fused kernel the call is a three-stage
+// pipeline over world chunks — H2D copies | pack + frames + unpack | D2H copies — on three
+// streams, so PCIe traffic in both directions overlaps the kernels.  Host arrays should be pinned
+// (cz_host_alloc); pageable memory works but the copies then serialise in the driver.
+static int host_pipe_init(cz_world *w) {
+    cz_ctx *ctx = w->ctx;
+    auto &pp = w->pipe;
+    if (pp.ready) return CZ_OK;
+    const long long NB = w->b.n;
+    int chunks = czf::env_int("CUBEZ_HOST_CHUNKS", 8);
+    if (!w->useFused) chunks = 1;
+    if (chunks > w->d.n_worlds) chunks = w->d.n_worlds;
+    if (chunks < 1) chunks = 1;
+    pp.chunks = chunks;
+    CK(ctx, cudaStreamCreateWithFlags(&pp.sUp, cudaStreamNonBlocking));
+    CK(ctx, cudaStreamCreateWithFlags(&pp.sDown, cudaStreamNonBlocking));
+    CK(ctx, cudaStreamCreateWithFlags(&pp.sComp2, cudaStreamNonBlocking));
+    pp.evUp.resize(chunks); pp.evComp.resize(chunks);
+    for (int c = 0; c < chunks; c++) {
+        CK(ctx, cudaEventCreateWithFlags(&pp.evUp[c], cudaEventDisableTiming));
+        CK(ctx, cudaEventCreateWithFlags(&pp.evComp[c], cudaEventDisableTiming));
+    }
+    CK(ctx, cudaEventCreateWithFlags(&pp.evBegin, cudaEventDisableTiming));
+    CK(ctx, cudaEventCreateWithFlags(&pp.evDownDone, cudaEventDisableTiming));
+    CK(ctx, cudaMalloc(&pp.dIn, sizeof(real) * NB * 26));    // pos3 ori4 vel3 rot3 acc3 iitb9 motion1
+    CK(ctx, cudaMalloc(&pp.dOut, sizeof(real) * NB * 38));   // pos3 ori4 vel3 rot3 motion1 lacc3 tr12 iitw9
+    CK(ctx, cudaMalloc(&pp.dFlags, 3 * (size_t)NB));
+    CK(ctx, cudaMalloc(&pp.dNext, sizeof(unsigned int) * chunks));
+    if (w->useFused) CK(ctx, cudaMalloc(&pp.cold2, sizeof(real) * w->fused.coldReals * (size_t)w->fused.grid * w->fused.groupsPerBlock));
+    pp.ready = true;
+    return CZ_OK;
+}
+
 int cz_world_step_host(cz_world *w, cz_bodies *io, cz_real dt, int32_t n_steps, cz_step_stats *stats) {
     if (!w || !io) return CZ_ERR_INVALID;
-    if (io->n != w->b.n) return fail(w->ctx, CZ_ERR_INVALID, "cz_world_step_host: io->n must equal n_worlds*bodies_per_world");
-    cz_bodies up = *io;
-    up.transform = nullptr; up.inverse_inertia_tensor_world = nullptr; up.last_frame_acceleration = nullptr;
-    up.inverse_mass = nullptr;   // constant after setup
-    int rc = upload_bodies(w->b, 0, w->b.n, &up);
-    if (rc) return rc;
-    if ((rc = cz_world_step(w, dt, n_steps, stats))) return rc;
-    cz_bodies down = *io;
-    down.acceleration = nullptr; down.linear_damping = nullptr; down.angular_damping = nullptr;
-    down.inverse_inertia_tensor = nullptr; down.inverse_mass = nullptr; down.can_sleep = nullptr;
-    return download_bodies(w->b, 0, w->b.n, &down);
+    cz_ctx *ctx = w->ctx;
+    if (io->n != w->b.n) return fail(ctx, CZ_ERR_INVALID, "cz_world_step_host: io->n must equal n_worlds*bodies_per_world");
+    if (!io->position || !io->orientation || !io->velocity || !io->rotation || !io->acceleration || !io->inverse_inertia_tensor ||
+        !io->motion || !io->is_awake || !io->can_sleep || !io->transform || !io->inverse_inertia_tensor_world || !io->last_frame_acceleration)
+        return fail(ctx, CZ_ERR_INVALID, "cz_world_step_host: every state array must be given");
+    CK(ctx, cudaSetDevice(ctx->device));
+    if ((w->d.flags & CZ_WORLD_FUSED) && !w->useFused)
+        return fail(ctx, CZ_ERR_INVALID, "CZ_WORLD_FUSED requested but the world does not fit the fused kernel");
+    int rc;
+    // damping: only touched (and the Pow factors refreshed) when the host changed it
+    cz_bodies damp{};
+    damp.n = io->n; damp.linear_damping = io->linear_damping; damp.angular_damping = io->angular_damping;
+    bool changed = (io->linear_damping && std::memcmp(w->b.h_lind.data(), io->linear_damping, sizeof(real) * io->n) != 0) ||
+                   (io->angular_damping && std::memcmp(w->b.h_angd.data(), io->angular_damping, sizeof(real) * io->n) != 0);
+    if (changed && (rc = upload_bodies(w->b, 0, io->n, &damp))) return rc;
+    if ((rc = world_prepare_step(w, dt))) return rc;
+    if ((rc = host_pipe_init(w))) return rc;
+    auto &pp = w->pipe;
+    const long long NB = w->b.n, B = w->d.bodies_per_world;
+    const int W = w->d.n_worlds;
+    // device staging layout
+    real *dPos = pp.dIn, *dOri = dPos + NB * 3, *dVel = dOri + NB * 4, *dRot = dVel + NB * 3, *dAcc = dRot + NB * 3, *dIitb = dAcc + NB * 3, *dMot = dIitb + NB * 9;
+    real *oPos = pp.dOut, *oOri = oPos + NB * 3, *oVel = oOri + NB * 4, *oRot = oVel + NB * 3, *oMot = oRot + NB * 3, *oLacc = oMot + NB, *oTr = oLacc + NB * 3, *oIitw = oTr + NB * 12;
+    uint8_t *fAwake = pp.dFlags, *fSleep = fAwake + NB, *fAwakeOut = fSleep + NB;
+    HostIn hin{dPos, dOri, dVel, dRot, dAcc, dIitb, dMot, fAwake, fSleep};
+    HostOut hout{oPos, oOri, oVel, oRot, oMot, oLacc, oTr, oIitw, fAwakeOut};
+    CK(ctx, cudaMemsetAsync(w->stats, 0, sizeof(unsigned long long) * ST_N, ctx->stream));
+    CK(ctx, cudaMemsetAsync(pp.dNext, 0, sizeof(unsigned int) * pp.chunks, ctx->stream));
+    CK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    CK(ctx, cudaEventRecord(pp.evBegin, ctx->stream));
+    CK(ctx, cudaStreamWaitEvent(pp.sUp, pp.evBegin, 0));     // staging buffers of the previous call are free
+    CK(ctx, cudaStreamWaitEvent(pp.sDown, pp.evBegin, 0));
+    CK(ctx, cudaStreamWaitEvent(pp.sComp2, pp.evBegin, 0));
+    long long launches = 0;
+#define UP(dst, src, comps) CK(ctx, cudaMemcpyAsync((dst) + b0 * (comps), (src) + b0 * (comps), sizeof(*(src)) * nb * (comps), cudaMemcpyHostToDevice, pp.sUp))
+#define DOWN(dst, src, comps) CK(ctx, cudaMemcpyAsync((dst) + b0 * (comps), (src) + b0 * (comps), sizeof(*(src)) * nb * (comps), cudaMemcpyDeviceToHost, pp.sDown))
+    for (int c = 0; c < pp.chunks; c++) {
+        const int w0 = (int)((long long)W * c / pp.chunks), w1 = (int)((long long)W * (c + 1) / pp.chunks);
+        const long long b0 = w0 * B, nb = (w1 - w0) * B;
+        if (nb == 0) continue;
+        UP(dPos, io->position, 3); UP(dOri, io->orientation, 4); UP(dVel, io->velocity, 3); UP(dRot, io->rotation, 3);
+        UP(dAcc, io->acceleration, 3); UP(dIitb, io->inverse_inertia_tensor, 9); UP(dMot, io->motion, 1);
+        UP(fAwake, io->is_awake, 1); UP(fSleep, io->can_sleep, 1);
+        CK(ctx, cudaEventRecord(pp.evUp[c], pp.sUp));
+        cudaStream_t cs = (w->useFused && (c & 1)) ? pp.sComp2 : ctx->stream;
+        CK(ctx, cudaStreamWaitEvent(cs, pp.evUp[c], 0));
+        k_pack_all<<<nblk(nb, 256), 256, 0, cs>>>(w->b.st, b0, nb, hin);
+        CKL(ctx);
+        launches++;
+        if (w->useFused) {
+            WorldParams p = world_params(w);
+            p.wFirst = w0; p.wCount = w1 - w0;
+            czf::FusedPlan fpl = w->fused;
+            if (c & 1) fpl.cold = pp.cold2;
+            rc = czf::launch(fpl, p, dt, w->bias, n_steps, pp.dNext + c, cs);
+            if (rc) return fail(ctx, CZ_ERR_CUDA, std::string("fused launch: ") + cudaGetErrorString((cudaError_t)rc));
+            launches++;
+        } else {
+            const long long keep = w->step_index;
+            for (int s = 0; s < n_steps; s++) {
+                if ((rc = world_step_multi(w, dt, launches))) return rc;
+                w->step_index++;
+            }
+            w->step_index = keep;
+        }
+        k_unpack_all<<<nblk(nb, 256), 256, 0, cs>>>(w->b.st, b0, nb, hout);
+        CKL(ctx);
+        launches++;
+        CK(ctx, cudaEventRecord(pp.evComp[c], cs));
+        CK(ctx, cudaStreamWaitEvent(pp.sDown, pp.evComp[c], 0));
+        DOWN(io->position, oPos, 3); DOWN(io->orientation, oOri, 4); DOWN(io->velocity, oVel, 3); DOWN(io->rotation, oRot, 3);
+        DOWN(io->motion, oMot, 1); DOWN(io->last_frame_acceleration, oLacc, 3); DOWN(io->transform, oTr, 12);
+        DOWN(io->inverse_inertia_tensor_world, oIitw, 9); DOWN(io->is_awake, fAwakeOut, 1);
+    }
+#undef UP
+#undef DOWN
+    w->step_index += n_steps;
+    CK(ctx, cudaEventRecord(pp.evDownDone, pp.sDown));
+    CK(ctx, cudaStreamWaitEvent(ctx->stream, pp.evDownDone, 0));
+    CK(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+    CK(ctx, cudaEventSynchronize(ctx->ev1));
+    float ms = 0;
+    CK(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    return read_stats(w, stats, launches, n_steps, ms);
 }
 
 // ---- object-API shims ------------------------------------------------------------------------
