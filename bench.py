@@ -222,7 +222,9 @@ def main():
         ms, _ = ctx.bench_integrate(K1_BODIES, warmup=3, steps=50, dt=DT)
         ach = K1_BODIES * K1_BYTES_F64 / (ms * 1e-3) / 1e9
         roofline_k1 = {"bound": "hbm", "kernel": "k_integrate<false> (Integrate+CalculateDerivedData, cfg5: 16Mi free bodies f64)",
-                       "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_kind": peak_kind,
+                       "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                       "traffic": 8.837e9,   # dram__bytes_read+write per launch, ncu --set full (profiles/r01_k1_integrate_f64.txt); algorithmic 8.909e9
+                       "peak_kind": peak_kind,
                        "ms_per_launch": ms, "body_steps_per_s": K1_BODIES / (ms * 1e-3), "bytes_per_body": K1_BYTES_F64}
 
     if rank == 0:
