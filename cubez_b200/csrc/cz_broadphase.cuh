@@ -1,0 +1,367 @@
+// cz_broadphase.cuh — K2: sort-based broadphase replacing the reference's O(n^2) pair scan
+// (examples/cubedrop.go:54-63 "yes this is O(n^2) and not good practice").
+//
+// Pipeline per frame for one large world of n colliders:
+//   k_bp_bounds     centre (collider transform column 3) + bounding radius -> bounds[i] (4 reals),
+//                   and the axis-aligned box of all centres (block reduce + ordered atomics)
+//   k_bp_keys       uniform grid, cell edge >= 2*Rmax*(1+margin): key = linear cell id, value = i
+//   radix sort      4 x 8-bit passes (cz_sort.cuh)
+//   k_bp_gather     bounds in sorted order (so the sweep reads neighbours with locality)
+//   k_bp_cells      cellRange[key] = [first, last) of every non-empty cell
+//   k_bp_pairs      every sorted body sweeps its 27 neighbour cells, inflated inclusive sphere test,
+//                   emits each unordered candidate once (sorted position p < q), warp-ballot compaction
+//   k_bp_narrow     both ordered checks (i,j) and (j,i) of every candidate through czn::check_pair
+//   k_bp_planes     every collider against every plane (planes bypass the grid)
+//   radix sort      contacts by canonical key (check id * 8 + vertex)  == the reference's append order
+//   k_bp_emit       gather into the world's as-generated contact arrays
+// False positives are free, a dropped pair would not be: the test is inclusive and inflated by
+// BP_MARGIN, the same margin czn::bounding_reject uses.
+#pragma once
+#include "cz_kernels.cuh"
+#include "cz_sort.cuh"
+
+namespace czbp {
+using namespace czm;
+using namespace czk;
+
+struct Bounds { real x, y, z, r; };
+
+// order-preserving map double -> int64 for atomicMin/Max
+__device__ __forceinline__ long long ord(double v) {
+    long long b = __double_as_longlong(v);
+    return b >= 0 ? b : (b ^ 0x7fffffffffffffffll);
+}
+__host__ __device__ __forceinline__ double unord(long long b) {
+    long long r = b >= 0 ? b : (b ^ 0x7fffffffffffffffll);
+    double d;
+    memcpy(&d, &r, sizeof(d));
+    return d;
+}
+
+// box[0..2] = min, box[3..5] = max (ordered ints), box[6] = max radius (ordered)
+__global__ void k_bp_bounds(BodyStore s, long long n, long long step, Bounds *bounds, long long *box) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    double mn[3] = {1e300, 1e300, 1e300}, mx[3] = {-1e300, -1e300, -1e300}, rmax = 0;
+    if (i < n) {
+        Bounds b;
+        const int shape = s.shape[i];
+        const bool active = shape != CZ_SHAPE_NONE && step >= (long long)s.active_from[i];
+        real2 x89 = s.ld(czb::C_X89, i), x1011 = s.ld(czb::C_X1011, i);
+        real2 h01 = s.ld(czb::C_H01, i), h2r = s.ld(czb::C_H2R, i);
+        b.x = x89.y; b.y = x1011.x; b.z = x1011.y;
+        b.r = shape == CZ_SHAPE_SPHERE ? h2r.y : rsqrt_(h01.x * h01.x + h01.y * h01.y + h2r.x * h2r.x);
+        if (!active) b.r = R_(-1);
+        bounds[i] = b;
+        if (active) {
+            mn[0] = mx[0] = (double)b.x; mn[1] = mx[1] = (double)b.y; mn[2] = mx[2] = (double)b.z;
+            rmax = (double)b.r;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            mn[k] = fmin(mn[k], __shfl_xor_sync(0xffffffffu, mn[k], o));
+            mx[k] = fmax(mx[k], __shfl_xor_sync(0xffffffffu, mx[k], o));
+        }
+        rmax = fmax(rmax, __shfl_xor_sync(0xffffffffu, rmax, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            atomicMin(&box[k], ord(mn[k]));
+            atomicMax(&box[3 + k], ord(mx[k]));
+        }
+        atomicMax(&box[6], ord(rmax));
+    }
+}
+
+struct Grid {
+    double ox, oy, oz, inv;   // origin and 1/cell
+    int nx, ny, nz;
+};
+
+__device__ __forceinline__ void cell_of(const Grid &g, const Bounds &b, int &cx, int &cy, int &cz) {
+    cx = min(max((int)floor(((double)b.x - g.ox) * g.inv), 0), g.nx - 1);
+    cy = min(max((int)floor(((double)b.y - g.oy) * g.inv), 0), g.ny - 1);
+    cz = min(max((int)floor(((double)b.z - g.oz) * g.inv), 0), g.nz - 1);
+}
+
+__global__ void k_bp_keys(const Bounds *bounds, long long n, Grid g, unsigned *keys, unsigned *vals) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    Bounds b = bounds[i];
+    unsigned key = 0xffffffffu;   // inactive colliders sort to the end
+    if (b.r >= R_(0)) {
+        int cx, cy, cz;
+        cell_of(g, b, cx, cy, cz);
+        key = (unsigned)((cz * g.ny + cy) * g.nx + cx);
+    }
+    keys[i] = key;
+    vals[i] = (unsigned)i;
+}
+
+__global__ void k_bp_gather(const Bounds *bounds, const unsigned *vals, long long n, Bounds *sorted) {
+    long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < n) sorted[p] = bounds[vals[p]];
+}
+
+__global__ void k_bp_cells(const unsigned *keys, long long n, uint2 *cellRange) {
+    long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const unsigned k = keys[p];
+    if (k == 0xffffffffu) return;
+    if (p == 0 || keys[p - 1] != k) cellRange[k].x = (unsigned)p;
+    if (p == n - 1 || keys[p + 1] != k) cellRange[k].y = (unsigned)(p + 1);
+}
+
+#define BP_MARGIN 1.005   // on the distance (1.01 on its square), as czn::bounding_reject
+
+// candidate pairs (original collider indices, a < b by sorted position) with warp-ballot compaction
+__global__ void __launch_bounds__(256) k_bp_pairs(const Bounds *sorted, const unsigned *keys, const unsigned *vals, long long n, Grid g,
+                                                  const uint2 *cellRange, uint2 *pairs, unsigned long long *nPairs, unsigned long long capacity) {
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    Bounds me;
+    me.r = R_(-1);
+    int cx = 0, cy = 0, cz = 0;
+    const bool valid = p < n && keys[p] != 0xffffffffu;
+    if (valid) { me = sorted[p]; cell_of(g, me, cx, cy, cz); }
+    const unsigned myVal = valid ? vals[p] : 0u;
+    for (int dz = -1; dz <= 1; dz++)
+        for (int dy = -1; dy <= 1; dy++) {
+            // the three cells of a row are consecutive keys -> one contiguous range of the sorted array
+            unsigned q0 = 0, q1 = 0;
+            if (valid) {
+                const int y = cy + dy, z = cz + dz;
+                if (y >= 0 && y < g.ny && z >= 0 && z < g.nz) {
+                    bool first = true;
+                    for (int dx = -1; dx <= 1; dx++) {
+                        const int x = cx + dx;
+                        if (x < 0 || x >= g.nx) continue;
+                        const uint2 r = cellRange[(z * g.ny + y) * g.nx + x];
+                        if (r.y > r.x) { if (first) { q0 = r.x; first = false; } q1 = r.y; }
+                    }
+                }
+            }
+            // all lanes iterate to the longest range of the warp so that the ballot is warp-wide
+            unsigned len = q1 > q0 ? q1 - q0 : 0u;
+            unsigned maxLen = len;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) maxLen = max(maxLen, __shfl_xor_sync(0xffffffffu, maxLen, o));
+            for (unsigned t = 0; t < maxLen; t++) {
+                bool hit = false;
+                unsigned other = 0;
+                const unsigned q = q0 + t;
+                if (t < len && (long long)q > p) {
+                    const Bounds ob = sorted[q];
+                    const double ddx = (double)ob.x - (double)me.x, ddy = (double)ob.y - (double)me.y, ddz = (double)ob.z - (double)me.z;
+                    const double rr = ((double)ob.r + (double)me.r) * BP_MARGIN;
+                    hit = ddx * ddx + ddy * ddy + ddz * ddz <= rr * rr + 1e-9;
+                    other = vals[q];
+                }
+                const unsigned ball = __ballot_sync(0xffffffffu, hit);
+                if (ball) {
+                    unsigned long long base = 0;
+                    if (lane == 0) base = atomicAdd(nPairs, (unsigned long long)__popc(ball));
+                    base = __shfl_sync(0xffffffffu, base, 0);
+                    if (hit) {
+                        const unsigned long long slot = base + __popc(ball & ((1u << lane) - 1u));
+                        if (slot < capacity) pairs[slot] = make_uint2(myVal, other);
+                    }
+                }
+            }
+        }
+}
+
+// ---- narrowphase on the candidates; contacts are produced unordered with their canonical key ----
+struct KeyedContacts {
+    unsigned long long *keys;   // check id * 8 + vertex
+    unsigned *vals;             // slot in the payload arrays
+    real *payload;              // [slot][8]: point3 normal3 pen
+    int2 *ids;                  // [slot] body indices
+    unsigned long long *count;
+    unsigned long long capacity;
+};
+__device__ __forceinline__ void push_contact(const KeyedContacts &kc, unsigned long long key, const GenContact &c) {
+    const unsigned long long slot = atomicAdd(kc.count, 1ull);
+    if (slot >= kc.capacity) return;
+    kc.keys[slot] = key;
+    kc.vals[slot] = (unsigned)slot;
+    real *r = kc.payload + slot * 8;
+#pragma unroll
+    for (int k = 0; k < 3; k++) { r[k] = c.point.c[k]; r[3 + k] = c.normal.c[k]; }
+    r[6] = c.pen;
+    kc.ids[slot] = make_int2(c.b0, c.b1);
+}
+
+__global__ void __launch_bounds__(128) k_bp_narrow(WorldParams p, const uint2 *pairs, unsigned long long nPairs, KeyedContacts kc) {
+    const unsigned long long t = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= nPairs * 2) return;
+    const uint2 pr = pairs[t >> 1];
+    const int a = (t & 1) ? (int)pr.y : (int)pr.x, b = (t & 1) ? (int)pr.x : (int)pr.y;   // both ordered checks
+    ColliderView one = load_collider(p.st, a, a), two = load_collider(p.st, b, b);
+    V3 v1 = zero3(), v2 = zero3();
+    if (one.shape != two.shape) { v1 = czb::ld_velocity(p.st, a); v2 = czb::ld_velocity(p.st, b); }
+    GenContact gc;
+    if (czn::check_pair(one, two, v1, v2, gc)) {
+        const unsigned long long check = (unsigned long long)a * (unsigned long long)(p.P + p.B) + (unsigned long long)(p.P + b);
+        push_contact(kc, check * 8ull, gc);
+    }
+}
+
+__global__ void __launch_bounds__(128) k_bp_planes(WorldParams p, KeyedContacts kc) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)p.B * p.P) return;
+    const int i = (int)(t / p.P), pl = (int)(t % p.P);
+    if (!body_active(p, i)) return;
+    ColliderView c = load_collider(p.st, i, i);
+    const unsigned long long check = (unsigned long long)i * (unsigned long long)(p.P + p.B) + (unsigned long long)pl;
+    if (c.shape == CZ_SHAPE_SPHERE) {
+        GenContact gc;
+        if (czn::sphere_halfspace(c, p.planes[pl], gc)) push_contact(kc, check * 8ull, gc);
+    } else if (c.shape == CZ_SHAPE_CUBE) {
+        const unsigned mask = czn::cube_halfspace_mask(c, p.planes[pl]);
+#pragma unroll 1
+        for (int v = 0; v < 8; v++)
+            if (mask & (1u << v)) {
+                GenContact gc;
+                czn::cube_halfspace_contact(c, p.planes[pl], v, gc);
+                push_contact(kc, check * 8ull + (unsigned long long)v, gc);
+            }
+    }
+}
+
+// sorted contacts -> the world's as-generated arrays (world 0)
+__global__ void k_bp_emit(WorldParams p, const unsigned *sortedVals, const real *payload, const int2 *idsArr, const unsigned long long *count) {
+    using namespace czr;
+    const unsigned long long n = *count;
+    const unsigned long long c = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c == 0) {
+        p.nContacts[0] = (int)(n > 0x7fffffffull ? 0x7fffffff : n);
+        if (n > (unsigned long long)p.Cc) raise_status(p.stats, CZ_ERR_CAPACITY);
+        atomicAdd(&p.stats[ST_CONTACTS], n);
+        atomicMax(&p.stats[ST_MAXC], n);
+    }
+    if (c >= n || c >= (unsigned long long)p.Cc) return;
+    const real *r = payload + (size_t)sortedVals[c] * 8;
+    const long long gs = (long long)p.W * p.Cc;
+#pragma unroll
+    for (int k = 0; k < 3; k++) { p.gen[(G_POINT + k) * gs + c] = r[k]; p.gen[(G_NORMAL + k) * gs + c] = r[3 + k]; }
+    p.gen[G_PEN * gs + c] = r[6];
+    p.gen[G_FRIC * gs + c] = R_(0.9);
+    p.gen[G_REST * gs + c] = R_(0.1);
+    const int2 ids = idsArr[sortedVals[c]];
+    p.gb0[c] = ids.x;
+    p.gb1[c] = ids.y;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+struct Broadphase {
+    long long n = 0;
+    Bounds *bounds = nullptr, *sorted = nullptr;
+    long long *box = nullptr;            // device [8]
+    long long *h_box = nullptr;          // pinned [8]
+    czs::RadixBuffers<unsigned> sortCells{};
+    uint2 *cellRange = nullptr;
+    long long cellCapacity = 0;
+    uint2 *pairs = nullptr;
+    unsigned long long pairCapacity = 0;
+    unsigned long long *counters = nullptr;      // device [2]: nPairs, nContacts
+    unsigned long long *h_counters = nullptr;    // pinned [2]
+    czs::RadixBuffers<unsigned long long> sortContacts{};
+    real *payload = nullptr;
+    int2 *ids = nullptr;
+    unsigned long long contactCapacity = 0;
+    Grid grid{};
+    unsigned long long lastPairs = 0, lastContacts = 0;
+};
+
+static inline cudaError_t bp_alloc(Broadphase &bp, long long n, unsigned long long pairCap, unsigned long long contactCap, long long maxCells) {
+    bp.n = n;
+    cudaError_t e;
+#define BPCK(x) if ((e = (x)) != cudaSuccess) return e
+    BPCK(cudaMalloc(&bp.bounds, sizeof(Bounds) * n));
+    BPCK(cudaMalloc(&bp.sorted, sizeof(Bounds) * n));
+    BPCK(cudaMalloc(&bp.box, sizeof(long long) * 8));
+    BPCK(cudaHostAlloc(&bp.h_box, sizeof(long long) * 8, cudaHostAllocDefault));
+    BPCK(czs::radix_alloc(bp.sortCells, n));
+    bp.cellCapacity = maxCells;
+    BPCK(cudaMalloc(&bp.cellRange, sizeof(uint2) * maxCells));
+    bp.pairCapacity = pairCap;
+    BPCK(cudaMalloc(&bp.pairs, sizeof(uint2) * pairCap));
+    BPCK(cudaMalloc(&bp.counters, sizeof(unsigned long long) * 2));
+    BPCK(cudaHostAlloc(&bp.h_counters, sizeof(unsigned long long) * 2, cudaHostAllocDefault));
+    bp.contactCapacity = contactCap;
+    if (contactCap) {
+        BPCK(czs::radix_alloc(bp.sortContacts, (long long)contactCap));
+        BPCK(cudaMalloc(&bp.payload, sizeof(real) * 8 * contactCap));
+        BPCK(cudaMalloc(&bp.ids, sizeof(int2) * contactCap));
+    }
+#undef BPCK
+    return cudaSuccess;
+}
+static inline void bp_free(Broadphase &bp) {
+    if (bp.bounds) cudaFree(bp.bounds);
+    if (bp.sorted) cudaFree(bp.sorted);
+    if (bp.box) cudaFree(bp.box);
+    if (bp.h_box) cudaFreeHost(bp.h_box);
+    czs::radix_free(bp.sortCells);
+    if (bp.cellRange) cudaFree(bp.cellRange);
+    if (bp.pairs) cudaFree(bp.pairs);
+    if (bp.counters) cudaFree(bp.counters);
+    if (bp.h_counters) cudaFreeHost(bp.h_counters);
+    czs::radix_free(bp.sortContacts);
+    if (bp.payload) cudaFree(bp.payload);
+    if (bp.ids) cudaFree(bp.ids);
+    bp = Broadphase();
+}
+
+static inline cudaError_t bp_reset_box(Broadphase &bp, cudaStream_t st) {
+    long long init[8] = {0x7fffffffffffffffll, 0x7fffffffffffffffll, 0x7fffffffffffffffll, (long long)0x8000000000000000ull,
+                         (long long)0x8000000000000000ull, (long long)0x8000000000000000ull, 0, 0};
+    memcpy(bp.h_box, init, sizeof(init));
+    return cudaMemcpyAsync(bp.box, bp.h_box, sizeof(init), cudaMemcpyHostToDevice, st);
+}
+
+// Candidate generation from bounds that are already in bp.bounds (box must be reduced too).
+// Returns cudaError; *launches accumulates.
+static inline cudaError_t bp_candidates(Broadphase &bp, cudaStream_t st, long long *launches) {
+    const long long n = bp.n;
+    cudaError_t e;
+    // grid from the box (one small D2H: the cell table size depends on it)
+    if ((e = cudaMemcpyAsync(bp.h_box, bp.box, sizeof(long long) * 8, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return e;
+    if ((e = cudaStreamSynchronize(st)) != cudaSuccess) return e;
+    double mn[3], mx[3];
+    for (int k = 0; k < 3; k++) { mn[k] = unord(bp.h_box[k]); mx[k] = unord(bp.h_box[3 + k]); }
+    double rmax = unord(bp.h_box[6]);
+    if (!(rmax > 0)) rmax = 1.0;
+    if (!(mx[0] >= mn[0])) { for (int k = 0; k < 3; k++) { mn[k] = 0; mx[k] = 0; } }
+    double cell = 2.0 * rmax * BP_MARGIN * 1.0001;
+    Grid g;
+    for (;;) {
+        g.nx = (int)floor((mx[0] - mn[0]) / cell) + 1; g.ny = (int)floor((mx[1] - mn[1]) / cell) + 1; g.nz = (int)floor((mx[2] - mn[2]) / cell) + 1;
+        if ((double)g.nx * g.ny * g.nz <= (double)bp.cellCapacity) break;
+        cell *= 1.26;   // coarser cells: more candidates, never fewer
+    }
+    g.ox = mn[0]; g.oy = mn[1]; g.oz = mn[2]; g.inv = 1.0 / cell;
+    bp.grid = g;
+    const long long cells = (long long)g.nx * g.ny * g.nz;
+    const unsigned nb = (unsigned)((n + 255) / 256);
+    k_bp_keys<<<nb, 256, 0, st>>>(bp.bounds, n, g, bp.sortCells.keys[0], bp.sortCells.vals[0]);
+    int bits = 8;
+    while (bits < 32 && (1ll << bits) <= cells) bits += 8;   // keys < cells, the inactive key is all ones
+    bits = 32;                                                // (inactive colliders carry 0xffffffff)
+    int cur = czs::radix_sort(bp.sortCells, n, bits, st, launches);
+    if ((e = cudaMemsetAsync(bp.cellRange, 0, sizeof(uint2) * cells, st)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(bp.counters, 0, sizeof(unsigned long long) * 2, st)) != cudaSuccess) return e;
+    k_bp_gather<<<nb, 256, 0, st>>>(bp.bounds, bp.sortCells.vals[cur], n, bp.sorted);
+    k_bp_cells<<<nb, 256, 0, st>>>(bp.sortCells.keys[cur], n, bp.cellRange);
+    k_bp_pairs<<<nb, 256, 0, st>>>(bp.sorted, bp.sortCells.keys[cur], bp.sortCells.vals[cur], n, g, bp.cellRange, bp.pairs, bp.counters, bp.pairCapacity);
+    if (launches) *launches += 4;
+    return cudaGetLastError();
+}
+
+}  // namespace czbp

@@ -18,6 +18,7 @@
 
 #include "cz_kernels.cuh"
 #include "cz_fused.cuh"
+#include "cz_broadphase.cuh"
 
 using namespace czk;
 
@@ -247,6 +248,8 @@ struct cz_world {
     ResolveScratch rs{};
     int resolveNT = 32;
     int resolveSmem = 0;        // dynamic shared bytes when staged in smem, 0 = global scratch
+    bool useBP = false;               // sort-based broadphase (K2) instead of the all-pairs tiles
+    czbp::Broadphase bp;
     bool useFused = false;
     czf::FusedPlan fused{};
     unsigned int *d_next = nullptr;   // dynamic world counter of the fused kernel
@@ -323,11 +326,23 @@ static int world_plan(cz_world *w) {
             CK(ctx, cudaMalloc(&w->rs.cb, sizeof(int) * (size_t)W * 2 * Cc));
         }
     }
+    // sort-based broadphase for one large world
+    w->useBP = false;
+    if (w->d.flags & CZ_WORLD_BROADPHASE) {
+        if (W != 1 || w->d.schedule != CZ_SCHED_ALL_PAIRS_ORDERED)
+            return fail(ctx, CZ_ERR_INVALID, "CZ_WORLD_BROADPHASE needs a single world with the all-pairs-ordered schedule");
+        if (!w->bp.bounds) {
+            cudaError_t e = czbp::bp_alloc(w->bp, B, (unsigned long long)B * 64ull + 1024ull, (unsigned long long)Cc * 2ull + 1024ull,
+                                           std::max<long long>(1ll << 22, 16ll * B));
+            if (e != cudaSuccess) return fail(ctx, CZ_ERR_CUDA, std::string("broadphase alloc: ") + cudaGetErrorString(e));
+        }
+        w->useBP = true;
+    }
     // fused small-world kernel
     w->useFused = false;
     if (!(w->d.flags & CZ_WORLD_NO_FUSED)) {
         if (w->fused.cold) { cudaFree(w->fused.cold); w->fused.cold = nullptr; }
-        w->useFused = czf::plan(w->fused, B, w->P, Cc, w->nchk, w->d.schedule, ctx->smem_optin, ctx->sm_count);
+        w->useFused = !w->useBP && czf::plan(w->fused, B, w->P, Cc, w->nchk, w->d.schedule, ctx->smem_optin, ctx->sm_count);
         if (w->useFused) {
             CK(ctx, cudaMalloc(&w->fused.cold, sizeof(real) * w->fused.coldReals * (size_t)w->fused.grid * w->fused.groupsPerBlock));
             if (!w->d_next) CK(ctx, cudaMalloc(&w->d_next, sizeof(unsigned int)));
@@ -428,6 +443,7 @@ int cz_world_destroy(cz_world *w) {
     cudaSetDevice(w->ctx->device);
     cudaStreamSynchronize(w->ctx->stream);
     batch_free(w->b);
+    if (w->bp.bounds) czbp::bp_free(w->bp);
     if (w->snap.st.base) batch_free(w->snap);
     if (w->d_phase0) cudaFree(w->d_phase0);
     void *ptrs[] = {w->d_one, w->d_two, w->gen, w->gb0, w->gb1, w->nContacts, w->posIters, w->velIters, w->stats,
@@ -592,7 +608,40 @@ static int world_step_multi(cz_world *w, real dt, long long &launches) {
     k_integrate<true><<<grid, 256, 0, ctx->stream>>>(w->b.st, dt, w->bias, w->step_index);
     CKL(ctx);
     launches++;
-    if (w->nchk > 0) {
+    if (w->useBP) {
+        // K2: sort-based broadphase -> candidate pairs -> narrowphase -> canonical contact sort
+        czbp::Broadphase &bp = w->bp;
+        cudaError_t e = czbp::bp_reset_box(bp, ctx->stream);
+        if (e != cudaSuccess) return fail(ctx, CZ_ERR_CUDA, cudaGetErrorString(e));
+        czbp::k_bp_bounds<<<nblk(NB, 256), 256, 0, ctx->stream>>>(w->b.st, NB, w->step_index, bp.bounds, bp.box);
+        launches++;
+        if ((e = czbp::bp_candidates(bp, ctx->stream, &launches)) != cudaSuccess) return fail(ctx, CZ_ERR_CUDA, cudaGetErrorString(e));
+        CK(ctx, cudaMemcpyAsync(bp.h_counters, bp.counters, sizeof(unsigned long long) * 2, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(ctx, cudaStreamSynchronize(ctx->stream));
+        const unsigned long long nPairs = bp.h_counters[0];
+        bp.lastPairs = nPairs;
+        if (nPairs > bp.pairCapacity) return fail(ctx, CZ_ERR_CAPACITY, "broadphase candidate-pair capacity exceeded");
+        czbp::KeyedContacts kc{bp.sortContacts.keys[0], bp.sortContacts.vals[0], bp.payload, bp.ids, bp.counters + 1, bp.contactCapacity};
+        if (nPairs) czbp::k_bp_narrow<<<nblk((long long)nPairs * 2, 128), 128, 0, ctx->stream>>>(p, bp.pairs, nPairs, kc);
+        if (p.P > 0) czbp::k_bp_planes<<<nblk((long long)p.B * p.P, 128), 128, 0, ctx->stream>>>(p, kc);
+        launches += 2;
+        CK(ctx, cudaMemcpyAsync(bp.h_counters, bp.counters, sizeof(unsigned long long) * 2, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(ctx, cudaStreamSynchronize(ctx->stream));
+        const unsigned long long nCont = bp.h_counters[1];
+        bp.lastContacts = nCont;
+        if (nCont > bp.contactCapacity || nCont > (unsigned long long)p.Cc) return fail(ctx, CZ_ERR_CAPACITY, "contact capacity exceeded (contacts_per_world too small)");
+        int bits = 8;
+        const unsigned long long maxKey = ((unsigned long long)p.B * (unsigned long long)(p.P + p.B) + 1ull) * 8ull;
+        while (bits < 64 && (1ull << bits) <= maxKey) bits += 8;
+        int cur = czs::radix_sort(bp.sortContacts, (long long)nCont, bits, ctx->stream, &launches);
+        czbp::k_bp_emit<<<nblk(std::max<long long>((long long)nCont, 1), 128), 128, 0, ctx->stream>>>(p, bp.sortContacts.vals[cur], bp.payload, bp.ids, bp.counters + 1);
+        launches++;
+        CKL(ctx);
+        if (w->resolveNT == 32) launch_resolve<32>(w, p, -1, dt, false);
+        else launch_resolve<256>(w, p, -1, dt, false);
+        CKL(ctx);
+        launches++;
+    } else if (w->nchk > 0) {
         if (w->tiles == 1) {
             k_narrow<NARROW_SINGLE><<<p.W, w->tileThreads, 0, ctx->stream>>>(p, 1, nullptr, nullptr, nullptr);
             CKL(ctx);
@@ -1115,6 +1164,147 @@ int cz_bench_integrate(cz_ctx *ctx, int64_t n, uint64_t seed, int32_t warmup, in
     }
     batch_free(b);
     return CZ_OK;
+}
+
+// ---- K2 entry points: host-buffer broadphase, microbench, sort test hooks ------------------------
+__global__ void k_bp_load_host(const real *centers, const real *radii, long long n, czbp::Bounds *bounds, long long *box) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    double mn[3] = {1e300, 1e300, 1e300}, mx[3] = {-1e300, -1e300, -1e300}, rmax = 0;
+    if (i < n) {
+        czbp::Bounds b{centers[i * 3], centers[i * 3 + 1], centers[i * 3 + 2], radii[i]};
+        bounds[i] = b;
+        for (int k = 0; k < 3; k++) mn[k] = mx[k] = (double)centers[i * 3 + k];
+        rmax = (double)b.r;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        for (int k = 0; k < 3; k++) {
+            mn[k] = fmin(mn[k], __shfl_xor_sync(0xffffffffu, mn[k], o));
+            mx[k] = fmax(mx[k], __shfl_xor_sync(0xffffffffu, mx[k], o));
+        }
+        rmax = fmax(rmax, __shfl_xor_sync(0xffffffffu, rmax, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        for (int k = 0; k < 3; k++) { atomicMin(&box[k], czbp::ord(mn[k])); atomicMax(&box[3 + k], czbp::ord(mx[k])); }
+        atomicMax(&box[6], czbp::ord(rmax));
+    }
+}
+// n unit-radius spheres uniformly scattered in a cube sized for the requested volume fill
+__global__ void k_bp_scatter_spheres(long long n, unsigned long long seed, double side, czbp::Bounds *bounds, long long *box) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    double mn[3] = {1e300, 1e300, 1e300}, mx[3] = {-1e300, -1e300, -1e300};
+    if (i < n) {
+        unsigned long long st = seed * 0x100000001B3ull + (unsigned long long)i * 0x9E3779B97F4A7C15ull;
+        czbp::Bounds b;
+        b.x = (real)(sm64_next(st) * side); b.y = (real)(sm64_next(st) * side); b.z = (real)(sm64_next(st) * side); b.r = R_(1.0);
+        bounds[i] = b;
+        mn[0] = mx[0] = (double)b.x; mn[1] = mx[1] = (double)b.y; mn[2] = mx[2] = (double)b.z;
+    }
+    for (int o = 16; o > 0; o >>= 1)
+        for (int k = 0; k < 3; k++) {
+            mn[k] = fmin(mn[k], __shfl_xor_sync(0xffffffffu, mn[k], o));
+            mx[k] = fmax(mx[k], __shfl_xor_sync(0xffffffffu, mx[k], o));
+        }
+    if ((threadIdx.x & 31) == 0) {
+        for (int k = 0; k < 3; k++) { atomicMin(&box[k], czbp::ord(mn[k])); atomicMax(&box[3 + k], czbp::ord(mx[k])); }
+        atomicMax(&box[6], czbp::ord(1.0));
+    }
+}
+
+int cz_broadphase_pairs(cz_ctx *ctx, int64_t n, const cz_real *centers, const cz_real *radii, int64_t capacity, int32_t *pairs, int64_t *n_pairs) {
+    if (!ctx || n <= 0 || !centers || !radii || !pairs || !n_pairs || capacity <= 0) return fail(ctx, CZ_ERR_INVALID, "cz_broadphase_pairs: bad argument");
+    CK(ctx, cudaSetDevice(ctx->device));
+    czbp::Broadphase bp;
+    cudaError_t e = czbp::bp_alloc(bp, n, (unsigned long long)capacity, 0, std::max<long long>(1ll << 22, 16 * n));
+    real *dc = nullptr, *dr = nullptr;
+    int rc = CZ_OK;
+    do {
+        if (e != cudaSuccess) { rc = fail(ctx, CZ_ERR_CUDA, cudaGetErrorString(e)); break; }
+        if (cudaMalloc(&dc, sizeof(real) * 3 * n) != cudaSuccess || cudaMalloc(&dr, sizeof(real) * n) != cudaSuccess) { rc = fail(ctx, CZ_ERR_NOMEM, "cudaMalloc"); break; }
+        cudaMemcpyAsync(dc, centers, sizeof(real) * 3 * n, cudaMemcpyHostToDevice, ctx->stream);
+        cudaMemcpyAsync(dr, radii, sizeof(real) * n, cudaMemcpyHostToDevice, ctx->stream);
+        czbp::bp_reset_box(bp, ctx->stream);
+        k_bp_load_host<<<nblk(n, 256), 256, 0, ctx->stream>>>(dc, dr, n, bp.bounds, bp.box);
+        long long launches = 0;
+        if ((e = czbp::bp_candidates(bp, ctx->stream, &launches)) != cudaSuccess) { rc = fail(ctx, CZ_ERR_CUDA, cudaGetErrorString(e)); break; }
+        unsigned long long cnt[2];
+        cudaMemcpyAsync(cnt, bp.counters, sizeof(cnt), cudaMemcpyDeviceToHost, ctx->stream);
+        if ((e = cudaStreamSynchronize(ctx->stream)) != cudaSuccess) { rc = fail(ctx, CZ_ERR_CUDA, cudaGetErrorString(e)); break; }
+        *n_pairs = (int64_t)cnt[0];
+        if (cnt[0] > (unsigned long long)capacity) { rc = fail(ctx, CZ_ERR_CAPACITY, "pair capacity exceeded"); break; }
+        cudaMemcpy(pairs, bp.pairs, sizeof(uint2) * cnt[0], cudaMemcpyDeviceToHost);
+    } while (0);
+    if (dc) cudaFree(dc);
+    if (dr) cudaFree(dr);
+    czbp::bp_free(bp);
+    return rc;
+}
+
+int cz_bench_broadphase(cz_ctx *ctx, int64_t n, uint64_t seed, double fill, int32_t warmup, int32_t steps, float *avg_ms, int64_t *n_pairs, float *sort_ms) {
+    if (!ctx || n <= 0 || steps <= 0 || !(fill > 0)) return fail(ctx, CZ_ERR_INVALID, "cz_bench_broadphase: bad argument");
+    CK(ctx, cudaSetDevice(ctx->device));
+    czbp::Broadphase bp;
+    cudaError_t e = czbp::bp_alloc(bp, n, (unsigned long long)n * 8ull + 1024ull, 0, std::max<long long>(1ll << 22, 16 * n));
+    if (e != cudaSuccess) { czbp::bp_free(bp); return fail(ctx, CZ_ERR_CUDA, cudaGetErrorString(e)); }
+    const double side = cbrt((double)n * (4.0 / 3.0) * 3.14159265358979323846 / fill);
+    float total = 0, totalSort = 0;
+    cudaEvent_t s0, s1;
+    cudaEventCreate(&s0); cudaEventCreate(&s1);
+    int rc = CZ_OK;
+    for (int it = 0; it < warmup + steps && rc == CZ_OK; it++) {
+        // (re)generate the bounds outside the timed region: the timed frame is keys -> sort -> cells -> sweep
+        czbp::bp_reset_box(bp, ctx->stream);
+        k_bp_scatter_spheres<<<nblk(n, 256), 256, 0, ctx->stream>>>(n, seed + it, side, bp.bounds, bp.box);
+        cudaEventRecord(ctx->ev0, ctx->stream);
+        long long launches = 0;
+        if ((e = czbp::bp_candidates(bp, ctx->stream, &launches)) != cudaSuccess) { rc = fail(ctx, CZ_ERR_CUDA, cudaGetErrorString(e)); break; }
+        cudaEventRecord(ctx->ev1, ctx->stream);
+        if ((e = cudaEventSynchronize(ctx->ev1)) != cudaSuccess) { rc = fail(ctx, CZ_ERR_CUDA, cudaGetErrorString(e)); break; }
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+        // the radix sort alone, on the same keys
+        czbp::k_bp_keys<<<nblk(n, 256), 256, 0, ctx->stream>>>(bp.bounds, n, bp.grid, bp.sortCells.keys[0], bp.sortCells.vals[0]);
+        cudaEventRecord(s0, ctx->stream);
+        czs::radix_sort(bp.sortCells, n, 32, ctx->stream, nullptr);
+        cudaEventRecord(s1, ctx->stream);
+        cudaEventSynchronize(s1);
+        float sms = 0;
+        cudaEventElapsedTime(&sms, s0, s1);
+        if (it >= warmup) { total += ms; totalSort += sms; }
+    }
+    unsigned long long cnt[2] = {0, 0};
+    cudaMemcpy(cnt, bp.counters, sizeof(cnt), cudaMemcpyDeviceToHost);
+    if (avg_ms) *avg_ms = total / steps;
+    if (sort_ms) *sort_ms = totalSort / steps;
+    if (n_pairs) *n_pairs = (int64_t)cnt[0];
+    cudaEventDestroy(s0); cudaEventDestroy(s1);
+    czbp::bp_free(bp);
+    return rc;
+}
+
+}  // extern "C"
+
+template <typename K> static int sort_pairs_host(cz_ctx *ctx, int64_t n, K *keys, uint32_t *vals, int bits) {
+    if (!ctx || n < 0 || !keys || !vals) return fail(ctx, CZ_ERR_INVALID, "cz_sort_pairs: bad argument");
+    if (n == 0) return CZ_OK;
+    CK(ctx, cudaSetDevice(ctx->device));
+    czs::RadixBuffers<K> buf{};
+    cudaError_t e = czs::radix_alloc(buf, n);
+    if (e != cudaSuccess) { czs::radix_free(buf); return fail(ctx, CZ_ERR_CUDA, cudaGetErrorString(e)); }
+    cudaMemcpyAsync(buf.keys[0], keys, sizeof(K) * n, cudaMemcpyHostToDevice, ctx->stream);
+    cudaMemcpyAsync(buf.vals[0], vals, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, ctx->stream);
+    int cur = czs::radix_sort(buf, n, bits, ctx->stream, nullptr);
+    cudaMemcpyAsync(keys, buf.keys[cur], sizeof(K) * n, cudaMemcpyDeviceToHost, ctx->stream);
+    cudaMemcpyAsync(vals, buf.vals[cur], sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, ctx->stream);
+    e = cudaStreamSynchronize(ctx->stream);
+    czs::radix_free(buf);
+    if (e != cudaSuccess) return fail(ctx, CZ_ERR_CUDA, cudaGetErrorString(e));
+    return CZ_OK;
+}
+extern "C" {
+
+int cz_sort_pairs_u32(cz_ctx *ctx, int64_t n, uint32_t *keys, uint32_t *vals) { return sort_pairs_host<unsigned>(ctx, n, keys, vals, 32); }
+int cz_sort_pairs_u64(cz_ctx *ctx, int64_t n, uint64_t *keys, uint32_t *vals, int32_t bits) {
+    return sort_pairs_host<unsigned long long>(ctx, n, (unsigned long long *)keys, vals, bits <= 0 ? 64 : (bits + 7) / 8 * 8);
 }
 
 }  // extern "C"

@@ -253,6 +253,20 @@ int cz_world_step_host(cz_world *w, cz_bodies *io, cz_real dt, int32_t n_steps, 
  * with CUDA events on the context stream; returns average ms per step. */
 int cz_bench_integrate(cz_ctx *ctx, int64_t n, uint64_t seed, int32_t warmup, int32_t steps, cz_real dt,
                        float *avg_ms, uint64_t *checksum);
+/* Sort-based broadphase (K2) on host-supplied bounding spheres: candidate pairs (i, j) whose
+ * spheres overlap within the library's 0.5 % inflation.  pairs holds 2*capacity ints; *n_pairs is
+ * the number found (may exceed capacity: CZ_ERR_CAPACITY).  Order is unspecified. */
+int cz_broadphase_pairs(cz_ctx *ctx, int64_t n, const cz_real *centers, const cz_real *radii, int64_t capacity,
+                        int32_t *pairs, int64_t *n_pairs);
+/* K2 microbench: n unit spheres scattered uniformly at `fill` volume fraction (splitmix64 seed),
+ * device resident; times bounds -> keys -> radix sort -> cell ranges -> neighbour sweep with CUDA
+ * events; returns average ms per frame and the number of candidate pairs. */
+int cz_bench_broadphase(cz_ctx *ctx, int64_t n, uint64_t seed, double fill, int32_t warmup, int32_t steps, float *avg_ms,
+                        int64_t *n_pairs, float *sort_ms);
+/* hand-written radix sort of (key, value) pairs on host buffers (test hook for cz_sort.cuh) */
+int cz_sort_pairs_u32(cz_ctx *ctx, int64_t n, uint32_t *keys, uint32_t *vals);
+int cz_sort_pairs_u64(cz_ctx *ctx, int64_t n, uint64_t *keys, uint32_t *vals, int32_t bits);
+
 /* device math self-test: runs op `op` of the math layer on one thread (tests port the
  * reference's math/ *_test.go known answers through this). */
 int cz_math_op(cz_ctx *ctx, int32_t op, const cz_real *in, cz_real *out);
