@@ -374,6 +374,7 @@ int cz_init(int device, cz_ctx **out) {
     cudaDeviceProp prop;
     CK(ctx, cudaGetDeviceProperties(&prop, device));
     ctx->sm_count = prop.multiProcessorCount;
+    if (const char *e = getenv("CUBEZ_L2_FETCH")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(e));
     ctx->smem_optin = prop.sharedMemPerBlockOptin;
     *out = ctx;
     return CZ_OK;
