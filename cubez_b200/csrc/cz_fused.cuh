@@ -55,7 +55,7 @@ static inline size_t world_bytes(int B, int Cc, int nchk) {
     size_t reals = (size_t)FB_NF * B + 2 * (size_t)Cc;
     size_t ints = 2 * (size_t)Cc + 2 * (size_t)B;
     size_t shorts = 2 * (size_t)nchk;          // per-check info + the queue of checks that need a full pair test
-    size_t bytes = reals * sizeof(real) + ints * sizeof(int) + shorts * sizeof(unsigned short) + (size_t)nchk;
+    size_t bytes = reals * sizeof(real) + ints * sizeof(int) + shorts * sizeof(unsigned short) + (size_t)nchk + (size_t)Cc;
     return (bytes + 15) / 16 * 16;
 }
 
@@ -223,6 +223,7 @@ __global__ void __launch_bounds__(128, MINB) k_world_fused(WorldParams p, FusedP
     s.info = (unsigned short *)(s.active + B);
     s.queue = s.info + p.nchk;
     s.cnt = (unsigned char *)(s.queue + p.nchk);
+    unsigned char *mlist = s.cnt + p.nchk;
     s.cold = fp.cold + ((size_t)blockIdx.x * fp.groupsPerBlock + grp) * fp.coldReals;
     s.pairGen = s.cold + (size_t)Cc * CW_NCOLD;
     const BodyStore &st = p.st;
@@ -232,6 +233,7 @@ __global__ void __launch_bounds__(128, MINB) k_world_fused(WorldParams p, FusedP
     x.cold = s.cold; x.cfs = 1; x.ccs = CW_NCOLD;       // AoS
     x.pen = s.pen; x.ddv = s.ddv; x.fric = nullptr; x.rest = nullptr;
     x.cb0 = s.cb0; x.cb1 = s.cb1; x.nC = 0; x.dt = dt;
+    x.mlist = Cc <= 256 ? mlist : nullptr;
     x.xb = nullptr; x.xbs = 0; x.store = st;
     GenView gv;
     gv.pn = s.cold; gv.fs = 1; gv.cs = CW_NCOLD; gv.pen = s.pen; gv.fric = nullptr; gv.rest = nullptr; gv.b0 = s.cb0; gv.b1 = s.cb1;

@@ -36,6 +36,7 @@ struct Ctx {
     real *pen, *ddv;            // hot: Penetration, desiredDeltaVelocity  [contact]
     real *fric, *rest;          // per-contact Friction / Restitution, or NULL: the constants 0.9 / 0.1
     int *cb0, *cb1;             // contact body indices (world-local, -1 = nil)
+    unsigned char *mlist;       // optional [capacity <= 256]: compacted list of contacts touched by a resolve
     int nC;
     real dt;
     // The rare "resolved body is asleep" path (contact.go:380-382) reads the body-space inverse
@@ -472,7 +473,12 @@ __device__ __forceinline__ int resolve_loop(const Ctx &x, bool enabled, int maxI
     static_assert(NT <= 32, "warp-level loop");
     const real *hot = VELOCITY ? x.ddv : x.pen;
     const unsigned full = 0xffffffffu;
+    const unsigned gshift = (threadIdx.x & 31u) & ~(unsigned)(NT - 1);
+    const unsigned gbits = NT == 32 ? 0xffffffffu : ((1u << NT) - 1u);
     bool done = !enabled || maxIterations <= 0;
+    int maxC = enabled ? x.nC : 0;   // longest contact list among the worlds of this warp
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) maxC = max(maxC, __shfl_xor_sync(full, maxC, o));
     int used = 0;
     while (true) {
         real best = R_(0.01);   // positionEpsilon / velocityEpsilon (contact.go:12-13)
@@ -499,11 +505,37 @@ __device__ __forceinline__ int resolve_loop(const Ctx &x, bool enabled, int maxI
             else commit_position(x, pc);
         }
         __syncwarp();
-        if (!done) {
+        if (x.mlist) {
+            // Propagation, compacted: only the contacts that share a body with the winner change
+            // (typically the 4 plane contacts of the same cube and a few pair contacts).  Pass 1 marks
+            // them with a cheap id compare and ballot-compacts their indices; pass 2 runs the update
+            // densely, one touched contact per lane.  (In place, ~3 of 4 lanes idled through the update.)
+            int nM = 0;
+            for (int c0 = 0; c0 < maxC; c0 += NT) {
+                const int c = c0 + tid;
+                bool m = false;
+                if (!done && c < x.nC) {
+                    const int c0b = x.cb0[c], c1b = x.cb1[c];
+                    m = c0b == ch.b[0] || c0b == ch.b[1] || (c1b >= 0 && (c1b == ch.b[0] || c1b == ch.b[1]));
+                }
+                const unsigned ball = (__ballot_sync(full, m) >> gshift) & gbits;
+                if (m) x.mlist[nM + __popc(ball & ((1u << tid) - 1u))] = (unsigned char)c;
+                nM += __popc(ball);
+            }
+            __syncwarp();
+            if (!done) {
+                for (int k = tid; k < nM; k += NT) {
+                    if (VELOCITY) propagate_velocity(x, x.mlist[k], ch);
+                    else propagate_position(x, x.mlist[k], ch);
+                }
+            }
+        } else if (!done) {
             for (int c = tid; c < x.nC; c += NT) {
                 if (VELOCITY) propagate_velocity(x, c, ch);
                 else propagate_position(x, c, ch);
             }
+        }
+        if (!done) {
             used++;
             if (used >= maxIterations) done = true;
         }

@@ -124,17 +124,17 @@ def _():
     sc = scenes.batched_cubedrop(n_worlds=W)
     ph = (np.arange(W) % 600).astype(np.int32)
     ref = None
-    for G, MB, LS in (("8", "2", "1"), ("8", "2", "0"), ("8", "3", "1"), ("8", "4", "1"), ("16", "2", "1"), ("32", "2", "1")):
-        os.environ["CUBEZ_FUSED_G"] = G; os.environ["CUBEZ_FUSED_MINB"] = MB; os.environ["CUBEZ_FUSED_LOCKSTEP"] = LS
+    for G, MB, LS, TH in (("8", "2", "1", "128"), ("8", "2", "1", "64"), ("8", "2", "1", "32"), ("8", "2", "0", "64"), ("16", "2", "1", "64")):
+        os.environ["CUBEZ_FUSED_G"] = G; os.environ["CUBEZ_FUSED_MINB"] = MB; os.environ["CUBEZ_FUSED_LOCKSTEP"] = LS; os.environ["CUBEZ_FUSED_THREADS"] = TH
         gpu = BatchedWorld.from_scene(sc, contacts_per_world=64)
         gpu.set_episodes(600, ph)
         t = time.time(); gpu.step(sc.dt, 600); pre = time.time() - t
         st = gpu.step(sc.dt, 60)
         ck = gpu.checksum_energy()[0]
         ref = ref or ck
-        print(f"   G={G} MINB={MB} LOCKSTEP={LS}: pre-roll {pre:.2f}s; {st['device_ms']/60:.3f} ms/frame -> {W*60/st['device_ms']/1e3:.2f} M world-steps/s; checksum same {ck == ref}; vel it/ws {st['vel_iterations']/(W*60):.2f}", flush=True)
+        print(f"   G={G} MINB={MB} LOCKSTEP={LS} THREADS={TH}: pre-roll {pre:.2f}s; {st['device_ms']/60:.3f} ms/frame -> {W*60/st['device_ms']/1e3:.2f} M world-steps/s; checksum same {ck == ref}; vel it/ws {st['vel_iterations']/(W*60):.2f}", flush=True)
         gpu.close()
-    for k in ("CUBEZ_FUSED_G", "CUBEZ_FUSED_MINB", "CUBEZ_FUSED_LOCKSTEP"):
+    for k in ("CUBEZ_FUSED_G", "CUBEZ_FUSED_MINB", "CUBEZ_FUSED_LOCKSTEP", "CUBEZ_FUSED_THREADS"):
         os.environ.pop(k)
 
 @section("step_host e2e timing (65536 worlds)")
