@@ -227,6 +227,17 @@ def main():
                        "peak_kind": peak_kind,
                        "ms_per_launch": ms, "body_steps_per_s": K1_BODIES / (ms * 1e-3), "bytes_per_body": K1_BYTES_F64}
 
+    roofline_k2 = None
+    if rank == 0 and not args.no_k1:
+        import ctypes as C
+        ms2, pairs, sms = C.c_float(), C.c_int64(), C.c_float()
+        ctx.check(ctx.lib.cz_bench_broadphase(ctx.h, K1_BODIES, 7, 0.05, 2, 5, C.byref(ms2), C.byref(pairs), C.byref(sms)))
+        alg = 148 * K1_BODIES + 8 * pairs.value          # 148 n + 8 q bytes (f64 bounds, 4-pass radix sort)
+        ach2 = alg / (ms2.value * 1e-3) / 1e9
+        roofline_k2 = {"bound": "hbm", "kernel": "K2 sort-based broadphase (keys, radix sort, gather, cell ranges, neighbour sweep): 16Mi unit spheres, 5% fill",
+                       "achieved": ach2, "peak": peak, "unit": "GB/s", "frac": ach2 / peak, "traffic": None, "peak_kind": peak_kind,
+                       "ms_per_frame": ms2.value, "radix_sort_ms": sms.value, "candidate_pairs": pairs.value}
+
     if rank == 0:
         cpu_value, cpu_s = cpu_oracle_sample(256, 1)
         line = {
@@ -244,6 +255,7 @@ def main():
             "clocks": sampler.summary(),
             "roofline": roofline,
             "roofline_k1": roofline_k1,
+            "roofline_k2": roofline_k2,
             "cpu_baseline": {"value": cpu_value, "unit": "world-steps/s", "cores": 1, "kind": "port",
                              "sample": f"256 worlds x {EPISODE} frames, 1 thread, {cpu_s:.1f} s (C++ restatement of the Go loops)"},
             "checksum": hex(red["checksum"]), "energy": red["energy"],

@@ -19,6 +19,7 @@
 #pragma once
 #include "cz_kernels.cuh"
 #include "cz_sort.cuh"
+#include <cstdio>
 
 namespace czbp {
 using namespace czm;
@@ -87,11 +88,12 @@ __device__ __forceinline__ void cell_of(const Grid &g, const Bounds &b, int &cx,
     cz = min(max((int)floor(((double)b.z - g.oz) * g.inv), 0), g.nz - 1);
 }
 
+#define BP_INACTIVE 0xffffffffu
 __global__ void k_bp_keys(const Bounds *bounds, long long n, Grid g, unsigned *keys, unsigned *vals) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     Bounds b = bounds[i];
-    unsigned key = 0xffffffffu;   // inactive colliders sort to the end
+    unsigned key = (unsigned)(g.nx * g.ny * g.nz);   // inactive colliders: one past the last cell, sorts to the end
     if (b.r >= R_(0)) {
         int cx, cy, cz;
         cell_of(g, b, cx, cy, cz);
@@ -106,75 +108,81 @@ __global__ void k_bp_gather(const Bounds *bounds, const unsigned *vals, long lon
     if (p < n) sorted[p] = bounds[vals[p]];
 }
 
-__global__ void k_bp_cells(const unsigned *keys, long long n, uint2 *cellRange) {
+__global__ void k_bp_cells(const unsigned *keys, long long n, unsigned nCells, uint2 *cellRange, unsigned *occ) {
     long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n) return;
     const unsigned k = keys[p];
-    if (k == 0xffffffffu) return;
-    if (p == 0 || keys[p - 1] != k) cellRange[k].x = (unsigned)p;
+    if (k >= nCells) return;
+    if (p == 0 || keys[p - 1] != k) { cellRange[k].x = (unsigned)p; atomicOr(&occ[k >> 5], 1u << (k & 31)); }
     if (p == n - 1 || keys[p + 1] != k) cellRange[k].y = (unsigned)(p + 1);
 }
 
 #define BP_MARGIN 1.005   // on the distance (1.01 on its square), as czn::bounding_reject
 
-// candidate pairs (original collider indices, a < b by sorted position) with warp-ballot compaction
+// candidate pairs (original collider indices; each unordered pair once).  Hits are rare (~0.2 per
+// body at 5 % fill), so they are staged per CTA in shared memory (shared-memory atomic for the slot)
+// and flushed with ONE global atomic per CTA and a coalesced copy; a per-hit warp ballot made every
+// lane iterate to the longest neighbour range of its warp and the kernel was issue-bound.
+#define BP_STAGE 1024
 __global__ void __launch_bounds__(256) k_bp_pairs(const Bounds *sorted, const unsigned *keys, const unsigned *vals, long long n, Grid g,
-                                                  const uint2 *cellRange, uint2 *pairs, unsigned long long *nPairs, unsigned long long capacity) {
+                                                  const uint2 *cellRange, const unsigned *occ, uint2 *pairs, unsigned long long *nPairs,
+                                                  unsigned long long capacity) {
+    __shared__ uint2 stage[BP_STAGE];
+    __shared__ unsigned nStage;
+    __shared__ unsigned long long base;
+    if (threadIdx.x == 0) nStage = 0;
+    __syncthreads();
     const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const int lane = threadIdx.x & 31;
-    Bounds me;
-    me.r = R_(-1);
-    int cx = 0, cy = 0, cz = 0;
-    const bool valid = p < n && keys[p] != 0xffffffffu;
-    if (valid) { me = sorted[p]; cell_of(g, me, cx, cy, cz); }
-    const unsigned myVal = valid ? vals[p] : 0u;
-    // Each unordered pair is emitted once, from the body that comes first in sorted (key) order, so
-    // only the "forward" half of the 27-cell neighbourhood is visited: the own row from the own cell
-    // on, and the four rows with a larger key ((dz,dy) = (0,+1), (+1,-1), (+1,0), (+1,+1)).
-    for (int row = 0; row < 5; row++) {
+    const bool valid = p < n && keys[p] < (unsigned)(g.nx * g.ny * g.nz);
+    if (valid) {
+        const Bounds me = sorted[p];
+        int cx, cy, cz;
+        cell_of(g, me, cx, cy, cz);
+        const unsigned myVal = vals[p];
+        // Each unordered pair is emitted once, from the body that comes first in sorted (key) order,
+        // so only the "forward" half of the 27-cell neighbourhood is visited: the own row from the own
+        // cell on, and the four rows with a larger key ((dz,dy) = (0,+1), (+1,-1), (+1,0), (+1,+1)).
+#pragma unroll 1
+        for (int row = 0; row < 5; row++) {
             const int dz = row >= 2 ? 1 : 0, dy = row == 0 ? 0 : (row == 1 ? 1 : row - 3);
+            const int y = cy + dy, z = cz + dz;
+            if (y < 0 || y >= g.ny || z < 0 || z >= g.nz) continue;
             // the cells of a row are consecutive keys -> one contiguous range of the sorted array
             unsigned q0 = 0, q1 = 0;
-            if (valid) {
-                const int y = cy + dy, z = cz + dz;
-                if (y >= 0 && y < g.ny && z >= 0 && z < g.nz) {
-                    bool first = true;
-                    for (int dx = row == 0 ? 0 : -1; dx <= 1; dx++) {
-                        const int x = cx + dx;
-                        if (x < 0 || x >= g.nx) continue;
-                        const uint2 r = cellRange[(z * g.ny + y) * g.nx + x];
-                        if (r.y > r.x) { if (first) { q0 = r.x; first = false; } q1 = r.y; }
-                    }
-                }
+            bool first = true;
+            for (int dx = row == 0 ? 0 : -1; dx <= 1; dx++) {
+                const int x = cx + dx;
+                if (x < 0 || x >= g.nx) continue;
+                // 1 bit per cell (L2-resident even when the 8-byte range table is not): most cells are empty
+                const unsigned c = (unsigned)((z * g.ny + y) * g.nx + x);
+                if (!((occ[c >> 5] >> (c & 31)) & 1u)) continue;
+                const uint2 r = cellRange[c];
+                if (first) { q0 = r.x; first = false; }
+                q1 = r.y;
             }
-            // all lanes iterate to the longest range of the warp so that the ballot is warp-wide
-            unsigned len = q1 > q0 ? q1 - q0 : 0u;
-            unsigned maxLen = len;
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) maxLen = max(maxLen, __shfl_xor_sync(0xffffffffu, maxLen, o));
-            for (unsigned t = 0; t < maxLen; t++) {
-                bool hit = false;
-                unsigned other = 0;
-                const unsigned q = q0 + t;
-                if (t < len && (long long)q > p) {
-                    const Bounds ob = sorted[q];
-                    const double ddx = (double)ob.x - (double)me.x, ddy = (double)ob.y - (double)me.y, ddz = (double)ob.z - (double)me.z;
-                    const double rr = ((double)ob.r + (double)me.r) * BP_MARGIN;
-                    hit = ddx * ddx + ddy * ddy + ddz * ddz <= rr * rr + 1e-9;
-                    other = vals[q];
-                }
-                const unsigned ball = __ballot_sync(0xffffffffu, hit);
-                if (ball) {
-                    unsigned long long base = 0;
-                    if (lane == 0) base = atomicAdd(nPairs, (unsigned long long)__popc(ball));
-                    base = __shfl_sync(0xffffffffu, base, 0);
-                    if (hit) {
-                        const unsigned long long slot = base + __popc(ball & ((1u << lane) - 1u));
-                        if (slot < capacity) pairs[slot] = make_uint2(myVal, other);
+            if (row == 0 && q0 <= (unsigned)p) q0 = (unsigned)p + 1;   // own cell: only bodies after me
+            for (unsigned q = q0; q < q1; q++) {
+                const Bounds ob = sorted[q];
+                const double ddx = (double)ob.x - (double)me.x, ddy = (double)ob.y - (double)me.y, ddz = (double)ob.z - (double)me.z;
+                const double rr = ((double)ob.r + (double)me.r) * BP_MARGIN;
+                if (ddx * ddx + ddy * ddy + ddz * ddz <= rr * rr + 1e-9) {
+                    const uint2 pr = make_uint2(myVal, vals[q]);
+                    const unsigned slot = atomicAdd(&nStage, 1u);
+                    if (slot < BP_STAGE) stage[slot] = pr;
+                    else {   // staging full: straight to global
+                        const unsigned long long gslot = atomicAdd(nPairs, 1ull);
+                        if (gslot < capacity) pairs[gslot] = pr;
                     }
                 }
             }
         }
+    }
+    __syncthreads();
+    const unsigned cnt = min(nStage, (unsigned)BP_STAGE);
+    if (threadIdx.x == 0 && cnt) base = atomicAdd(nPairs, (unsigned long long)cnt);
+    __syncthreads();
+    for (unsigned i = threadIdx.x; i < cnt; i += blockDim.x)
+        if (base + i < capacity) pairs[base + i] = stage[i];
 }
 
 // ---- narrowphase on the candidates; contacts are produced unordered with their canonical key ----
@@ -269,6 +277,7 @@ struct Broadphase {
     long long *h_box = nullptr;          // pinned [8]
     czs::RadixBuffers<unsigned> sortCells{};
     uint2 *cellRange = nullptr;
+    unsigned *occ = nullptr;             // occupancy bit per cell
     long long cellCapacity = 0;
     uint2 *pairs = nullptr;
     unsigned long long pairCapacity = 0;
@@ -280,6 +289,9 @@ struct Broadphase {
     unsigned long long contactCapacity = 0;
     Grid grid{};
     unsigned long long lastPairs = 0, lastContacts = 0;
+    bool trace = false;                  // per-stage CUDA-event timing (diagnostics)
+    cudaEvent_t tev[8] = {};
+    float stageMs[8] = {};               // keys, sort, memset, gather, cells, pairs
 };
 
 static inline cudaError_t bp_alloc(Broadphase &bp, long long n, unsigned long long pairCap, unsigned long long contactCap, long long maxCells) {
@@ -293,6 +305,7 @@ static inline cudaError_t bp_alloc(Broadphase &bp, long long n, unsigned long lo
     BPCK(czs::radix_alloc(bp.sortCells, n));
     bp.cellCapacity = maxCells;
     BPCK(cudaMalloc(&bp.cellRange, sizeof(uint2) * maxCells));
+    BPCK(cudaMalloc(&bp.occ, sizeof(unsigned) * (maxCells / 32 + 1)));
     bp.pairCapacity = pairCap;
     BPCK(cudaMalloc(&bp.pairs, sizeof(uint2) * pairCap));
     BPCK(cudaMalloc(&bp.counters, sizeof(unsigned long long) * 2));
@@ -313,6 +326,7 @@ static inline void bp_free(Broadphase &bp) {
     if (bp.h_box) cudaFreeHost(bp.h_box);
     czs::radix_free(bp.sortCells);
     if (bp.cellRange) cudaFree(bp.cellRange);
+    if (bp.occ) cudaFree(bp.occ);
     if (bp.pairs) cudaFree(bp.pairs);
     if (bp.counters) cudaFree(bp.counters);
     if (bp.h_counters) cudaFreeHost(bp.h_counters);
@@ -344,8 +358,8 @@ static inline cudaError_t bp_candidates(Broadphase &bp, cudaStream_t st, long lo
     if (!(mx[0] >= mn[0])) { for (int k = 0; k < 3; k++) { mn[k] = 0; mx[k] = 0; } }
     // cell edge = 2 x the minimum (2*Rmax): at a few % volume fill the minimum-size grid is ~10 cells
     // per body, and its table (memset + scattered writes + 14 lookups per body) costs more than the
-    // extra distance tests of a coarser grid (measured at 16 Mi spheres, 5 % fill: 4.05 ms -> 3.05 ms)
-    double scale = 2.0;
+    // extra distance tests of a slightly coarser grid (measured at 16 Mi spheres, 5 % fill; see profiles/)
+    double scale = 1.3;
     if (const char *e = getenv("CUBEZ_BP_CELL_SCALE")) { double sc = atof(e); if (sc >= 1.0 && sc <= 8.0) scale = sc; }
     double cell = 2.0 * rmax * BP_MARGIN * 1.0001 * scale;
     Grid g;
@@ -354,21 +368,46 @@ static inline cudaError_t bp_candidates(Broadphase &bp, cudaStream_t st, long lo
         if ((double)g.nx * g.ny * g.nz <= (double)bp.cellCapacity) break;
         cell *= 1.26;   // coarser cells: more candidates, never fewer
     }
+    // one radix pass less when a slightly coarser grid brings the key width under a byte boundary
+    for (int tries = 0; tries < 4; tries++) {
+        const double c = (double)g.nx * g.ny * g.nz + 1.0;
+        int kb = 1;
+        while ((double)(1ull << kb) < c) kb++;
+        const int over = kb % 8;   // bits above the last full byte
+        if (over == 0 || over > 2) break;
+        const double cell2 = cell * 1.26;
+        Grid h = g;
+        h.nx = (int)floor((mx[0] - mn[0]) / cell2) + 1; h.ny = (int)floor((mx[1] - mn[1]) / cell2) + 1; h.nz = (int)floor((mx[2] - mn[2]) / cell2) + 1;
+        cell = cell2; g = h;
+    }
     g.ox = mn[0]; g.oy = mn[1]; g.oz = mn[2]; g.inv = 1.0 / cell;
     bp.grid = g;
     const long long cells = (long long)g.nx * g.ny * g.nz;
     const unsigned nb = (unsigned)((n + 255) / 256);
+    if (bp.trace) { for (int k = 0; k < 8; k++) if (!bp.tev[k]) cudaEventCreate(&bp.tev[k]); cudaEventRecord(bp.tev[0], st); }
     k_bp_keys<<<nb, 256, 0, st>>>(bp.bounds, n, g, bp.sortCells.keys[0], bp.sortCells.vals[0]);
+    if (bp.trace) cudaEventRecord(bp.tev[1], st);
     int bits = 8;
-    while (bits < 32 && (1ll << bits) <= cells) bits += 8;   // keys < cells, the inactive key is all ones
-    bits = 32;                                                // (inactive colliders carry 0xffffffff)
+    while (bits < 32 && (1ll << bits) <= cells) bits += 8;   // keys <= cells (the inactive key)
     int cur = czs::radix_sort(bp.sortCells, n, bits, st, launches);
-    if ((e = cudaMemsetAsync(bp.cellRange, 0, sizeof(uint2) * cells, st)) != cudaSuccess) return e;
+    if (bp.trace) cudaEventRecord(bp.tev[2], st);
+    // only the occupancy bits are cleared: range entries are read for occupied cells only
+    if ((e = cudaMemsetAsync(bp.occ, 0, sizeof(unsigned) * (cells / 32 + 1), st)) != cudaSuccess) return e;
     if ((e = cudaMemsetAsync(bp.counters, 0, sizeof(unsigned long long) * 2, st)) != cudaSuccess) return e;
+    if (bp.trace) cudaEventRecord(bp.tev[3], st);
     k_bp_gather<<<nb, 256, 0, st>>>(bp.bounds, bp.sortCells.vals[cur], n, bp.sorted);
-    k_bp_cells<<<nb, 256, 0, st>>>(bp.sortCells.keys[cur], n, bp.cellRange);
-    k_bp_pairs<<<nb, 256, 0, st>>>(bp.sorted, bp.sortCells.keys[cur], bp.sortCells.vals[cur], n, g, bp.cellRange, bp.pairs, bp.counters, bp.pairCapacity);
+    if (bp.trace) cudaEventRecord(bp.tev[4], st);
+    k_bp_cells<<<nb, 256, 0, st>>>(bp.sortCells.keys[cur], n, (unsigned)cells, bp.cellRange, bp.occ);
+    if (bp.trace) cudaEventRecord(bp.tev[5], st);
+    k_bp_pairs<<<nb, 256, 0, st>>>(bp.sorted, bp.sortCells.keys[cur], bp.sortCells.vals[cur], n, g, bp.cellRange, bp.occ, bp.pairs, bp.counters, bp.pairCapacity);
     if (launches) *launches += 4;
+    if (bp.trace) {
+        cudaEventRecord(bp.tev[6], st);
+        cudaEventSynchronize(bp.tev[6]);
+        for (int k = 0; k < 6; k++) cudaEventElapsedTime(&bp.stageMs[k], bp.tev[k], bp.tev[k + 1]);
+        fprintf(stderr, "[bp] cells %lld (%dx%dx%d) bits %d | keys %.3f sort %.3f memset %.3f gather %.3f cells %.3f pairs %.3f ms\n", cells, g.nx, g.ny, g.nz,
+                bits, bp.stageMs[0], bp.stageMs[1], bp.stageMs[2], bp.stageMs[3], bp.stageMs[4], bp.stageMs[5]);
+    }
     return cudaGetLastError();
 }
 

@@ -98,7 +98,7 @@ static inline bool plan(FusedPlan &fp, int B, int P, int Cc, int nchk, int sched
     fp.worldBytes = wb;
     fp.smemBytes = smem;
     fp.keepContacts = env_int("CUBEZ_FUSED_KEEP_CONTACTS", 1);
-    fp.lockstep = env_int("CUBEZ_FUSED_LOCKSTEP", 1);
+    fp.lockstep = env_int("CUBEZ_FUSED_LOCKSTEP", 3);   // 0 none, 1 frame start, 2 + before narrowphase/resolve, 3 + between the two loops
     fp.coldReals = (size_t)Cc * czr::CW_NCOLD + (size_t)nchk * 8;   // + staging of pair-test contacts
     fp.cold = nullptr;
     return true;
@@ -312,7 +312,7 @@ __global__ void __launch_bounds__(128, MINB) k_world_fused(WorldParams p, FusedP
                 }
             }
             __syncwarp(mask);
-            if (LOCKSTEP) __syncthreads();
+            if (LOCKSTEP && fp.lockstep >= 2) __syncthreads();
 
             // ---- generateContacts (cubedrop.go:42-67), three passes --------------------------------
             // A: every check gets its cheap test: plane checks are evaluated (vertex mask), pair
@@ -452,13 +452,13 @@ __global__ void __launch_bounds__(128, MINB) k_world_fused(WorldParams p, FusedP
             }
             __syncwarp(mask);
             // ---- ResolveContacts(8*len) (cubedrop.go:72-74) -----------------------------------
-            if (LOCKSTEP) __syncthreads();
+            if (LOCKSTEP && fp.lockstep >= 2) __syncthreads();
             int st2 = 0;
             x.nC = nC;
             for (int c = tid; c < nC; c += G) prepare_contact(x, c, gv);
             __syncwarp(mask);
             lastPos = resolve_loop<G, false>(x, nC > 0, nC * 8, tid, &st2);
-            if (LOCKSTEP) __syncthreads();
+            if (LOCKSTEP && fp.lockstep >= 3) __syncthreads();
             lastVel = resolve_loop<G, true>(x, nC > 0, nC * 8, tid, &st2);
             if (st2) status = st2;
             accPos += (unsigned long long)lastPos;

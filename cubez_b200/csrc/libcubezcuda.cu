@@ -1246,6 +1246,7 @@ int cz_bench_broadphase(cz_ctx *ctx, int64_t n, uint64_t seed, double fill, int3
     czbp::Broadphase bp;
     cudaError_t e = czbp::bp_alloc(bp, n, (unsigned long long)n * 8ull + 1024ull, 0, std::max<long long>(1ll << 22, 16 * n));
     if (e != cudaSuccess) { czbp::bp_free(bp); return fail(ctx, CZ_ERR_CUDA, cudaGetErrorString(e)); }
+    bp.trace = getenv("CUBEZ_BP_TRACE") != nullptr;
     const double side = cbrt((double)n * (4.0 / 3.0) * 3.14159265358979323846 / fill);
     float total = 0, totalSort = 0;
     cudaEvent_t s0, s1;
@@ -1265,7 +1266,7 @@ int cz_bench_broadphase(cz_ctx *ctx, int64_t n, uint64_t seed, double fill, int3
         // the radix sort alone, on the same keys
         czbp::k_bp_keys<<<nblk(n, 256), 256, 0, ctx->stream>>>(bp.bounds, n, bp.grid, bp.sortCells.keys[0], bp.sortCells.vals[0]);
         cudaEventRecord(s0, ctx->stream);
-        czs::radix_sort(bp.sortCells, n, 32, ctx->stream, nullptr);
+        { int kb = 8; const long long cells = (long long)bp.grid.nx * bp.grid.ny * bp.grid.nz; while (kb < 32 && (1ll << kb) <= cells) kb += 8; czs::radix_sort(bp.sortCells, n, kb, ctx->stream, nullptr); }
         cudaEventRecord(s1, ctx->stream);
         cudaEventSynchronize(s1);
         float sms = 0;
