@@ -249,3 +249,25 @@ def test_frictionless_one_body_contact_reports_nil_dereference(both):
     with pytest.raises(CubezError) as e:
         gpu.resolve_contacts(8, cs, b, 1.0 / 60.0)
     assert e.value.code == _abi.CZ_ERR_NIL_BODY
+
+
+def test_resolve_static_static_contact_gives_nan_like_the_reference(both):
+    """Two infinite-mass bodies in contact: totalInertia = 0 -> 0/0 = NaN moves (contact.go:329-330).
+    The reference propagates the NaN silently and never selects a NaN contact again; so do we."""
+    gpu, cpu, prec = both
+    b = Bodies.defaults(3, prec)
+    b.inverse_mass[:] = (0, 0, 1); b.inverse_inertia_tensor[2, (0, 4, 8)] = 1
+    b.position[:] = ((0, 0, 0), (0, 0.9, 0), (3, 0, 0))
+    cpu.calculate_derived_data(b)
+    cs = Contacts(2, prec); cs.count = 2
+    cs.body0[:] = (0, 2); cs.body1[:] = (1, -1)
+    cs.normal[:] = ((0, -1, 0), (0, 1, 0)); cs.point[:] = ((0, 0.45, 0), (3, -0.5, 0)); cs.penetration[:] = (0.1, 0.05)
+    cs.friction[:] = 0.9; cs.restitution[:] = 0.1
+    ga, gb, ca, cb = cs.copy(), b.copy(), cs.copy(), b.copy()
+    for x in (ga, ca):
+        x.capacity = 2; x.count = 2
+    with np.errstate(all="ignore"):
+        assert gpu.resolve_contacts(16, ga, gb, 1.0 / 60.0) == cpu.resolve_contacts(16, ca, cb, 1.0 / 60.0)
+    assert_bodies_equal(gb, cb)
+    assert np.isnan(gb.position[0]).any() and not np.isnan(gb.position[2]).any()
+    assert np.array_equal(ga.valid("penetration"), ca.valid("penetration"), equal_nan=True)

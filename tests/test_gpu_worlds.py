@@ -180,3 +180,32 @@ def test_episode_reset_staggered_phases(path):
     for f in STATE_FIELDS:
         assert np.array_equal(getattr(g, f), getattr(c, f)), f
     gpu.close()
+
+
+@pytest.mark.parametrize("path", ["multi", "fused8", "fused32"])
+def test_collider_offsets_and_two_planes(path):
+    """Non-identity collider Offset matrices (colliders.go:43,61) and a second, tilted plane:
+    exercises the full transform = body.transform x Offset product and multi-plane schedules."""
+    scene = scenes.batched_cubedrop(n_worlds=6)
+    rng = np.random.default_rng(11)
+    n = scene.bodies.n
+    off = scene.colliders.offset
+    q = rng.normal(size=(n, 4)); q /= np.linalg.norm(q, axis=1, keepdims=True)
+    w, x, y, z = q.T
+    off[:, 0] = 1 - 2 * y * y - 2 * z * z; off[:, 1] = 2 * x * y + 2 * w * z; off[:, 2] = 2 * x * z - 2 * w * y
+    off[:, 3] = 2 * x * y - 2 * w * z; off[:, 4] = 1 - 2 * x * x - 2 * z * z; off[:, 5] = 2 * y * z + 2 * w * x
+    off[:, 6] = 2 * x * z + 2 * w * y; off[:, 7] = 2 * y * z - 2 * w * x; off[:, 8] = 1 - 2 * x * x - 2 * y * y
+    off[:, 9:12] = rng.uniform(-0.2, 0.2, (n, 3))
+    off[::3] = (1, 0, 0, 0, 1, 0, 0, 0, 1, 0, 0, 0)          # every third collider keeps the identity (fast path)
+    scene.planes = _abi.Planes([[0, 1, 0], [0.6, 0.8, 0.0]], [0.0, -3.0], scene.prec)
+    gpu, cpu = make_world(scene, path), OracleWorld.from_scene(scene)
+    for s in range(0, 200, 20):
+        gs, cs = gpu.step(scene.dt, 20), cpu.step(scene.dt, 20)
+        for k in ("contacts", "pos_iterations", "vel_iterations"):
+            assert gs[k] == cs[k], (s, k, gs[k], cs[k])
+        assert gpu.contact_pairs(3) == cpu.contact_pairs(3)
+    g, c = gpu.download(), cpu.download()
+    for f in STATE_FIELDS + ("transform",):
+        assert np.array_equal(getattr(g, f), getattr(c, f)), f
+    assert np.array_equal(gpu.download_colliders().transform, cpu.download_colliders().transform)
+    gpu.close()
