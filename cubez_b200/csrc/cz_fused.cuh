@@ -49,6 +49,12 @@ struct FusedPlan {
     int lockstep;        // CTA barriers between the phases of a frame (instruction-cache locality)
     real *cold;          // [grid*groupsPerBlock][Cc*CW_NCOLD]
     size_t coldReals;    // per group
+    // split mode: one launch per phase of the frame (A: integrate + narrowphase + prepare, B: position
+    // loop, C: velocity loop); contact state lives in per-WORLD global arrays between the launches
+    int split, splitMinb;
+    real *coldW;         // [W][Cc*CW_NCOLD]
+    real *hotPen, *hotDdv;   // [W][Cc]
+    int *hotCb0, *hotCb1;    // [W][Cc]
 };
 
 static inline size_t world_bytes(int B, int Cc, int nchk) {
@@ -65,7 +71,7 @@ static inline int env_int(const char *name, int dflt) {
 }
 
 // Decide whether (and how) a world shape runs on the fused kernel.
-static inline bool plan(FusedPlan &fp, int B, int P, int Cc, int nchk, int schedule, size_t smemOptin, int smCount) {
+static inline bool plan(FusedPlan &fp, int B, int P, int Cc, int nchk, int schedule, size_t smemOptin, int smCount, int W) {
     (void)P; (void)schedule;
     if (B > 64 || nchk > 1024 || nchk <= 0) return false;
     const size_t wb = world_bytes(B, Cc, nchk);
@@ -87,7 +93,7 @@ static inline bool plan(FusedPlan &fp, int B, int P, int Cc, int nchk, int sched
     if (bps > maxByThreads) bps = maxByThreads;
     int minb = env_int("CUBEZ_FUSED_MINB", 2);     // register budget: 65536 / (128 * MINB) per thread
     if (minb < 2) minb = 2;
-    if (minb > 4) minb = 4;
+    if (minb > 3) minb = 3;
     if (bps > minb * (128 / threads)) bps = minb * (128 / threads);
     fp.minb = minb;
     fp.G = G;
@@ -98,6 +104,16 @@ static inline bool plan(FusedPlan &fp, int B, int P, int Cc, int nchk, int sched
     fp.worldBytes = wb;
     fp.smemBytes = smem;
     fp.keepContacts = env_int("CUBEZ_FUSED_KEEP_CONTACTS", 1);
+    // Large batches run one launch per phase of the frame (every warp of the GPU is then in the same
+    // code region: +15 % on 65 536 worlds); small batches keep the single persistent launch.
+    fp.split = env_int("CUBEZ_FUSED_SPLIT", W >= 8192 ? 1 : 0);
+    fp.splitMinb = env_int("CUBEZ_FUSED_SPLIT_MINB", 2);
+    if (fp.split && G == 8 && fp.splitMinb > 2) {   // more resident blocks for the (smaller) per-phase kernels
+        int b2 = (int)(perSM / (smem + 1024));
+        if (b2 > fp.splitMinb * (128 / threads)) b2 = fp.splitMinb * (128 / threads);
+        if (b2 > bps) bps = b2;
+    }
+    fp.coldW = nullptr; fp.hotPen = fp.hotDdv = nullptr; fp.hotCb0 = fp.hotCb1 = nullptr;
     fp.lockstep = env_int("CUBEZ_FUSED_LOCKSTEP", 3);   // 0 none, 1 frame start, 2 + before narrowphase/resolve, 3 + between the two loops
     fp.coldReals = (size_t)Cc * czr::CW_NCOLD + (size_t)nchk * 8;   // + staging of pair-test contacts
     fp.cold = nullptr;
@@ -204,7 +220,8 @@ __device__ __forceinline__ void stage_world(const Staged &s, const BodyStore &st
 // position | resolve velocity) between CTA barriers, so the warps of a CTA execute the same
 // code region at the same time (the kernel is ~7 k SASS instructions, far larger than the
 // instruction caches; without this every warp is in a different region and fetch-bound).
-template <int G, int MINB, bool LOCKSTEP>
+enum { PH_A = 1, PH_B = 2, PH_C = 4, PH_ALL = 7 };
+template <int G, int MINB, bool LOCKSTEP, int PH>
 __global__ void __launch_bounds__(128, MINB) k_world_fused(WorldParams p, FusedPlan fp, real dt, real bias, int nSteps, unsigned int *nextWorld) {
     using namespace czr;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -224,8 +241,9 @@ __global__ void __launch_bounds__(128, MINB) k_world_fused(WorldParams p, FusedP
     s.queue = s.info + p.nchk;
     s.cnt = (unsigned char *)(s.queue + p.nchk);
     unsigned char *mlist = s.cnt + p.nchk;
-    s.cold = fp.cold + ((size_t)blockIdx.x * fp.groupsPerBlock + grp) * fp.coldReals;
-    s.pairGen = s.cold + (size_t)Cc * CW_NCOLD;
+    real *const groupScratch = fp.cold + ((size_t)blockIdx.x * fp.groupsPerBlock + grp) * fp.coldReals;
+    s.cold = groupScratch;
+    s.pairGen = groupScratch + (size_t)Cc * CW_NCOLD;
     const BodyStore &st = p.st;
 
     Ctx x;
@@ -256,12 +274,28 @@ __global__ void __launch_bounds__(128, MINB) k_world_fused(WorldParams p, FusedP
         const long long gbase = (long long)w * B;
         x.body_base = gbase;
         if (live) stage_world<G>(s, st, gbase, B, tid);
-        __syncwarp(mask);
         int lastC = 0, lastPos = 0, lastVel = 0;
+        if (PH != PH_ALL) {   // split mode: contact state of this world lives in global memory between launches
+            s.cold = fp.coldW + (size_t)w * Cc * CW_NCOLD;
+            x.cold = s.cold; gv.pn = s.cold;
+            if (!(PH & PH_A) && live) {
+                lastC = p.nContacts[w];
+                const int nL = lastC > Cc ? 0 : lastC;
+                const size_t o = (size_t)w * Cc;
+                for (int c = tid; c < nL; c += G) {
+                    s.cb0[c] = fp.hotCb0[o + c]; s.cb1[c] = fp.hotCb1[o + c];
+                    if (PH & PH_B) s.pen[c] = fp.hotPen[o + c];
+                    if (PH & PH_C) s.ddv[c] = fp.hotDdv[o + c];
+                }
+            }
+        }
+        __syncwarp(mask);
 
         for (int stepNo = 0; stepNo < nSteps; stepNo++) {
             const long long step = p.step_index + stepNo;
             if (LOCKSTEP) __syncthreads();
+            int nC = 0;
+            if (PH & PH_A) {
             if (live && episode_wraps(p, w, step)) {   // RL-style episode reset: restore the snapshot
                 stage_world<G>(s, p.snap, gbase, B, tid);
                 for (int b = tid; b < B; b += G) {   // the body transform lives in the global store
@@ -382,7 +416,6 @@ __global__ void __launch_bounds__(128, MINB) k_world_fused(WorldParams p, FusedP
                 }
             }
             __syncwarp(mask);
-            int nC = 0;
             for (int k0 = 0; k0 < p.nchk; k0 += G) {   // pass C: ordered emission (uniform trip count: warp-wide scan)
                 const int k = k0 + tid;
                 const int cnt = (live && k < p.nchk) ? (int)s.cnt[k] : 0;
@@ -453,16 +486,24 @@ __global__ void __launch_bounds__(128, MINB) k_world_fused(WorldParams p, FusedP
             __syncwarp(mask);
             // ---- ResolveContacts(8*len) (cubedrop.go:72-74) -----------------------------------
             if (LOCKSTEP && fp.lockstep >= 2) __syncthreads();
-            int st2 = 0;
             x.nC = nC;
             for (int c = tid; c < nC; c += G) prepare_contact(x, c, gv);
             __syncwarp(mask);
-            lastPos = resolve_loop<G, false>(x, nC > 0, nC * 8, tid, &st2);
+            } else {   // phases B / C of split mode: the contacts were prepared by the phase-A launch
+                nC = lastC > Cc ? 0 : lastC;
+                x.nC = nC;
+            }
+            int st2 = 0;
+            if (PH & PH_B) {
+                lastPos = resolve_loop<G, false>(x, nC > 0, nC * 8, tid, &st2);
+                accPos += (unsigned long long)lastPos;
+            }
             if (LOCKSTEP && fp.lockstep >= 3) __syncthreads();
-            lastVel = resolve_loop<G, true>(x, nC > 0, nC * 8, tid, &st2);
+            if (PH & PH_C) {
+                lastVel = resolve_loop<G, true>(x, nC > 0, nC * 8, tid, &st2);
+                accVel += (unsigned long long)lastVel;
+            }
             if (st2) status = st2;
-            accPos += (unsigned long long)lastPos;
-            accVel += (unsigned long long)lastVel;
             __syncwarp(mask);
         }
 
@@ -488,10 +529,18 @@ __global__ void __launch_bounds__(128, MINB) k_world_fused(WorldParams p, FusedP
             czb::st_m34(st, czb::C_X01, gi, ctr);
             st.awake[gi] = s.fb[BW_AWAKE * B + b] != R_(0) ? 1 : 0;
         }
+        if (PH != PH_ALL && live) {   // hand the contact state to the next phase's launch
+            const int nS = lastC > Cc ? 0 : lastC;
+            const size_t o = (size_t)w * Cc;
+            for (int c = tid; c < nS; c += G) {
+                if (PH & PH_A) { fp.hotCb0[o + c] = s.cb0[c]; fp.hotCb1[o + c] = s.cb1[c]; fp.hotDdv[o + c] = s.ddv[c]; }
+                if (PH & (PH_A | PH_B)) fp.hotPen[o + c] = s.pen[c];
+            }
+        }
         if (tid == 0 && live) {
-            p.nContacts[w] = lastC;
-            p.posIters[w] = lastPos;
-            p.velIters[w] = lastVel;
+            if (PH & PH_A) p.nContacts[w] = lastC;
+            if (PH & PH_B) p.posIters[w] = lastPos;
+            if (PH & PH_C) p.velIters[w] = lastVel;
         }
         __syncwarp(mask);
     }
@@ -504,29 +553,39 @@ __global__ void __launch_bounds__(128, MINB) k_world_fused(WorldParams p, FusedP
     }
 }
 
-// returns 0 or a cudaError_t
-static inline int launch(const FusedPlan &fp, const WorldParams &p, real dt, real bias, int nSteps, unsigned int *nextWorld, cudaStream_t stream) {
+// returns 0 or a cudaError_t.  phases = PH_ALL (persistent over nSteps frames) or one of PH_A/B/C.
+static inline int launch(const FusedPlan &fp, const WorldParams &p, real dt, real bias, int nSteps, unsigned int *nextWorld, cudaStream_t stream,
+                         int phases = PH_ALL) {
     cudaError_t e = cudaMemsetAsync(nextWorld, 0, sizeof(unsigned int), stream);   // stream-ordered before the launch
     if (e != cudaSuccess) return (int)e;
     int grid = fp.grid;
     const int needed = (p.wCount + fp.groupsPerBlock - 1) / fp.groupsPerBlock;
     if (grid > needed) grid = needed;
-#define CZF_LAUNCH(GG, MB, LS)                                                                                        \
+#define CZF_LAUNCH(GG, MB, LS, PHS)                                                                                   \
     do {                                                                                                            \
         if (fp.smemBytes > 48 * 1024)                                                                               \
-            e = cudaFuncSetAttribute(k_world_fused<GG, MB, LS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fp.smemBytes); \
-        if (e == cudaSuccess) k_world_fused<GG, MB, LS><<<grid, fp.threads, fp.smemBytes, stream>>>(p, fp, dt, bias, nSteps, nextWorld); \
+            e = cudaFuncSetAttribute(k_world_fused<GG, MB, LS, PHS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fp.smemBytes); \
+        if (e == cudaSuccess) k_world_fused<GG, MB, LS, PHS><<<grid, fp.threads, fp.smemBytes, stream>>>(p, fp, dt, bias, nSteps, nextWorld); \
     } while (0)
 #define CZF_LAUNCH_G(GG)                                                                                            \
     do {                                                                                                            \
-        if (fp.lockstep) {                                                                                          \
-            if (fp.minb == 2) CZF_LAUNCH(GG, 2, true);                                                              \
-            else if (fp.minb == 3) CZF_LAUNCH(GG, 3, true);                                                         \
-            else CZF_LAUNCH(GG, 4, true);                                                                           \
+        if (phases != PH_ALL && GG == 8 && fp.splitMinb == 3) {                                                     \
+            if (phases == PH_A) CZF_LAUNCH(8, 3, false, PH_A);                                                      \
+            else if (phases == PH_B) CZF_LAUNCH(8, 3, false, PH_B);                                                 \
+            else CZF_LAUNCH(8, 3, false, PH_C);                                                                     \
+        } else if (phases != PH_ALL && GG == 8 && fp.splitMinb == 4) {                                              \
+            if (phases == PH_A) CZF_LAUNCH(8, 4, false, PH_A);                                                      \
+            else if (phases == PH_B) CZF_LAUNCH(8, 4, false, PH_B);                                                 \
+            else CZF_LAUNCH(8, 4, false, PH_C);                                                                     \
+        } else if (phases == PH_A) CZF_LAUNCH(GG, 2, false, PH_A);                                                  \
+        else if (phases == PH_B) CZF_LAUNCH(GG, 2, false, PH_B);                                                    \
+        else if (phases == PH_C) CZF_LAUNCH(GG, 2, false, PH_C);                                                    \
+        else if (fp.lockstep) {                                                                                     \
+            if (fp.minb <= 2) CZF_LAUNCH(GG, 2, true, PH_ALL);                                                      \
+            else CZF_LAUNCH(GG, 3, true, PH_ALL);                                                                   \
         } else {                                                                                                    \
-            if (fp.minb == 2) CZF_LAUNCH(GG, 2, false);                                                             \
-            else if (fp.minb == 3) CZF_LAUNCH(GG, 3, false);                                                        \
-            else CZF_LAUNCH(GG, 4, false);                                                                          \
+            if (fp.minb <= 2) CZF_LAUNCH(GG, 2, false, PH_ALL);                                                     \
+            else CZF_LAUNCH(GG, 3, false, PH_ALL);                                                                  \
         }                                                                                                           \
     } while (0)
     if (fp.G == 8) CZF_LAUNCH_G(8);

@@ -342,10 +342,20 @@ static int world_plan(cz_world *w) {
     w->useFused = false;
     if (!(w->d.flags & CZ_WORLD_NO_FUSED)) {
         if (w->fused.cold) { cudaFree(w->fused.cold); w->fused.cold = nullptr; }
-        w->useFused = !w->useBP && czf::plan(w->fused, B, w->P, Cc, w->nchk, w->d.schedule, ctx->smem_optin, ctx->sm_count);
+        { void *sp[] = {w->fused.coldW, w->fused.hotPen, w->fused.hotDdv, w->fused.hotCb0, w->fused.hotCb1};
+          for (void *q : sp) if (q) cudaFree(q); }
+        w->useFused = !w->useBP && czf::plan(w->fused, B, w->P, Cc, w->nchk, w->d.schedule, ctx->smem_optin, ctx->sm_count, W);
         if (w->useFused) {
             CK(ctx, cudaMalloc(&w->fused.cold, sizeof(real) * w->fused.coldReals * (size_t)w->fused.grid * w->fused.groupsPerBlock));
             if (!w->d_next) CK(ctx, cudaMalloc(&w->d_next, sizeof(unsigned int)));
+            if (w->fused.split) {
+                const size_t WC = (size_t)W * Cc;
+                CK(ctx, cudaMalloc(&w->fused.coldW, sizeof(real) * WC * czr::CW_NCOLD));
+                CK(ctx, cudaMalloc(&w->fused.hotPen, sizeof(real) * WC));
+                CK(ctx, cudaMalloc(&w->fused.hotDdv, sizeof(real) * WC));
+                CK(ctx, cudaMalloc(&w->fused.hotCb0, sizeof(int) * WC));
+                CK(ctx, cudaMalloc(&w->fused.hotCb1, sizeof(int) * WC));
+            }
         }
     }
     return CZ_OK;
@@ -448,7 +458,8 @@ int cz_world_destroy(cz_world *w) {
     if (w->snap.st.base) batch_free(w->snap);
     if (w->d_phase0) cudaFree(w->d_phase0);
     void *ptrs[] = {w->d_one, w->d_two, w->gen, w->gb0, w->gb1, w->nContacts, w->posIters, w->velIters, w->stats,
-                    w->tileCount, w->tileBase, w->hitCount, w->rs.bw, w->rs.cw, w->rs.cb, w->fused.cold, w->d_next};
+                    w->tileCount, w->tileBase, w->hitCount, w->rs.bw, w->rs.cw, w->rs.cb, w->fused.cold, w->d_next,
+                    w->fused.coldW, w->fused.hotPen, w->fused.hotDdv, w->fused.hotCb0, w->fused.hotCb1};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (w->h_stats) cudaFreeHost(w->h_stats);
     if (w->h_pin) cudaFreeHost(w->h_pin);
@@ -719,9 +730,20 @@ int cz_world_step(cz_world *w, cz_real dt, int32_t n_steps, cz_step_stats *stats
     }
     if (w->useFused) {
         WorldParams p = world_params(w);
-        rc = czf::launch(w->fused, p, dt, w->bias, n_steps, w->d_next, ctx->stream);
+        if (w->fused.split) {   // one launch per phase and frame: every warp of the GPU runs the same code region
+            for (int s = 0; s < n_steps && !rc; s++) {
+                p.step_index = w->step_index + s;
+                for (int ph : {czf::PH_A, czf::PH_B, czf::PH_C}) {
+                    rc = czf::launch(w->fused, p, dt, w->bias, 1, w->d_next, ctx->stream, ph);
+                    if (rc) break;
+                    launches++;
+                }
+            }
+        } else {
+            rc = czf::launch(w->fused, p, dt, w->bias, n_steps, w->d_next, ctx->stream);
+            launches++;
+        }
         if (rc) return fail(ctx, CZ_ERR_CUDA, std::string("fused launch: ") + cudaGetErrorString((cudaError_t)rc));
-        launches++;
         w->step_index += n_steps;
     } else {
         for (int s = 0; s < n_steps; s++) {

@@ -209,3 +209,26 @@ def test_collider_offsets_and_two_planes(path):
         assert np.array_equal(getattr(g, f), getattr(c, f)), f
     assert np.array_equal(gpu.download_colliders().transform, cpu.download_colliders().transform)
     gpu.close()
+
+
+def test_split_phase_launches_equal_persistent_kernel():
+    """Large batches run one launch per phase of the frame (contact state in per-world global
+    arrays between launches); it must give exactly the persistent kernel's results."""
+    scene = scenes.batched_cubedrop(n_worlds=96)
+    phase0 = (np.arange(96) * 5) % 140
+    sums = []
+    for split in ("0", "1"):
+        os.environ["CUBEZ_FUSED_SPLIT"] = split
+        try:
+            w = make_world(scene, "fused8")
+        finally:
+            os.environ.pop("CUBEZ_FUSED_SPLIT")
+        w.set_episodes(140, phase0)
+        st = w.step(scene.dt, 300)
+        sums.append((w.checksum_energy()[0], st["contacts"], st["pos_iterations"], st["vel_iterations"], tuple(w.contact_pairs(7))))
+        w.close()
+    assert sums[0] == sums[1]
+    cpu = OracleWorld.from_scene(scene)
+    cpu.set_episodes(140, phase0)
+    cs = cpu.step(scene.dt, 300, n_threads=8)
+    assert sums[1][0] == cpu.checksum_energy()[0] and sums[1][1:4] == (cs["contacts"], cs["pos_iterations"], cs["vel_iterations"])
