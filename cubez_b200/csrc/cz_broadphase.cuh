@@ -4,12 +4,17 @@
 // Pipeline per frame for one large world of n colliders:
 //   k_bp_bounds     centre (collider transform column 3) + bounding radius -> bounds[i] (4 reals),
 //                   and the axis-aligned box of all centres (block reduce + ordered atomics)
-//   k_bp_keys       uniform grid, cell edge >= 2*Rmax*(1+margin): key = linear cell id, value = i
-//   radix sort      4 x 8-bit passes (cz_sort.cuh)
-//   k_bp_gather     bounds in sorted order (so the sweep reads neighbours with locality)
-//   k_bp_cells      cellRange[key] = [first, last) of every non-empty cell
-//   k_bp_pairs      every sorted body sweeps its 27 neighbour cells, inflated inclusive sphere test,
-//                   emits each unordered candidate once (sorted position p < q), warp-ballot compaction
+//   uniform grid, cell edge >= 2*Rmax*(1+margin); key = linear cell id.  Two sorts by cell key:
+//   (default) ONE-PASS radix sort with radix = number of cells (counting sort):
+//     k_bp_count    key of body i, rank of i inside its cell (L2 atomic on the cell counter)
+//     scan          exclusive scan of the counters -> first sorted position of every cell
+//     k_bp_place    body i -> sorted[start[cell] + rank]: one 32-byte sector per body (float centre
+//                   relative to the grid origin, inflated radius, original index, cell coordinates)
+//     k_bp_sweep    every sorted body walks the forward half of its 27-cell neighbourhood as five
+//                   contiguous ranges of the sorted array (a row of cells = consecutive keys) in ONE
+//                   flattened loop, float sphere test, each unordered candidate emitted once
+//   (CUBEZ_BP_SORT=radix) the LSD 8-bit radix sort of cz_sort.cuh:
+//     k_bp_keys -> radix sort -> k_bp_gather -> k_bp_cells -> k_bp_pairs (f64 test)
 //   k_bp_narrow     both ordered checks (i,j) and (j,i) of every candidate through czn::check_pair
 //   k_bp_planes     every collider against every plane (planes bypass the grid)
 //   radix sort      contacts by canonical key (check id * 8 + vertex)  == the reference's append order
@@ -19,7 +24,10 @@
 #pragma once
 #include "cz_kernels.cuh"
 #include "cz_sort.cuh"
+#include <algorithm>
+#include <cmath>
 #include <cstdio>
+#include <cstdlib>
 
 namespace czbp {
 using namespace czm;
@@ -78,12 +86,16 @@ __global__ void k_bp_bounds(BodyStore s, long long n, long long step, Bounds *bo
 }
 
 struct Grid {
-    double ox, oy, oz, inv;   // origin and 1/cell
+    double ox, oy, oz, inv;   // origin and 1/cell (y and z; x too on the radix path)
+    double invx;              // 1/cell along x: rows of cells are contiguous in the sorted array, so the counting path
+                              // makes x-cells as long as the table budget asks and looks up the exact x-range per body
+    double e1;                // float rounding bound of a grid-relative coordinate: extent * 2^-24
+    double rmaxInfl;          // >= every Entry::r
     int nx, ny, nz;
 };
 
 __device__ __forceinline__ void cell_of(const Grid &g, const Bounds &b, int &cx, int &cy, int &cz) {
-    cx = min(max((int)floor(((double)b.x - g.ox) * g.inv), 0), g.nx - 1);
+    cx = min(max((int)floor(((double)b.x - g.ox) * g.invx), 0), g.nx - 1);
     cy = min(max((int)floor(((double)b.y - g.oy) * g.inv), 0), g.ny - 1);
     cz = min(max((int)floor(((double)b.z - g.oz) * g.inv), 0), g.nz - 1);
 }
@@ -173,6 +185,158 @@ __global__ void __launch_bounds__(256) k_bp_pairs(const Bounds *sorted, const un
                         const unsigned long long gslot = atomicAdd(nPairs, 1ull);
                         if (gslot < capacity) pairs[gslot] = pr;
                     }
+                }
+            }
+        }
+    }
+    __syncthreads();
+    const unsigned cnt = min(nStage, (unsigned)BP_STAGE);
+    if (threadIdx.x == 0 && cnt) base = atomicAdd(nPairs, (unsigned long long)cnt);
+    __syncthreads();
+    for (unsigned i = threadIdx.x; i < cnt; i += blockDim.x)
+        if (base + i < capacity) pairs[base + i] = stage[i];
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// One-pass (counting) sort by cell + flattened sweep — the default candidate generator
+// ------------------------------------------------------------------------------------------------
+// One 32-byte sector per sorted body: scattered writes fill whole sectors (no read-modify-write in
+// L2) and the sweep's test needs only the first 16 bytes.
+struct __align__(16) Entry {
+    float x, y, z, r;          // centre relative to the grid origin; radius * BP_MARGIN + float slack, rounded up
+    unsigned idx, cx, cy, cz;  // original collider index, cell coordinates
+};
+static_assert(sizeof(Entry) == 32, "Entry must be one sector");
+
+// L2 residency plan of the counting path: the cell table (4 B per cell, hit at random by one atomic
+// and one load per body) is tagged evict_last; everything that streams through once (bounds, ranks,
+// the scattered sorted entries) is tagged evict_first, so the streams do not push the table out.
+__device__ __forceinline__ unsigned long long l2_evict_last() {
+    unsigned long long p;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ unsigned long long l2_evict_first() {
+    unsigned long long p;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+    return p;
+}
+__device__ __forceinline__ unsigned atom_add_keep(unsigned *a, unsigned v, unsigned long long pol) {
+    unsigned old;
+    asm volatile("atom.global.add.L2::cache_hint.u32 %0, [%1], %2, %3;" : "=r"(old) : "l"(a), "r"(v), "l"(pol) : "memory");
+    return old;
+}
+__device__ __forceinline__ unsigned ld_keep(const unsigned *a, unsigned long long pol) {
+    unsigned v;
+    asm volatile("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(a), "l"(pol));
+    return v;
+}
+// bounds are read once per pass: streaming loads keep the cell table resident in L2
+__device__ __forceinline__ Bounds ld_bounds_stream(const Bounds *p) {
+    Bounds b;
+#ifdef CUBEZ_REAL_FLOAT
+    const float4 v = __ldcs(reinterpret_cast<const float4 *>(p));
+    b.x = v.x; b.y = v.y; b.z = v.z; b.r = v.w;
+#else
+    const double2 v0 = __ldcs(reinterpret_cast<const double2 *>(p)), v1 = __ldcs(reinterpret_cast<const double2 *>(p) + 1);
+    b.x = v0.x; b.y = v0.y; b.z = v1.x; b.r = v1.y;
+#endif
+    return b;
+}
+
+__device__ __forceinline__ bool cell_key(const Grid &g, const Bounds &b, int &cx, int &cy, int &cz, unsigned &key) {
+    if (!(b.r >= R_(0))) return false;   // inactive (r = -1)
+    cell_of(g, b, cx, cy, cz);
+    key = (unsigned)((cz * g.ny + cy) * g.nx + cx);
+    return true;
+}
+
+__global__ void __launch_bounds__(256) k_bp_count(const Bounds *__restrict__ bounds, long long n, Grid g, unsigned *__restrict__ cellCount,
+                                                  unsigned *__restrict__ rank) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const Bounds b = ld_bounds_stream(bounds + i);
+    int cx, cy, cz;
+    unsigned key;
+    if (cell_key(g, b, cx, cy, cz, key)) __stcs(rank + i, atom_add_keep(&cellCount[key], 1u, l2_evict_last()));
+}
+
+// slack: float rounding of the relative centre is <= extent * 2^-24 per coordinate (Grid::e1); each
+// radius carries 4*e1, so the float test accepts every pair the exact inflated test accepts.
+__global__ void __launch_bounds__(256) k_bp_place(const Bounds *__restrict__ bounds, long long n, Grid g, const unsigned *__restrict__ cellStart,
+                                                  const unsigned *__restrict__ rank, Entry *__restrict__ sorted) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const Bounds b = ld_bounds_stream(bounds + i);
+    int cx, cy, cz;
+    unsigned key;
+    if (!cell_key(g, b, cx, cy, cz, key)) return;
+    const unsigned p = ld_keep(cellStart + key, l2_evict_last()) + __ldcs(rank + i);
+    const float x = (float)((double)b.x - g.ox), y = (float)((double)b.y - g.oy), z = (float)((double)b.z - g.oz);
+    const float r = __double2float_ru(((double)b.r * BP_MARGIN + 4.0 * g.e1) * 1.000002);   // 2e-6: the float roundings of the test itself
+    // ONE 256-bit store: the scattered write fills its sector, so L2 never fetches it first
+    const unsigned long long w0 = (unsigned long long)__float_as_uint(x) | ((unsigned long long)__float_as_uint(y) << 32);
+    const unsigned long long w1 = (unsigned long long)__float_as_uint(z) | ((unsigned long long)__float_as_uint(r) << 32);
+    const unsigned long long w2 = (unsigned long long)(unsigned)i | ((unsigned long long)(unsigned)cx << 32);
+    const unsigned long long w3 = (unsigned long long)(unsigned)cy | ((unsigned long long)(unsigned)cz << 32);
+    asm volatile("st.global.L2::cache_hint.v4.b64 [%0], {%1,%2,%3,%4}, %5;" ::"l"(sorted + p), "l"(w0), "l"(w1), "l"(w2), "l"(w3), "l"(l2_evict_first()) : "memory");
+}
+
+__global__ void __launch_bounds__(256) k_bp_sweep(const Entry *__restrict__ sorted, long long n, Grid g, const unsigned *__restrict__ cellStart,
+                                                  uint2 *pairs, unsigned long long *nPairs, unsigned long long capacity) {
+    __shared__ uint2 stage[BP_STAGE];
+    __shared__ unsigned nStage;
+    __shared__ unsigned long long base;
+    if (threadIdx.x == 0) nStage = 0;
+    __syncthreads();
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const unsigned cells = (unsigned)(g.nx * g.ny * g.nz);
+    const unsigned nActive = cellStart[cells];
+    if (p < (long long)nActive) {
+        const float4 me = *reinterpret_cast<const float4 *>(sorted + p);
+        const uint4 mi = *(reinterpret_cast<const uint4 *>(sorted + p) + 1);
+        const int cx = (int)mi.y, cy = (int)mi.z, cz = (int)mi.w;
+        // x-cells that can hold a partner: every centre within my radius + the largest radius (+ rounding slack)
+        const double reach = ((double)me.w + g.rmaxInfl) * 1.000002 + 8.0 * g.e1;
+        const int xl = min(max((int)floor(((double)me.x - reach) * g.invx), 0), cx);
+        const int xh = max(min((int)floor(((double)me.x + reach) * g.invx), g.nx - 1), cx);
+        // five contiguous ranges of the sorted array: the own row from the body after me to the end
+        // of cell xh, and the rows (dz,dy) = (0,+1), (+1,-1), (+1,0), (+1,+1) over cells xl..xh
+        unsigned a0, e0, a1 = 0, e1 = 0, a2 = 0, e2 = 0, a3 = 0, e3 = 0, a4 = 0, e4 = 0;
+        const unsigned rowOwn = (unsigned)((cz * g.ny + cy) * g.nx);
+        a0 = (unsigned)p + 1u;
+        e0 = cellStart[rowOwn + xh + 1];
+        const bool yUp = cy + 1 < g.ny, yDn = cy > 0, zUp = cz + 1 < g.nz;
+        if (yUp) { const unsigned r = rowOwn + g.nx; a1 = cellStart[r + xl]; e1 = cellStart[r + xh + 1]; }
+        if (zUp) {
+            const unsigned rz = rowOwn + (unsigned)(g.nx * g.ny);
+            a3 = cellStart[rz + xl]; e3 = cellStart[rz + xh + 1];
+            if (yDn) { const unsigned r = rz - g.nx; a2 = cellStart[r + xl]; e2 = cellStart[r + xh + 1]; }
+            if (yUp) { const unsigned r = rz + g.nx; a4 = cellStart[r + xl]; e4 = cellStart[r + xh + 1]; }
+        }
+        // one flattened loop over the five ranges: a warp iterates to the longest TOTAL of its lanes,
+        // not to the sum of the per-row maxima.  The flat counter k maps to a sorted position through a
+        // branch-free select chain (a divergent "next range" branch ran once per lane and range).
+        const unsigned c1 = e0 - a0, c2 = c1 + (e1 - a1), c3 = c2 + (e2 - a2), c4 = c3 + (e3 - a3), total = c4 + (e4 - a4);
+        const unsigned o0 = a0, o1 = a1 - c1, o2 = a2 - c2, o3 = a3 - c3, o4 = a4 - c4;
+        for (unsigned k = 0; k < total; k++) {
+            unsigned off = k < c1 ? o0 : o1;
+            off = k < c2 ? off : o2;
+            off = k < c3 ? off : o3;
+            off = k < c4 ? off : o4;
+            const unsigned q = off + k;
+            const float4 ob = *reinterpret_cast<const float4 *>(sorted + q);
+            const float dx = ob.x - me.x, dy = ob.y - me.y, dz = ob.z - me.z;
+            const float rr = ob.w + me.w;
+            const float d2 = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, dx * dx));
+            if (d2 <= rr * rr) {
+                const uint2 pr = make_uint2(mi.x, sorted[q].idx);
+                const unsigned slot = atomicAdd(&nStage, 1u);
+                if (slot < BP_STAGE) stage[slot] = pr;
+                else {   // staging full: straight to global
+                    const unsigned long long gslot = atomicAdd(nPairs, 1ull);
+                    if (gslot < capacity) pairs[gslot] = pr;
                 }
             }
         }
@@ -276,9 +440,13 @@ struct Broadphase {
     long long *box = nullptr;            // device [8]
     long long *h_box = nullptr;          // pinned [8]
     czs::RadixBuffers<unsigned> sortCells{};
-    uint2 *cellRange = nullptr;
+    uint2 *cellRange = nullptr;          // radix path: [first,last) per cell; counting path: reused as cellStart (unsigned[2*cap])
     unsigned *occ = nullptr;             // occupancy bit per cell
     long long cellCapacity = 0;
+    Entry *entries = nullptr;            // counting path: one sector per sorted body
+    unsigned *rank = nullptr;            // counting path: rank of body i inside its cell
+    unsigned *scanScratch = nullptr;
+    bool useRadix = false;               // CUBEZ_BP_SORT=radix
     uint2 *pairs = nullptr;
     unsigned long long pairCapacity = 0;
     unsigned long long *counters = nullptr;      // device [2]: nPairs, nContacts
@@ -306,6 +474,10 @@ static inline cudaError_t bp_alloc(Broadphase &bp, long long n, unsigned long lo
     bp.cellCapacity = maxCells;
     BPCK(cudaMalloc(&bp.cellRange, sizeof(uint2) * maxCells));
     BPCK(cudaMalloc(&bp.occ, sizeof(unsigned) * (maxCells / 32 + 1)));
+    BPCK(cudaMalloc(&bp.entries, sizeof(Entry) * n));
+    BPCK(cudaMalloc(&bp.rank, sizeof(unsigned) * n));
+    BPCK(cudaMalloc(&bp.scanScratch, sizeof(unsigned) * (size_t)czs::scan_scratch_elems(maxCells + 1)));
+    { const char *m = getenv("CUBEZ_BP_SORT"); bp.useRadix = m && m[0] == 'r'; }
     bp.pairCapacity = pairCap;
     BPCK(cudaMalloc(&bp.pairs, sizeof(uint2) * pairCap));
     BPCK(cudaMalloc(&bp.counters, sizeof(unsigned long long) * 2));
@@ -327,6 +499,9 @@ static inline void bp_free(Broadphase &bp) {
     czs::radix_free(bp.sortCells);
     if (bp.cellRange) cudaFree(bp.cellRange);
     if (bp.occ) cudaFree(bp.occ);
+    if (bp.entries) cudaFree(bp.entries);
+    if (bp.rank) cudaFree(bp.rank);
+    if (bp.scanScratch) cudaFree(bp.scanScratch);
     if (bp.pairs) cudaFree(bp.pairs);
     if (bp.counters) cudaFree(bp.counters);
     if (bp.h_counters) cudaFreeHost(bp.h_counters);
@@ -356,35 +531,87 @@ static inline cudaError_t bp_candidates(Broadphase &bp, cudaStream_t st, long lo
     double rmax = unord(bp.h_box[6]);
     if (!(rmax > 0)) rmax = 1.0;
     if (!(mx[0] >= mn[0])) { for (int k = 0; k < 3; k++) { mn[k] = 0; mx[k] = 0; } }
-    // cell edge = 2 x the minimum (2*Rmax): at a few % volume fill the minimum-size grid is ~10 cells
-    // per body, and its table (memset + scattered writes + 14 lookups per body) costs more than the
-    // extra distance tests of a slightly coarser grid (measured at 16 Mi spheres, 5 % fill; see profiles/)
-    double scale = 1.3;
-    if (const char *e = getenv("CUBEZ_BP_CELL_SCALE")) { double sc = atof(e); if (sc >= 1.0 && sc <= 8.0) scale = sc; }
-    double cell = 2.0 * rmax * BP_MARGIN * 1.0001 * scale;
+    const double extent = std::max(mx[0] - mn[0], std::max(mx[1] - mn[1], mx[2] - mn[2]));
+    const double e1 = extent * (1.0 / 16777216.0);
     Grid g;
-    for (;;) {
-        g.nx = (int)floor((mx[0] - mn[0]) / cell) + 1; g.ny = (int)floor((mx[1] - mn[1]) / cell) + 1; g.nz = (int)floor((mx[2] - mn[2]) / cell) + 1;
-        if ((double)g.nx * g.ny * g.nz <= (double)bp.cellCapacity) break;
-        cell *= 1.26;   // coarser cells: more candidates, never fewer
-    }
-    // one radix pass less when a slightly coarser grid brings the key width under a byte boundary
-    for (int tries = 0; tries < 4; tries++) {
-        const double c = (double)g.nx * g.ny * g.nz + 1.0;
-        int kb = 1;
-        while ((double)(1ull << kb) < c) kb++;
-        const int over = kb % 8;   // bits above the last full byte
-        if (over == 0 || over > 2) break;
-        const double cell2 = cell * 1.26;
-        Grid h = g;
-        h.nx = (int)floor((mx[0] - mn[0]) / cell2) + 1; h.ny = (int)floor((mx[1] - mn[1]) / cell2) + 1; h.nz = (int)floor((mx[2] - mn[2]) / cell2) + 1;
-        cell = cell2; g = h;
+    g.e1 = e1;
+    double cell;
+    auto dims = [&](double c, Grid &h) {
+        h.nx = (int)floor((mx[0] - mn[0]) / c) + 1; h.ny = (int)floor((mx[1] - mn[1]) / c) + 1; h.nz = (int)floor((mx[2] - mn[2]) / c) + 1;
+        return (double)h.nx * h.ny * h.nz;
+    };
+    if (bp.useRadix) {
+        // cell edge = 1.3 x the minimum (2*Rmax): at a few % volume fill the minimum-size grid is ~10 cells
+        // per body, and its table (memset + scattered writes + 14 lookups per body) costs more than the
+        // extra distance tests of a slightly coarser grid (measured at 16 Mi spheres, 5 % fill; see profiles/)
+        double scale = 1.3;
+        if (const char *ev = getenv("CUBEZ_BP_CELL_SCALE")) { double sc = atof(ev); if (sc >= 1.0 && sc <= 8.0) scale = sc; }
+        cell = 2.0 * rmax * BP_MARGIN * 1.0001 * scale;
+        while (dims(cell, g) > (double)bp.cellCapacity) cell *= 1.26;   // coarser cells: more candidates, never fewer
+        // one radix pass less when a slightly coarser grid brings the key width under a byte boundary
+        for (int tries = 0; tries < 4; tries++) {
+            const double c = (double)g.nx * g.ny * g.nz + 1.0;
+            int kb = 1;
+            while ((double)(1ull << kb) < c) kb++;
+            const int over = kb % 8;   // bits above the last full byte
+            if (over == 0 || over > 2) break;
+            cell *= 1.26;
+            dims(cell, g);
+        }
+    } else {
+        // Counting sort.  y and z cells take the minimum edge (3x3 rows of cells around a body; the edge
+        // covers the inflated float test of k_bp_sweep: 2*(Rmax*margin + 4*e1) plus the distance slack).
+        // A row of x-cells is one contiguous range of the sorted array and k_bp_sweep looks up the exact
+        // x-interval per body, so the x edge is free: it is set by the table budget (~cellsPerBody cells per
+        // collider; the table is memset, hit by one atomic per body, scanned and streamed by the sweep).
+        // Tests per body ~ 4.5 * (2R + ex) * eyz^2 * density: minimal eyz is optimal for any budget.
+        double cpb = 1.0;
+        if (const char *ev = getenv("CUBEZ_BP_CELLS_PER_BODY")) { double v = atof(ev); if (v >= 0.01 && v <= 64.0) cpb = v; }
+        const double minEdge = 2.0 * (rmax * BP_MARGIN + 4.0 * e1) * 1.0001 + 4.0 * e1;
+        const double target = std::min((double)bp.cellCapacity - 1.0, std::max(4096.0, cpb * (double)n));
+        cell = minEdge;
+        auto rows = [&](double c) { g.ny = (int)floor((mx[1] - mn[1]) / c) + 1; g.nz = (int)floor((mx[2] - mn[2]) / c) + 1; return (double)g.ny * g.nz; };
+        if (rows(cell) > target) {
+            const double ly = mx[1] - mn[1], lz = mx[2] - mn[2];
+            if (ly > cell && lz > cell) cell = std::max(cell, sqrt(ly * lz / target));
+            while (rows(cell) > target) cell *= 1.02;
+        }
+        const double lx = mx[0] - mn[0];
+        double nxd = floor(target / ((double)g.ny * g.nz));
+        nxd = std::min(nxd, floor(lx / (minEdge * 0.25)) + 1.0);   // finer than a quarter of the reach buys nothing
+        g.nx = (int)std::max(1.0, std::min(nxd, 2147483647.0));
+        const double ex = lx > 0 ? lx / g.nx : 1.0;
+        g.invx = 1.0 / ex;
+        g.rmaxInfl = (double)(float)((rmax * BP_MARGIN + 4.0 * e1) * 1.000002) * 1.000001;
     }
     g.ox = mn[0]; g.oy = mn[1]; g.oz = mn[2]; g.inv = 1.0 / cell;
+    if (bp.useRadix) { g.invx = g.inv; g.rmaxInfl = rmax * BP_MARGIN; }
     bp.grid = g;
     const long long cells = (long long)g.nx * g.ny * g.nz;
     const unsigned nb = (unsigned)((n + 255) / 256);
     if (bp.trace) { for (int k = 0; k < 8; k++) if (!bp.tev[k]) cudaEventCreate(&bp.tev[k]); cudaEventRecord(bp.tev[0], st); }
+    if (!bp.useRadix) {
+        unsigned *cellStart = reinterpret_cast<unsigned *>(bp.cellRange);
+        if ((e = cudaMemsetAsync(cellStart, 0, sizeof(unsigned) * (cells + 1), st)) != cudaSuccess) return e;
+        if ((e = cudaMemsetAsync(bp.counters, 0, sizeof(unsigned long long) * 2, st)) != cudaSuccess) return e;
+        if (bp.trace) cudaEventRecord(bp.tev[1], st);
+        k_bp_count<<<nb, 256, 0, st>>>(bp.bounds, n, g, cellStart, bp.rank);
+        if (bp.trace) cudaEventRecord(bp.tev[2], st);
+        int l = czs::exclusive_scan_u32(cellStart, cells + 1, bp.scanScratch, st);
+        if (bp.trace) cudaEventRecord(bp.tev[3], st);
+        k_bp_place<<<nb, 256, 0, st>>>(bp.bounds, n, g, cellStart, bp.rank, bp.entries);
+        if (bp.trace) cudaEventRecord(bp.tev[4], st);
+        k_bp_sweep<<<nb, 256, 0, st>>>(bp.entries, n, g, cellStart, bp.pairs, bp.counters, bp.pairCapacity);
+        if (launches) *launches += 3 + l;
+        if (bp.trace) {
+            cudaEventRecord(bp.tev[5], st);
+            cudaEventSynchronize(bp.tev[5]);
+            for (int k = 0; k < 5; k++) cudaEventElapsedTime(&bp.stageMs[k], bp.tev[k], bp.tev[k + 1]);
+            fprintf(stderr, "[bp] cells %lld (%dx%dx%d) | memset %.3f count %.3f scan %.3f place %.3f sweep %.3f ms\n", cells, g.nx, g.ny, g.nz,
+                    bp.stageMs[0], bp.stageMs[1], bp.stageMs[2], bp.stageMs[3], bp.stageMs[4]);
+        }
+        return cudaGetLastError();
+    }
     k_bp_keys<<<nb, 256, 0, st>>>(bp.bounds, n, g, bp.sortCells.keys[0], bp.sortCells.vals[0]);
     if (bp.trace) cudaEventRecord(bp.tev[1], st);
     int bits = 8;
