@@ -234,9 +234,9 @@ def main():
         ctx.check(ctx.lib.cz_bench_broadphase(ctx.h, K1_BODIES, 7, 0.05, 2, 5, C.byref(ms2), C.byref(pairs), C.byref(sms)))
         alg = 148 * K1_BODIES + 8 * pairs.value          # 148 n + 8 q bytes (f64 bounds, 4-pass radix sort)
         ach2 = alg / (ms2.value * 1e-3) / 1e9
-        roofline_k2 = {"bound": "hbm", "kernel": "K2 sort-based broadphase (keys, radix sort, gather, cell ranges, neighbour sweep): 16Mi unit spheres, 5% fill",
+        roofline_k2 = {"bound": "hbm", "kernel": "K2 sort-based broadphase (one-pass counting sort by cell key: count, scan, place; neighbour sweep): 16Mi unit spheres, 5% fill",
                        "achieved": ach2, "peak": peak, "unit": "GB/s", "frac": ach2 / peak, "traffic": None, "peak_kind": peak_kind,
-                       "ms_per_frame": ms2.value, "radix_sort_ms": sms.value, "candidate_pairs": pairs.value}
+                       "ms_per_frame": ms2.value, "lsd_radix_sort_alone_ms": sms.value, "candidate_pairs": pairs.value}
 
     if rank == 0:
         cpu_value, cpu_s = cpu_oracle_sample(256, 1)
@@ -250,7 +250,7 @@ def main():
                        "l2": "state (%.0f MB/GPU) larger than L2; frames of one call run from shared memory" % (nb * 84 * 16 / 1e6)},
             "body_steps_per_s": value * BODIES_PER_WORLD,
             "e2e": {"value": e2e_value, "unit": "world-steps/s", "h2d_bytes_per_step": h2d * world_size, "d2h_bytes_per_step": d2h * world_size,
-                    "ms_per_step": e2e_ms, "api": "cz_world_step_host: pinned host arrays, 1 frame per call, 8-chunk H2D | step | D2H pipeline on 3 streams"},
+                    "ms_per_step": e2e_ms, "api": "cz_world_step_host: pinned host arrays (full body state in, full body state out), 1 frame per call, 8-chunk H2D | pack+step+unpack | D2H pipeline, 3 compute streams"},
             "gpu_launches": int(red["counters"]["launches"]),
             "clocks": sampler.summary(),
             "roofline": roofline,

@@ -10,6 +10,7 @@
 //
 // No CPU fallback exists in this file: every compute entry point launches CUDA kernels and
 // returns CZ_ERR_CUDA when the runtime reports an error (e.g. no device).
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -264,13 +265,15 @@ struct cz_world {
     struct HostPipe {
         bool ready = false;
         int chunks = 1;
-        cudaStream_t sUp = nullptr, sDown = nullptr, sComp2 = nullptr;   // sComp2: odd chunks, so kernel tails overlap
+        cudaStream_t sUp = nullptr, sDown = nullptr;
+        int nComp = 1;                               // compute streams: chunk c runs on stream c % nComp, so kernel tails overlap
+        cudaStream_t sComp[4] = {nullptr, nullptr, nullptr, nullptr};   // [0] is the context stream
         std::vector<cudaEvent_t> evUp, evComp;
         cudaEvent_t evBegin = nullptr, evDownDone = nullptr;
         real *dIn = nullptr, *dOut = nullptr;        // per-field device staging
         uint8_t *dFlags = nullptr;                   // awake_in, can_sleep_in, awake_out
         unsigned int *dNext = nullptr;               // per-chunk world counters
-        real *cold2 = nullptr;                       // second cold-contact scratch: odd chunks run concurrently with even ones
+        real *coldX[4] = {nullptr, nullptr, nullptr, nullptr};   // cold-contact scratch per extra compute stream (kernels of different chunks co-run)
     } pipe;
     real *h_pin = nullptr;
     size_t h_pin_bytes = 0;
@@ -464,11 +467,11 @@ int cz_world_destroy(cz_world *w) {
     if (w->h_stats) cudaFreeHost(w->h_stats);
     if (w->h_pin) cudaFreeHost(w->h_pin);
     if (w->pipe.ready) {
-        cudaStreamDestroy(w->pipe.sUp); cudaStreamDestroy(w->pipe.sDown); cudaStreamDestroy(w->pipe.sComp2);
+        cudaStreamDestroy(w->pipe.sUp); cudaStreamDestroy(w->pipe.sDown); for (int k = 1; k < w->pipe.nComp; k++) cudaStreamDestroy(w->pipe.sComp[k]);
         for (auto e : w->pipe.evUp) cudaEventDestroy(e);
         for (auto e : w->pipe.evComp) cudaEventDestroy(e);
         cudaEventDestroy(w->pipe.evBegin); cudaEventDestroy(w->pipe.evDownDone);
-        cudaFree(w->pipe.dIn); cudaFree(w->pipe.dOut); cudaFree(w->pipe.dFlags); cudaFree(w->pipe.dNext); if (w->pipe.cold2) cudaFree(w->pipe.cold2);
+        cudaFree(w->pipe.dIn); cudaFree(w->pipe.dOut); cudaFree(w->pipe.dFlags); cudaFree(w->pipe.dNext); for (int k = 1; k < 4; k++) if (w->pipe.coldX[k]) cudaFree(w->pipe.coldX[k]);
     }
     delete w;
     return CZ_OK;
@@ -868,7 +871,9 @@ static int host_pipe_init(cz_world *w) {
     pp.chunks = chunks;
     CK(ctx, cudaStreamCreateWithFlags(&pp.sUp, cudaStreamNonBlocking));
     CK(ctx, cudaStreamCreateWithFlags(&pp.sDown, cudaStreamNonBlocking));
-    CK(ctx, cudaStreamCreateWithFlags(&pp.sComp2, cudaStreamNonBlocking));
+    pp.nComp = w->useFused ? std::min(4, std::max(1, czf::env_int("CUBEZ_HOST_COMP_STREAMS", 3))) : 1;
+    pp.sComp[0] = ctx->stream;
+    for (int k = 1; k < pp.nComp; k++) CK(ctx, cudaStreamCreateWithFlags(&pp.sComp[k], cudaStreamNonBlocking));
     pp.evUp.resize(chunks); pp.evComp.resize(chunks);
     for (int c = 0; c < chunks; c++) {
         CK(ctx, cudaEventCreateWithFlags(&pp.evUp[c], cudaEventDisableTiming));
@@ -880,7 +885,7 @@ static int host_pipe_init(cz_world *w) {
     CK(ctx, cudaMalloc(&pp.dOut, sizeof(real) * NB * 38));   // pos3 ori4 vel3 rot3 motion1 lacc3 tr12 iitw9
     CK(ctx, cudaMalloc(&pp.dFlags, 3 * (size_t)NB));
     CK(ctx, cudaMalloc(&pp.dNext, sizeof(unsigned int) * chunks));
-    if (w->useFused) CK(ctx, cudaMalloc(&pp.cold2, sizeof(real) * w->fused.coldReals * (size_t)w->fused.grid * w->fused.groupsPerBlock));
+    for (int k = 1; k < pp.nComp; k++) CK(ctx, cudaMalloc(&pp.coldX[k], sizeof(real) * w->fused.coldReals * (size_t)w->fused.grid * w->fused.groupsPerBlock));
     pp.ready = true;
     return CZ_OK;
 }
@@ -896,12 +901,10 @@ int cz_world_step_host(cz_world *w, cz_bodies *io, cz_real dt, int32_t n_steps, 
     if ((w->d.flags & CZ_WORLD_FUSED) && !w->useFused)
         return fail(ctx, CZ_ERR_INVALID, "CZ_WORLD_FUSED requested but the world does not fit the fused kernel");
     int rc;
-    // damping: only touched (and the Pow factors refreshed) when the host changed it
+    // damping: only touched (and the Pow factors refreshed) when the host changed it.  The comparison
+    // runs per chunk inside the pipeline loop (8 MB of memcmp up front cost ~0.5 ms of idle GPU).
     cz_bodies damp{};
     damp.n = io->n; damp.linear_damping = io->linear_damping; damp.angular_damping = io->angular_damping;
-    bool changed = (io->linear_damping && std::memcmp(w->b.h_lind.data(), io->linear_damping, sizeof(real) * io->n) != 0) ||
-                   (io->angular_damping && std::memcmp(w->b.h_angd.data(), io->angular_damping, sizeof(real) * io->n) != 0);
-    if (changed && (rc = upload_bodies(w->b, 0, io->n, &damp))) return rc;
     if ((rc = world_prepare_step(w, dt))) return rc;
     if ((rc = host_pipe_init(w))) return rc;
     auto &pp = w->pipe;
@@ -913,26 +916,52 @@ int cz_world_step_host(cz_world *w, cz_bodies *io, cz_real dt, int32_t n_steps, 
     uint8_t *fAwake = pp.dFlags, *fSleep = fAwake + NB, *fAwakeOut = fSleep + NB;
     HostIn hin{dPos, dOri, dVel, dRot, dAcc, dIitb, dMot, fAwake, fSleep};
     HostOut hout{oPos, oOri, oVel, oRot, oMot, oLacc, oTr, oIitw, fAwakeOut};
+    static const bool hostTrace = getenv("CUBEZ_HOST_TRACE") != nullptr;
+    const auto tc0 = std::chrono::steady_clock::now();
     CK(ctx, cudaMemsetAsync(w->stats, 0, sizeof(unsigned long long) * ST_N, ctx->stream));
     CK(ctx, cudaMemsetAsync(pp.dNext, 0, sizeof(unsigned int) * pp.chunks, ctx->stream));
     CK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
     CK(ctx, cudaEventRecord(pp.evBegin, ctx->stream));
     CK(ctx, cudaStreamWaitEvent(pp.sUp, pp.evBegin, 0));     // staging buffers of the previous call are free
     CK(ctx, cudaStreamWaitEvent(pp.sDown, pp.evBegin, 0));
-    CK(ctx, cudaStreamWaitEvent(pp.sComp2, pp.evBegin, 0));
+    for (int k = 1; k < pp.nComp; k++) CK(ctx, cudaStreamWaitEvent(pp.sComp[k], pp.evBegin, 0));
     long long launches = 0;
+    std::vector<cudaEvent_t> trEv;   // trace only: [chunk][up end, compute begin, compute end, down end]
+    if (hostTrace) { trEv.resize((size_t)pp.chunks * 4); for (auto &e : trEv) cudaEventCreate(&e); }
 #define UP(dst, src, comps) CK(ctx, cudaMemcpyAsync((dst) + b0 * (comps), (src) + b0 * (comps), sizeof(*(src)) * nb * (comps), cudaMemcpyHostToDevice, pp.sUp))
 #define DOWN(dst, src, comps) CK(ctx, cudaMemcpyAsync((dst) + b0 * (comps), (src) + b0 * (comps), sizeof(*(src)) * nb * (comps), cudaMemcpyDeviceToHost, pp.sDown))
+    // chunk boundaries: short first and last chunks (pipeline fill = first upload, drain = last download)
+    std::vector<int> wEdge(pp.chunks + 1, 0);
+    {
+        std::vector<double> wt(pp.chunks, 1.0);
+        if (pp.chunks >= 4 && !czf::env_int("CUBEZ_HOST_EVEN_CHUNKS", 0)) { wt[0] = wt[pp.chunks - 1] = 0.5; wt[1] = wt[pp.chunks - 2] = 0.85; }
+        double tot = 0, run = 0;
+        for (double v : wt) tot += v;
+        for (int c = 0; c < pp.chunks; c++) { run += wt[c]; wEdge[c + 1] = (int)((double)W * run / tot + 0.5); }
+        wEdge[pp.chunks] = W;
+    }
     for (int c = 0; c < pp.chunks; c++) {
-        const int w0 = (int)((long long)W * c / pp.chunks), w1 = (int)((long long)W * (c + 1) / pp.chunks);
+        const int w0 = wEdge[c], w1 = wEdge[c + 1];
         const long long b0 = w0 * B, nb = (w1 - w0) * B;
-        if (nb == 0) continue;
+        if (nb <= 0) continue;
         UP(dPos, io->position, 3); UP(dOri, io->orientation, 4); UP(dVel, io->velocity, 3); UP(dRot, io->rotation, 3);
         UP(dAcc, io->acceleration, 3); UP(dIitb, io->inverse_inertia_tensor, 9); UP(dMot, io->motion, 1);
         UP(fAwake, io->is_awake, 1); UP(fSleep, io->can_sleep, 1);
         CK(ctx, cudaEventRecord(pp.evUp[c], pp.sUp));
-        cudaStream_t cs = (w->useFused && (c & 1)) ? pp.sComp2 : ctx->stream;
+        if (hostTrace) cudaEventRecord(trEv[c * 4 + 0], pp.sUp);
+        // this chunk's damping slice, compared while its upload is in flight
+        if ((io->linear_damping && std::memcmp(w->b.h_lind.data() + b0, io->linear_damping + b0, sizeof(real) * nb) != 0) ||
+            (io->angular_damping && std::memcmp(w->b.h_angd.data() + b0, io->angular_damping + b0, sizeof(real) * nb) != 0)) {
+            // rare: the host changed damping.  Drain the compute streams, refresh every Pow factor, go on.
+            CK(ctx, cudaStreamSynchronize(ctx->stream));
+            for (int k = 1; k < pp.nComp; k++) CK(ctx, cudaStreamSynchronize(pp.sComp[k]));
+            if ((rc = upload_bodies(w->b, 0, io->n, &damp))) return rc;
+            if ((rc = world_prepare_step(w, dt))) return rc;
+            CK(ctx, cudaStreamSynchronize(ctx->stream));
+        }
+        cudaStream_t cs = pp.sComp[c % pp.nComp];
         CK(ctx, cudaStreamWaitEvent(cs, pp.evUp[c], 0));
+        if (hostTrace) cudaEventRecord(trEv[c * 4 + 1], cs);
         k_pack_all<<<nblk(nb, 256), 256, 0, cs>>>(w->b.st, b0, nb, hin);
         CKL(ctx);
         launches++;
@@ -940,10 +969,21 @@ int cz_world_step_host(cz_world *w, cz_bodies *io, cz_real dt, int32_t n_steps, 
             WorldParams p = world_params(w);
             p.wFirst = w0; p.wCount = w1 - w0;
             czf::FusedPlan fpl = w->fused;
-            if (c & 1) fpl.cold = pp.cold2;
-            rc = czf::launch(fpl, p, dt, w->bias, n_steps, pp.dNext + c, cs);
+            if (c % pp.nComp) fpl.cold = pp.coldX[c % pp.nComp];
+            if (w->fused.split && !czf::env_int("CUBEZ_HOST_NO_SPLIT", 0)) {   // one launch per phase and frame, as cz_world_step does for large batches
+                for (int s2 = 0; s2 < n_steps && !rc; s2++) {
+                    p.step_index = w->step_index + s2;
+                    for (int ph : {czf::PH_A, czf::PH_B, czf::PH_C}) {
+                        rc = czf::launch(fpl, p, dt, w->bias, 1, pp.dNext + c, cs, ph);
+                        if (rc) break;
+                        launches++;
+                    }
+                }
+            } else {
+                rc = czf::launch(fpl, p, dt, w->bias, n_steps, pp.dNext + c, cs);
+                launches++;
+            }
             if (rc) return fail(ctx, CZ_ERR_CUDA, std::string("fused launch: ") + cudaGetErrorString((cudaError_t)rc));
-            launches++;
         } else {
             const long long keep = w->step_index;
             for (int s = 0; s < n_steps; s++) {
@@ -956,10 +996,12 @@ int cz_world_step_host(cz_world *w, cz_bodies *io, cz_real dt, int32_t n_steps, 
         CKL(ctx);
         launches++;
         CK(ctx, cudaEventRecord(pp.evComp[c], cs));
+        if (hostTrace) cudaEventRecord(trEv[c * 4 + 2], cs);
         CK(ctx, cudaStreamWaitEvent(pp.sDown, pp.evComp[c], 0));
         DOWN(io->position, oPos, 3); DOWN(io->orientation, oOri, 4); DOWN(io->velocity, oVel, 3); DOWN(io->rotation, oRot, 3);
         DOWN(io->motion, oMot, 1); DOWN(io->last_frame_acceleration, oLacc, 3); DOWN(io->transform, oTr, 12);
         DOWN(io->inverse_inertia_tensor_world, oIitw, 9); DOWN(io->is_awake, fAwakeOut, 1);
+        if (hostTrace) cudaEventRecord(trEv[c * 4 + 3], pp.sDown);
     }
 #undef UP
 #undef DOWN
@@ -967,10 +1009,24 @@ int cz_world_step_host(cz_world *w, cz_bodies *io, cz_real dt, int32_t n_steps, 
     CK(ctx, cudaEventRecord(pp.evDownDone, pp.sDown));
     CK(ctx, cudaStreamWaitEvent(ctx->stream, pp.evDownDone, 0));
     CK(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+    const auto tc1 = std::chrono::steady_clock::now();
     CK(ctx, cudaEventSynchronize(ctx->ev1));
+    const auto tc2 = std::chrono::steady_clock::now();
     float ms = 0;
     CK(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
-    return read_stats(w, stats, launches, n_steps, ms);
+    rc = read_stats(w, stats, launches, n_steps, ms);
+    if (hostTrace) {
+        const auto tc3 = std::chrono::steady_clock::now();
+        auto us = [](auto a, auto b) { return (double)std::chrono::duration_cast<std::chrono::nanoseconds>(b - a).count() * 1e-3; };
+        fprintf(stderr, "[step_host] enqueue %.0f us | wait %.0f us | stats %.0f us | device events %.0f us\n", us(tc0, tc1), us(tc1, tc2), us(tc2, tc3), ms * 1e3);
+        for (int c = 0; c < pp.chunks; c++) {
+            float t[4] = {0, 0, 0, 0};
+            for (int k = 0; k < 4; k++) cudaEventElapsedTime(&t[k], ctx->ev0, trEv[c * 4 + k]);
+            fprintf(stderr, "   chunk %d (%d worlds): up done %.2f | compute %.2f..%.2f | down done %.2f ms\n", c, wEdge[c + 1] - wEdge[c], t[0], t[1], t[2], t[3]);
+        }
+        for (auto &e : trEv) cudaEventDestroy(e);
+    }
+    return rc;
 }
 
 // ---- object-API shims ------------------------------------------------------------------------

@@ -7,7 +7,7 @@ from cubez_b200.api import BatchedWorld, Context
 W = 65536
 sc = scenes.batched_cubedrop(n_worlds=W)
 ctx = Context.get(0, "f64")
-for chunks in (1, 2, 4, 8, 16):
+for chunks in [int(a) for a in sys.argv[1:]] or (4, 8, 12, 16):
     os.environ["CUBEZ_HOST_CHUNKS"] = str(chunks)
     gpu = BatchedWorld.from_scene(sc, contacts_per_world=64)
     gpu.set_episodes(600, (np.arange(W) % 600).astype(np.int32))
