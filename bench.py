@@ -205,6 +205,27 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_ms = float(t.item())
     e2e_value = W * world_size / (e2e_ms * 1e-3)
+
+    # ---- RL-style loop: worlds stay resident, actions in, observations out ------
+    # every frame: batched AddVelocity for every body from pinned host memory (48 B/body H2D), one frame,
+    # position + orientation + velocity + rotation back (104 B/body D2H)
+    act = ctx.pinned_array((nb, 3))
+    act[...] = np.random.default_rng(1 + rank).uniform(-1e-3, 1e-3, (nb, 3))
+    obs = ctx.pinned_bodies(nb, fields=BatchedWorld.OBS_FIELDS)
+    world.step_rl(act, None, obs, DT, 1)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        world.step_rl(act, None, obs, DT, 1)
+    barrier()
+    rl_ms = (time.perf_counter() - t0) * 1e3 / args.e2e_steps
+    if world_size > 1:
+        t = torch.tensor([rl_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        rl_ms = float(t.item())
+    e2e_rl = {"value": W * world_size / (rl_ms * 1e-3), "unit": "world-steps/s", "h2d_bytes_per_step": nb * 24 * world_size,
+              "d2h_bytes_per_step": nb * 13 * 8 * world_size, "ms_per_step": rl_ms,
+              "api": "cz_world_step_rl: device-resident worlds; batched AddVelocity in, position/orientation/velocity/rotation out, pinned host arrays, 1 frame per call"}
     sampler.stop_flag = True
     sampler.join(timeout=2)
 
@@ -251,6 +272,7 @@ def main():
             "body_steps_per_s": value * BODIES_PER_WORLD,
             "e2e": {"value": e2e_value, "unit": "world-steps/s", "h2d_bytes_per_step": h2d * world_size, "d2h_bytes_per_step": d2h * world_size,
                     "ms_per_step": e2e_ms, "api": "cz_world_step_host: pinned host arrays (full body state in, full body state out), 1 frame per call, 8-chunk H2D | pack+step+unpack | D2H pipeline, 3 compute streams"},
+            "e2e_rl": e2e_rl,
             "gpu_launches": int(red["counters"]["launches"]),
             "clocks": sampler.summary(),
             "roofline": roofline,

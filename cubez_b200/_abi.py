@@ -293,6 +293,7 @@ def declare(lib: C.CDLL, prec: Precision, prefix: str = "cz_"):
         "world_last_step_counts": ([VP, P32, P32, P32], C.c_int),
         "world_checksum_energy": ([VP, C.POINTER(C.c_uint64), C.POINTER(C.c_double)], C.c_int),
         "world_step_host": ([VP, PB, R, C.c_int32, C.POINTER(CzStepStats)], C.c_int),
+        "world_step_rl": ([VP, PR, PR, PB, R, C.c_int32, C.POINTER(CzStepStats)], C.c_int),
         "bench_integrate": ([VP, C.c_int64, C.c_uint64, C.c_int32, C.c_int32, R, C.POINTER(C.c_float), C.POINTER(C.c_uint64)], C.c_int),
         "math_op": ([VP, C.c_int32, PR, PR], C.c_int),
         "broadphase_pairs": ([VP, C.c_int64, PR, PR, C.c_int64, P32, C.POINTER(C.c_int64)], C.c_int),
@@ -313,7 +314,7 @@ EXPORTED = (
     "world_upload_bodies world_upload_colliders world_upload_planes world_upload_schedule world_set_activation "
     "world_set_pow world_set_step_index world_set_episodes world_step world_synchronize world_download_bodies "
     "world_download_colliders world_download_contacts world_last_step_counts world_checksum_energy "
-    "world_step_host bench_integrate math_op broadphase_pairs bench_broadphase sort_pairs_u32 sort_pairs_u64"
+    "world_step_host world_step_rl bench_integrate math_op broadphase_pairs bench_broadphase sort_pairs_u32 sort_pairs_u64"
 ).split()
 
 

@@ -115,20 +115,34 @@ class Context:
         contacts.take(cst)
         return int(iters[0]), int(iters[1])
 
-    def pinned_bodies(self, n: int) -> Bodies:
+    def pinned_array(self, shape, dtype=None) -> np.ndarray:
+        """A page-locked host array (cz_host_alloc), e.g. the action buffers of BatchedWorld.step_rl."""
+        dtype = np.dtype(self.prec.dtype if dtype is None else dtype)
+        count = int(np.prod(shape))
+        raw = C.c_void_p()
+        self.check(self.lib.cz_host_alloc(self.h, max(1, count * dtype.itemsize), C.byref(raw)))
+        buf = (C.c_uint8 * max(1, count * dtype.itemsize)).from_address(raw.value)
+        arr = np.frombuffer(buf, dtype=dtype, count=count).reshape(shape)
+        self._pinned_keep = getattr(self, "_pinned_keep", []) + [(raw, buf)]
+        arr[...] = 0
+        return arr
+
+    def pinned_bodies(self, n: int, fields=None) -> Bodies:
         """A Bodies record whose arrays live in page-locked host memory (cz_host_alloc): the
         zero-copy views a cgo caller would get with unsafe.Slice over C-allocated buffers.  Used
-        with BatchedWorld.step_host so the H2D / D2H copies are truly asynchronous."""
+        with BatchedWorld.step_host / step_rl so the H2D / D2H copies are truly asynchronous.
+        `fields` limits the record to the named arrays (the others stay NULL)."""
         b = Bodies.__new__(Bodies)
-        b.n, b.prec, b.a = int(n), self.prec, {}
+        b.n, b.prec, b.a = int(n), self.prec, {name: None for name, _ in _abi.BODY_FIELDS}
         isz = np.dtype(self.prec.dtype).itemsize
-        total = sum(max(1, n * max(comp, 1)) * (1 if comp == 0 else isz) + 64 for _, comp in _abi.BODY_FIELDS)
+        wanted = [(name, comp) for name, comp in _abi.BODY_FIELDS if fields is None or name in fields]
+        total = sum(max(1, n * max(comp, 1)) * (1 if comp == 0 else isz) + 64 for _, comp in wanted)
         raw = C.c_void_p()
         self.check(self.lib.cz_host_alloc(self.h, total, C.byref(raw)))
         buf = (C.c_uint8 * total).from_address(raw.value)
         b._pinned = (raw, buf)
         off = 0
-        for name, comp in _abi.BODY_FIELDS:
+        for name, comp in wanted:
             dt = np.uint8 if comp == 0 else self.prec.dtype
             cnt = n * max(comp, 1)
             arr = np.frombuffer(buf, dtype=dt, count=cnt, offset=off)
@@ -228,6 +242,24 @@ class BatchedWorld:
         st = CzStepStats()
         bst = bodies.struct()
         self.ctx.check(self.lib.cz_world_step_host(self.h, C.byref(bst), self.prec.ctype(dt), n_steps, C.byref(st)))
+        return st.as_dict()
+
+    OBS_FIELDS = ("position", "orientation", "velocity", "rotation")
+
+    def step_rl(self, add_velocity=None, add_rotation=None, obs: Optional[Bodies] = None, dt=None, n_steps: int = 1) -> dict:
+        """RL-style step of device-resident worlds: batched AddVelocity / AddRotation in
+        (rigidbody.go:195-202, arrays [n_bodies, 3] or None), n_steps frames, then the arrays
+        present in `obs` filled (e.g. ctx.pinned_bodies(n, fields=BatchedWorld.OBS_FIELDS))."""
+        PR = C.POINTER(self.prec.ctype)
+        def ptr(a):
+            if a is None:
+                return None
+            assert a.dtype == self.prec.dtype and a.flags["C_CONTIGUOUS"] and a.size == self.n_worlds * self.B * 3
+            return a.ctypes.data_as(PR)
+        st = CzStepStats()
+        ost = obs.struct() if obs is not None else None
+        self.ctx.check(self.lib.cz_world_step_rl(self.h, ptr(add_velocity), ptr(add_rotation), None if ost is None else C.byref(ost),
+                                                 self.prec.ctype(dt), n_steps, C.byref(st)))
         return st.as_dict()
 
     def synchronize(self):

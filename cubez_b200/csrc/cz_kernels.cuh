@@ -201,25 +201,44 @@ __global__ void k_pack_all(czb::BodyStore s, long long first, long long n, HostI
     s.awake[i] = h.awake[i];
     s.can_sleep[i] = h.can_sleep[i];
 }
+// every output array is optional (NULL = not wanted): cz_world_step_host asks for all of them,
+// cz_world_step_rl for the observation the caller named
 __global__ void k_unpack_all(czb::BodyStore s, long long first, long long n, HostOut h) {
     using namespace czb;
     long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
     const long long i = first + t;
-    V3 pos = ld_position(s, i), vel = ld_velocity(s, i), rot = ld_rotation(s, i), la = ld_last_acc(s, i);
-    Q4 q = ld_orientation(s, i);
-    M34 tr = ld_transform(s, i);
-    M3 iw = ld_iit_world(s, i);
+    if (h.pos) { V3 v = ld_position(s, i); for (int k = 0; k < 3; k++) h.pos[i * 3 + k] = v.c[k]; }
+    if (h.vel) { V3 v = ld_velocity(s, i); for (int k = 0; k < 3; k++) h.vel[i * 3 + k] = v.c[k]; }
+    if (h.rot) { V3 v = ld_rotation(s, i); for (int k = 0; k < 3; k++) h.rot[i * 3 + k] = v.c[k]; }
+    if (h.lacc) { V3 v = ld_last_acc(s, i); for (int k = 0; k < 3; k++) h.lacc[i * 3 + k] = v.c[k]; }
+    if (h.ori) { Q4 q = ld_orientation(s, i); for (int k = 0; k < 4; k++) h.ori[i * 4 + k] = q.c[k]; }
+    if (h.tr) {
+        M34 tr = ld_transform(s, i);
 #pragma unroll
-    for (int k = 0; k < 3; k++) { h.pos[i * 3 + k] = pos.c[k]; h.vel[i * 3 + k] = vel.c[k]; h.rot[i * 3 + k] = rot.c[k]; h.lacc[i * 3 + k] = la.c[k]; }
+        for (int k = 0; k < 12; k++) h.tr[i * 12 + k] = tr.c[k];
+    }
+    if (h.iitw) {
+        M3 iw = ld_iit_world(s, i);
 #pragma unroll
-    for (int k = 0; k < 4; k++) h.ori[i * 4 + k] = q.c[k];
-#pragma unroll
-    for (int k = 0; k < 12; k++) h.tr[i * 12 + k] = tr.c[k];
-#pragma unroll
-    for (int k = 0; k < 9; k++) h.iitw[i * 9 + k] = iw.c[k];
-    h.motion[i] = s.ld(C_P2M, i).y;
-    h.awake[i] = s.awake[i];
+        for (int k = 0; k < 9; k++) h.iitw[i * 9 + k] = iw.c[k];
+    }
+    if (h.motion) h.motion[i] = s.ld(C_P2M, i).y;
+    if (h.awake) h.awake[i] = s.awake[i];
+}
+
+// Batched RigidBody.AddVelocity / AddRotation (rigidbody.go:195-202): Velocity.Add(v), Rotation.Add(v),
+// one rounding per component, applied to every body of the range (sleeping bodies are not woken — the
+// reference does not either).  Either array may be NULL.
+__global__ void k_apply_actions(czb::BodyStore s, long long first, long long n, const real *addVel, const real *addRot) {
+    using namespace czb;
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const long long i = first + t;
+    real2 v01 = s.ld(C_V01, i), v2r0 = s.ld(C_V2R0, i), r12 = s.ld(C_R12, i);
+    if (addVel) { v01.x = v01.x + addVel[i * 3]; v01.y = v01.y + addVel[i * 3 + 1]; v2r0.x = v2r0.x + addVel[i * 3 + 2]; }
+    if (addRot) { v2r0.y = v2r0.y + addRot[i * 3]; r12.x = r12.x + addRot[i * 3 + 1]; r12.y = r12.y + addRot[i * 3 + 2]; }
+    s.st(C_V01, i, v01); s.st(C_V2R0, i, v2r0); s.st(C_R12, i, r12);
 }
 
 __global__ void k_fill_u8(uint8_t *p, long long n, uint8_t v) {

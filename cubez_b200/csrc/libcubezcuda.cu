@@ -859,6 +859,19 @@ int cz_world_checksum_energy(cz_world *w, uint64_t *checksum, double *energy) {
 // pipeline over world chunks — H2D copies | pack + frames + unpack | D2H copies — on three
 // streams, so PCIe traffic in both directions overlaps the kernels.  Host arrays should be pinned
 // (cz_host_alloc); pageable memory works but the copies then serialise in the driver.
+// chunk boundaries of the host pipelines: short first and last chunks (pipeline fill = first upload,
+// drain = last download)
+static std::vector<int> host_chunk_edges(int chunks, int W) {
+    std::vector<int> wEdge(chunks + 1, 0);
+    std::vector<double> wt(chunks, 1.0);
+    if (chunks >= 4 && !czf::env_int("CUBEZ_HOST_EVEN_CHUNKS", 0)) { wt[0] = wt[chunks - 1] = 0.5; wt[1] = wt[chunks - 2] = 0.85; }
+    double tot = 0, run = 0;
+    for (double v : wt) tot += v;
+    for (int c = 0; c < chunks; c++) { run += wt[c]; wEdge[c + 1] = (int)((double)W * run / tot + 0.5); }
+    wEdge[chunks] = W;
+    return wEdge;
+}
+
 static int host_pipe_init(cz_world *w) {
     cz_ctx *ctx = w->ctx;
     auto &pp = w->pipe;
@@ -930,16 +943,7 @@ int cz_world_step_host(cz_world *w, cz_bodies *io, cz_real dt, int32_t n_steps, 
     if (hostTrace) { trEv.resize((size_t)pp.chunks * 4); for (auto &e : trEv) cudaEventCreate(&e); }
 #define UP(dst, src, comps) CK(ctx, cudaMemcpyAsync((dst) + b0 * (comps), (src) + b0 * (comps), sizeof(*(src)) * nb * (comps), cudaMemcpyHostToDevice, pp.sUp))
 #define DOWN(dst, src, comps) CK(ctx, cudaMemcpyAsync((dst) + b0 * (comps), (src) + b0 * (comps), sizeof(*(src)) * nb * (comps), cudaMemcpyDeviceToHost, pp.sDown))
-    // chunk boundaries: short first and last chunks (pipeline fill = first upload, drain = last download)
-    std::vector<int> wEdge(pp.chunks + 1, 0);
-    {
-        std::vector<double> wt(pp.chunks, 1.0);
-        if (pp.chunks >= 4 && !czf::env_int("CUBEZ_HOST_EVEN_CHUNKS", 0)) { wt[0] = wt[pp.chunks - 1] = 0.5; wt[1] = wt[pp.chunks - 2] = 0.85; }
-        double tot = 0, run = 0;
-        for (double v : wt) tot += v;
-        for (int c = 0; c < pp.chunks; c++) { run += wt[c]; wEdge[c + 1] = (int)((double)W * run / tot + 0.5); }
-        wEdge[pp.chunks] = W;
-    }
+    const std::vector<int> wEdge = host_chunk_edges(pp.chunks, W);
     for (int c = 0; c < pp.chunks; c++) {
         const int w0 = wEdge[c], w1 = wEdge[c + 1];
         const long long b0 = w0 * B, nb = (w1 - w0) * B;
@@ -1027,6 +1031,122 @@ int cz_world_step_host(cz_world *w, cz_bodies *io, cz_real dt, int32_t n_steps, 
         for (auto &e : trEv) cudaEventDestroy(e);
     }
     return rc;
+}
+
+
+int cz_world_step_rl(cz_world *w, const cz_real *add_velocity, const cz_real *add_rotation, cz_bodies *obs, cz_real dt, int32_t n_steps,
+                     cz_step_stats *stats) {
+    if (!w || n_steps < 0) return fail(nullptr, CZ_ERR_INVALID, "cz_world_step_rl: bad argument");
+    cz_ctx *ctx = w->ctx;
+    if (obs && obs->n != w->b.n) return fail(ctx, CZ_ERR_INVALID, "cz_world_step_rl: obs->n must equal n_worlds*bodies_per_world");
+    CK(ctx, cudaSetDevice(ctx->device));
+    if (!w->useFused) {
+        // any world shape: actions, resident step, observations (no chunk pipeline: the multi-kernel path steps the whole batch)
+        const long long NB0 = w->b.n;
+        int rc0;
+        if (add_velocity || add_rotation) {
+            if ((rc0 = host_pipe_init(w))) return rc0;
+            real *dV = w->pipe.dIn, *dR = dV + NB0 * 3;
+            if (add_velocity) CK(ctx, cudaMemcpyAsync(dV, add_velocity, sizeof(real) * NB0 * 3, cudaMemcpyHostToDevice, ctx->stream));
+            if (add_rotation) CK(ctx, cudaMemcpyAsync(dR, add_rotation, sizeof(real) * NB0 * 3, cudaMemcpyHostToDevice, ctx->stream));
+            k_apply_actions<<<nblk(NB0, 256), 256, 0, ctx->stream>>>(w->b.st, 0, NB0, add_velocity ? dV : nullptr, add_rotation ? dR : nullptr);
+            CKL(ctx);
+        }
+        if ((rc0 = cz_world_step(w, dt, n_steps, stats))) return rc0;
+        if (obs) {
+            cz_bodies o{};
+            o.n = obs->n; o.position = obs->position; o.orientation = obs->orientation; o.velocity = obs->velocity; o.rotation = obs->rotation;
+            o.motion = obs->motion; o.is_awake = obs->is_awake; o.transform = obs->transform;
+            o.inverse_inertia_tensor_world = obs->inverse_inertia_tensor_world; o.last_frame_acceleration = obs->last_frame_acceleration;
+            return download_bodies(w->b, 0, NB0, &o);
+        }
+        return CZ_OK;
+    }
+    int rc;
+    if ((rc = world_prepare_step(w, dt))) return rc;
+    if ((rc = host_pipe_init(w))) return rc;
+    auto &pp = w->pipe;
+    const long long NB = w->b.n, B = w->d.bodies_per_world;
+    const int W = w->d.n_worlds;
+    real *dVel = pp.dIn, *dRot = dVel + NB * 3;
+    real *oPos = pp.dOut, *oOri = oPos + NB * 3, *oVel = oOri + NB * 4, *oRot = oVel + NB * 3, *oMot = oRot + NB * 3, *oLacc = oMot + NB, *oTr = oLacc + NB * 3, *oIitw = oTr + NB * 12;
+    uint8_t *fAwakeOut = pp.dFlags + 2 * NB;
+    HostOut hout{};
+    if (obs) {
+        hout.pos = obs->position ? oPos : nullptr; hout.ori = obs->orientation ? oOri : nullptr; hout.vel = obs->velocity ? oVel : nullptr;
+        hout.rot = obs->rotation ? oRot : nullptr; hout.motion = obs->motion ? oMot : nullptr; hout.lacc = obs->last_frame_acceleration ? oLacc : nullptr;
+        hout.tr = obs->transform ? oTr : nullptr; hout.iitw = obs->inverse_inertia_tensor_world ? oIitw : nullptr; hout.awake = obs->is_awake ? fAwakeOut : nullptr;
+    }
+    const bool anyOut = hout.pos || hout.ori || hout.vel || hout.rot || hout.motion || hout.lacc || hout.tr || hout.iitw || hout.awake;
+    const bool anyIn = add_velocity || add_rotation;
+    CK(ctx, cudaMemsetAsync(w->stats, 0, sizeof(unsigned long long) * ST_N, ctx->stream));
+    CK(ctx, cudaMemsetAsync(pp.dNext, 0, sizeof(unsigned int) * pp.chunks, ctx->stream));
+    CK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    CK(ctx, cudaEventRecord(pp.evBegin, ctx->stream));
+    CK(ctx, cudaStreamWaitEvent(pp.sUp, pp.evBegin, 0));
+    CK(ctx, cudaStreamWaitEvent(pp.sDown, pp.evBegin, 0));
+    for (int k = 1; k < pp.nComp; k++) CK(ctx, cudaStreamWaitEvent(pp.sComp[k], pp.evBegin, 0));
+    long long launches = 0;
+    // observations are a third of the full state: fewer, larger chunks keep the fused kernels efficient
+    const int chunks = std::max(1, std::min(pp.chunks, czf::env_int("CUBEZ_RL_CHUNKS", 4)));
+    const std::vector<int> wEdge = host_chunk_edges(chunks, W);
+#define UP(dst, src, comps) CK(ctx, cudaMemcpyAsync((dst) + b0 * (comps), (src) + b0 * (comps), sizeof(*(src)) * nb * (comps), cudaMemcpyHostToDevice, pp.sUp))
+#define DOWN(dst, src, comps) if (dst) CK(ctx, cudaMemcpyAsync((dst) + b0 * (comps), (src) + b0 * (comps), sizeof(*(src)) * nb * (comps), cudaMemcpyDeviceToHost, pp.sDown))
+    for (int c = 0; c < chunks; c++) {
+        const int w0 = wEdge[c], w1 = wEdge[c + 1];
+        const long long b0 = w0 * B, nb = (w1 - w0) * B;
+        if (nb <= 0) continue;
+        cudaStream_t cs = pp.sComp[c % pp.nComp];
+        if (anyIn) {
+            if (add_velocity) UP(dVel, add_velocity, 3);
+            if (add_rotation) UP(dRot, add_rotation, 3);
+            CK(ctx, cudaEventRecord(pp.evUp[c], pp.sUp));
+            CK(ctx, cudaStreamWaitEvent(cs, pp.evUp[c], 0));
+            k_apply_actions<<<nblk(nb, 256), 256, 0, cs>>>(w->b.st, b0, nb, add_velocity ? dVel : nullptr, add_rotation ? dRot : nullptr);
+            CKL(ctx);
+            launches++;
+        }
+        WorldParams p = world_params(w);
+        p.wFirst = w0; p.wCount = w1 - w0;
+        czf::FusedPlan fpl = w->fused;
+        if (c % pp.nComp) fpl.cold = pp.coldX[c % pp.nComp];
+        if (w->fused.split) {
+            for (int s2 = 0; s2 < n_steps && !rc; s2++) {
+                p.step_index = w->step_index + s2;
+                for (int ph : {czf::PH_A, czf::PH_B, czf::PH_C}) {
+                    rc = czf::launch(fpl, p, dt, w->bias, 1, pp.dNext + c, cs, ph);
+                    if (rc) break;
+                    launches++;
+                }
+            }
+        } else if (n_steps > 0) {
+            rc = czf::launch(fpl, p, dt, w->bias, n_steps, pp.dNext + c, cs);
+            launches++;
+        }
+        if (rc) return fail(ctx, CZ_ERR_CUDA, std::string("fused launch: ") + cudaGetErrorString((cudaError_t)rc));
+        if (anyOut) {
+            k_unpack_all<<<nblk(nb, 256), 256, 0, cs>>>(w->b.st, b0, nb, hout);
+            CKL(ctx);
+            launches++;
+        }
+        CK(ctx, cudaEventRecord(pp.evComp[c], cs));
+        CK(ctx, cudaStreamWaitEvent(pp.sDown, pp.evComp[c], 0));
+        if (anyOut) {
+            DOWN(obs->position, oPos, 3); DOWN(obs->orientation, oOri, 4); DOWN(obs->velocity, oVel, 3); DOWN(obs->rotation, oRot, 3);
+            DOWN(obs->motion, oMot, 1); DOWN(obs->last_frame_acceleration, oLacc, 3); DOWN(obs->transform, oTr, 12);
+            DOWN(obs->inverse_inertia_tensor_world, oIitw, 9); DOWN(obs->is_awake, fAwakeOut, 1);
+        }
+    }
+#undef UP
+#undef DOWN
+    w->step_index += n_steps;
+    CK(ctx, cudaEventRecord(pp.evDownDone, pp.sDown));
+    CK(ctx, cudaStreamWaitEvent(ctx->stream, pp.evDownDone, 0));
+    CK(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+    CK(ctx, cudaEventSynchronize(ctx->ev1));
+    float ms = 0;
+    CK(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    return read_stats(w, stats, launches, n_steps, ms);
 }
 
 // ---- object-API shims ------------------------------------------------------------------------

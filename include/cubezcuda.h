@@ -247,6 +247,16 @@ int cz_world_checksum_energy(cz_world *w, uint64_t *checksum, double *energy);
 /* Host-buffer step: upload primary state, run n_steps, download state, all on the world's
  * stream with pinned staging (the end-to-end call a host-resident caller makes). */
 int cz_world_step_host(cz_world *w, cz_bodies *io, cz_real dt, int32_t n_steps, cz_step_stats *stats);
+/* RL-style step for device-resident worlds: actions in, observations out.
+ * Before the first of the n_steps frames every body i receives Velocity.Add(add_velocity[3i..])
+ * and Rotation.Add(add_rotation[3i..]) — the batched form of RigidBody.AddVelocity / AddRotation
+ * (rigidbody.go:195-202); either array may be NULL (no call).  After the frames, every non-NULL
+ * array among obs->{position, orientation, velocity, rotation, motion, is_awake, transform,
+ * inverse_inertia_tensor_world, last_frame_acceleration} is filled (obs->n = n_worlds *
+ * bodies_per_world; obs may be NULL).  Host arrays should be pinned; transfers are pipelined in
+ * chunks against the step.  Episode resets (cz_world_set_episodes) happen on the device. */
+int cz_world_step_rl(cz_world *w, const cz_real *add_velocity, const cz_real *add_rotation, cz_bodies *obs, cz_real dt,
+                     int32_t n_steps, cz_step_stats *stats);
 
 /* ---- microbench / diagnostics -------------------------------------------------------- */
 /* Integrate + CalculateDerivedData over n device-resident free bodies, `steps` times, timed

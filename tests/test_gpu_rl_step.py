@@ -1,0 +1,96 @@
+"""GPU: the RL-style step — batched AddVelocity / AddRotation in, observations
+out, worlds resident on the device — against the oracle driven the way a host loop over the
+reference API would drive it (AddVelocity / AddRotation on every body, then the frame)."""
+import numpy as np
+import pytest
+
+from cubez_b200 import _abi, scenes
+from cubez_b200.api import BatchedWorld, Context
+from oracle_lib import OracleWorld
+
+pytestmark = pytest.mark.gpu
+
+OBS = ("position", "orientation", "velocity", "rotation", "motion", "is_awake", "transform", "inverse_inertia_tensor_world",
+       "last_frame_acceleration")
+
+
+def oracle_apply(cpu, av, ar):
+    d = cpu.download()
+    if av is not None:
+        d.velocity[...] = d.velocity + av          # Vector3.Add: one rounding per component
+    if ar is not None:
+        d.rotation[...] = d.rotation + ar
+    cpu.upload_bodies(d)
+
+
+@pytest.mark.parametrize("n_worlds,flags", [(64, 0), (700, 0), (8, _abi.WORLD_NO_FUSED)])
+def test_step_rl_matches_oracle_with_actions(n_worlds, flags):
+    sc = scenes.batched_cubedrop(n_worlds=n_worlds)
+    ctx = Context.get(0, "f64")
+    gpu = BatchedWorld.from_scene(sc, flags=flags, contacts_per_world=64)
+    cpu = OracleWorld.from_scene(sc)
+    nb = n_worlds * 8
+    rng = np.random.default_rng(n_worlds)
+    av, ar = ctx.pinned_array((nb, 3)), ctx.pinned_array((nb, 3))
+    obs = ctx.pinned_bodies(nb, fields=OBS)
+    for frame in range(0, 140, 4):
+        kind = (frame // 4) % 4
+        a = rng.uniform(-0.3, 0.3, (nb, 3)) * (rng.uniform(0, 1, (nb, 1)) < 0.2) if kind in (0, 1) else None
+        r = rng.uniform(-0.5, 0.5, (nb, 3)) * (rng.uniform(0, 1, (nb, 1)) < 0.2) if kind in (1, 2) else None
+        if a is not None:
+            av[...] = a
+        if r is not None:
+            ar[...] = r
+        gs = gpu.step_rl(av if a is not None else None, ar if r is not None else None, obs, sc.dt, 4)
+        oracle_apply(cpu, a, r)
+        cs = cpu.step(sc.dt, 4)
+        for k in ("contacts", "pos_iterations", "vel_iterations"):
+            assert gs[k] == cs[k], (frame, k)
+        c = cpu.download()
+        for f in OBS:
+            assert np.array_equal(getattr(obs, f), getattr(c, f)), (frame, f)
+    g = gpu.download()
+    for f in OBS:
+        assert np.array_equal(getattr(g, f), getattr(obs, f)), f      # the observation is the resident state
+    gpu.close()
+
+
+def test_step_rl_partial_observation_and_no_actions():
+    """Only the named arrays are written; without actions the call is cz_world_step + download."""
+    sc = scenes.batched_cubedrop(n_worlds=300)
+    ctx = Context.get(0, "f64")
+    a, b = BatchedWorld.from_scene(sc, contacts_per_world=64), BatchedWorld.from_scene(sc, contacts_per_world=64)
+    obs = ctx.pinned_bodies(300 * 8, fields=BatchedWorld.OBS_FIELDS)
+    for _ in range(30):
+        sa = a.step_rl(None, None, obs, sc.dt, 5)
+        sb = b.step(sc.dt, 5)
+        assert sa["contacts"] == sb["contacts"] and sa["vel_iterations"] == sb["vel_iterations"]
+    d = b.download()
+    for f in BatchedWorld.OBS_FIELDS:
+        assert np.array_equal(getattr(obs, f), getattr(d, f)), f
+    assert obs.transform is None and obs.motion is None
+    assert a.checksum_energy()[0] == b.checksum_energy()[0]
+    a.close(); b.close()
+
+
+def test_step_rl_with_episode_resets_f32():
+    """Episodes wrap on the device; float32 build."""
+    sc = scenes.batched_cubedrop(_abi.F32, n_worlds=96)
+    ctx = Context.get(0, "f32")
+    gpu = BatchedWorld.from_scene(sc, contacts_per_world=64, ctx=ctx)
+    cpu = OracleWorld.from_scene(sc)
+    ph = (np.arange(96) * 7 % 50).astype(np.int32)
+    gpu.set_episodes(50, ph); cpu.set_episodes(50, ph)
+    nb = 96 * 8
+    av = ctx.pinned_array((nb, 3))
+    obs = ctx.pinned_bodies(nb, fields=BatchedWorld.OBS_FIELDS)
+    rng = np.random.default_rng(3)
+    for frame in range(0, 120, 3):
+        av[...] = rng.uniform(-0.2, 0.2, (nb, 3)).astype(np.float32)
+        gpu.step_rl(av, None, obs, sc.dt, 3)
+        oracle_apply(cpu, av, None)
+        cpu.step(sc.dt, 3)
+        c = cpu.download()
+        for f in BatchedWorld.OBS_FIELDS:
+            assert np.array_equal(getattr(obs, f), getattr(c, f)), (frame, f)
+    gpu.close()
