@@ -270,7 +270,7 @@ __global__ void __launch_bounds__(128, MINB) k_world_fused(WorldParams p, FusedP
         } else if (!__any_sync(mask, live ? 1 : 0)) {
             break;
         }
-        const int w = live ? p.wFirst + (int)wu : 0;
+        const int w = live ? (p.order ? p.order[p.wFirst + (int)wu] : p.wFirst + (int)wu) : 0;
         const long long gbase = (long long)w * B;
         x.body_base = gbase;
         if (live) stage_world<G>(s, st, gbase, B, tid);
@@ -550,6 +550,63 @@ __global__ void __launch_bounds__(128, MINB) k_world_fused(WorldParams p, FusedP
         if (accVel) atomicAdd(&p.stats[ST_VEL], accVel);
         atomicMax(&p.stats[ST_MAXC], (unsigned long long)maxC);
         if (status) raise_status(p.stats, status);
+    }
+}
+
+
+// Processing order of the worlds of one launch: the counters of the previous frame (contacts for the
+// integrate + narrowphase + prepare phase, position / velocity iterations for the two loops) predict
+// this frame's cost well, so worlds are fetched in descending key order.  The expensive worlds start
+// first (a short tail at the end of every launch — per-chunk launches of the host pipelines are
+// only a few world-rounds long), and the worlds that share a warp run for a similar number of
+// iterations (the groups of a warp iterate in lockstep to the longest of them).
+// Counting sort of world ids into 64 buckets, one CTA per key; result-neutral: worlds are independent.
+__global__ void __launch_bounds__(1024) k_order_worlds(const int *kContacts, const int *kPos, const int *kVel, int first, int count, int W, int *order3) {
+    // per-warp histograms (a few buckets hold most worlds: one shared counter per bucket would serialise),
+    // warp w owns the contiguous slice [w*per, (w+1)*per) of the range -> stable, deterministic order
+    __shared__ unsigned hist[32][64];
+    __shared__ unsigned bucketStart[64];
+    const int which = blockIdx.x;
+    const int *key = which == 0 ? kContacts : (which == 1 ? kPos : kVel);
+    const int shift = which == 0 ? 0 : (which == 1 ? 1 : 2);
+    int *order = order3 + (size_t)which * W;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int per = ((count + 31) / 32 + 31) / 32 * 32;   // elements per warp, a multiple of 32
+    const int lo = warp * per, hi = min(count, lo + per);
+    for (int b = lane; b < 64; b += 32) hist[warp][b] = 0;
+    __syncwarp();
+    for (int k0 = lo; k0 < hi; k0 += 32) {
+        const int k = k0 + lane;
+        const bool valid = k < hi;
+        const unsigned b = valid ? 63u - min(63u, (unsigned)max(key[first + k], 0) >> shift) : 64u;
+        const unsigned peers = __match_any_sync(0xffffffffu, b);
+        if (valid && lane == __ffs(peers) - 1) hist[warp][b] += __popc(peers);
+        __syncwarp();
+    }
+    __syncthreads();
+    if (threadIdx.x < 64) {   // per bucket: exclusive prefix over the warps, and the bucket total
+        unsigned run = 0;
+        for (int w2 = 0; w2 < 32; w2++) { const unsigned c = hist[w2][threadIdx.x]; hist[w2][threadIdx.x] = run; run += c; }
+        bucketStart[threadIdx.x] = run;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned run = 0;
+        for (int b = 0; b < 64; b++) { const unsigned c = bucketStart[b]; bucketStart[b] = run; run += c; }
+    }
+    __syncthreads();
+    for (int k0 = lo; k0 < hi; k0 += 32) {
+        const int k = k0 + lane;
+        const bool valid = k < hi;
+        const unsigned b = valid ? 63u - min(63u, (unsigned)max(key[first + k], 0) >> shift) : 64u;
+        const unsigned peers = __match_any_sync(0xffffffffu, b);
+        if (valid) {
+            const unsigned pos = bucketStart[b] + hist[warp][b] + __popc(peers & ((1u << lane) - 1u));
+            order[first + pos] = first + k;
+        }
+        __syncwarp();
+        if (valid && lane == __ffs(peers) - 1) hist[warp][b] += __popc(peers);
+        __syncwarp();
     }
 }
 

@@ -20,6 +20,7 @@ struct WorldParams {
     BodyStore st;
     int W, B, P, Cc;          // worlds, bodies per world, planes, contact capacity per world
     int wFirst, wCount;       // world range a fused launch works on (chunked host pipeline)
+    const int *order;         // optional: order[wFirst + k] = k-th world to process (expensive worlds first), else identity
     int nchk;                 // checks per world
     int schedule;
     const int *chk_one, *chk_two;   // explicit schedule (shared by all worlds)

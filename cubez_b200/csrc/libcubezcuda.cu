@@ -254,6 +254,8 @@ struct cz_world {
     bool useFused = false;
     czf::FusedPlan fused{};
     unsigned int *d_next = nullptr;   // dynamic world counter of the fused kernel
+    int *order3 = nullptr;            // [3][W] processing order per phase (czf::k_order_worlds)
+    bool useOrder = false;
     real bias = (real)NAN;
     // episodes
     int episodeLen = 0;
@@ -284,6 +286,7 @@ static WorldParams world_params(cz_world *w) {
     p.st = w->b.st;
     p.W = w->d.n_worlds; p.B = w->d.bodies_per_world; p.P = w->P; p.Cc = w->d.contacts_per_world;
     p.wFirst = 0; p.wCount = w->d.n_worlds;
+    p.order = nullptr;
     p.nchk = w->nchk;
     p.schedule = w->d.schedule;
     p.chk_one = w->d_one; p.chk_two = w->d_two;
@@ -294,6 +297,18 @@ static WorldParams world_params(cz_world *w) {
     p.stats = w->stats;
     p.episodeLen = w->episodeLen; p.episodeStep0 = w->episodeStep0; p.phase0 = w->d_phase0; p.snap = w->snap.st;
     return p;
+}
+
+
+// launch the per-phase world ordering for a world range and return the order pointer of a phase
+static inline void order_worlds(cz_world *w, const WorldParams &p, cudaStream_t st, long long &launches) {
+    if (!w->useOrder) return;
+    czf::k_order_worlds<<<3, 1024, 0, st>>>(p.nContacts, p.posIters, p.velIters, p.wFirst, p.wCount, p.W, w->order3);
+    launches++;
+}
+static inline const int *phase_order(cz_world *w, int ph) {
+    if (!w->useOrder) return nullptr;
+    return w->order3 + (size_t)(ph == czf::PH_A ? 0 : (ph == czf::PH_B ? 1 : 2)) * w->d.n_worlds;
 }
 
 // (Re)derive everything that depends on the schedule size / capacities.
@@ -351,6 +366,8 @@ static int world_plan(cz_world *w) {
         if (w->useFused) {
             CK(ctx, cudaMalloc(&w->fused.cold, sizeof(real) * w->fused.coldReals * (size_t)w->fused.grid * w->fused.groupsPerBlock));
             if (!w->d_next) CK(ctx, cudaMalloc(&w->d_next, sizeof(unsigned int)));
+            if (!w->order3) CK(ctx, cudaMalloc(&w->order3, sizeof(int) * 3 * (size_t)W));
+            w->useOrder = czf::env_int("CUBEZ_FUSED_ORDER", 1) != 0 && W >= 64;
             if (w->fused.split) {
                 const size_t WC = (size_t)W * Cc;
                 CK(ctx, cudaMalloc(&w->fused.coldW, sizeof(real) * WC * czr::CW_NCOLD));
@@ -461,7 +478,7 @@ int cz_world_destroy(cz_world *w) {
     if (w->snap.st.base) batch_free(w->snap);
     if (w->d_phase0) cudaFree(w->d_phase0);
     void *ptrs[] = {w->d_one, w->d_two, w->gen, w->gb0, w->gb1, w->nContacts, w->posIters, w->velIters, w->stats,
-                    w->tileCount, w->tileBase, w->hitCount, w->rs.bw, w->rs.cw, w->rs.cb, w->fused.cold, w->d_next,
+                    w->tileCount, w->tileBase, w->hitCount, w->rs.bw, w->rs.cw, w->rs.cb, w->fused.cold, w->d_next, w->order3,
                     w->fused.coldW, w->fused.hotPen, w->fused.hotDdv, w->fused.hotCb0, w->fused.hotCb1};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (w->h_stats) cudaFreeHost(w->h_stats);
@@ -736,13 +753,17 @@ int cz_world_step(cz_world *w, cz_real dt, int32_t n_steps, cz_step_stats *stats
         if (w->fused.split) {   // one launch per phase and frame: every warp of the GPU runs the same code region
             for (int s = 0; s < n_steps && !rc; s++) {
                 p.step_index = w->step_index + s;
+                order_worlds(w, p, ctx->stream, launches);
                 for (int ph : {czf::PH_A, czf::PH_B, czf::PH_C}) {
+                    p.order = phase_order(w, ph);
                     rc = czf::launch(w->fused, p, dt, w->bias, 1, w->d_next, ctx->stream, ph);
                     if (rc) break;
                     launches++;
                 }
             }
         } else {
+            order_worlds(w, p, ctx->stream, launches);
+            p.order = phase_order(w, czf::PH_C);
             rc = czf::launch(w->fused, p, dt, w->bias, n_steps, w->d_next, ctx->stream);
             launches++;
         }
@@ -977,13 +998,17 @@ int cz_world_step_host(cz_world *w, cz_bodies *io, cz_real dt, int32_t n_steps, 
             if (w->fused.split && !czf::env_int("CUBEZ_HOST_NO_SPLIT", 0)) {   // one launch per phase and frame, as cz_world_step does for large batches
                 for (int s2 = 0; s2 < n_steps && !rc; s2++) {
                     p.step_index = w->step_index + s2;
+                    order_worlds(w, p, cs, launches);
                     for (int ph : {czf::PH_A, czf::PH_B, czf::PH_C}) {
+                        p.order = phase_order(w, ph);
                         rc = czf::launch(fpl, p, dt, w->bias, 1, pp.dNext + c, cs, ph);
                         if (rc) break;
                         launches++;
                     }
                 }
             } else {
+                order_worlds(w, p, cs, launches);
+                p.order = phase_order(w, czf::PH_C);
                 rc = czf::launch(fpl, p, dt, w->bias, n_steps, pp.dNext + c, cs);
                 launches++;
             }
@@ -1113,13 +1138,17 @@ int cz_world_step_rl(cz_world *w, const cz_real *add_velocity, const cz_real *ad
         if (w->fused.split) {
             for (int s2 = 0; s2 < n_steps && !rc; s2++) {
                 p.step_index = w->step_index + s2;
+                order_worlds(w, p, cs, launches);
                 for (int ph : {czf::PH_A, czf::PH_B, czf::PH_C}) {
+                    p.order = phase_order(w, ph);
                     rc = czf::launch(fpl, p, dt, w->bias, 1, pp.dNext + c, cs, ph);
                     if (rc) break;
                     launches++;
                 }
             }
         } else if (n_steps > 0) {
+            order_worlds(w, p, cs, launches);
+            p.order = phase_order(w, czf::PH_C);
             rc = czf::launch(fpl, p, dt, w->bias, n_steps, pp.dNext + c, cs);
             launches++;
         }

@@ -232,3 +232,31 @@ def test_split_phase_launches_equal_persistent_kernel():
     cpu.set_episodes(140, phase0)
     cs = cpu.step(scene.dt, 300, n_threads=8)
     assert sums[1][0] == cpu.checksum_energy()[0] and sums[1][1:4] == (cs["contacts"], cs["pos_iterations"], cs["vel_iterations"])
+
+
+def test_cost_ordered_scheduling_is_result_neutral(monkeypatch):
+    """czf::k_order_worlds only permutes the order in which worlds are fetched: state, counters and
+    checksum are identical with and without it, resident and chunked."""
+    import numpy as np
+    from cubez_b200 import scenes
+    from cubez_b200.api import BatchedWorld
+    sc = scenes.batched_cubedrop(n_worlds=1500)
+    res = []
+    for order in ("1", "0"):
+        monkeypatch.setenv("CUBEZ_FUSED_ORDER", order)
+        monkeypatch.setenv("CUBEZ_FUSED_SPLIT", "1")
+        w = BatchedWorld.from_scene(sc, contacts_per_world=64)
+        tot = {"contacts": 0, "pos_iterations": 0, "vel_iterations": 0}
+        for _ in range(40):
+            st = w.step(sc.dt, 5)
+            for k in tot:
+                tot[k] += st[k]
+        for _ in range(10):
+            st = w.step_rl(None, None, None, sc.dt, 2)
+            for k in tot:
+                tot[k] += st[k]
+        res.append((tot, w.checksum_energy()[0], w.last_counts()))
+        w.close()
+    assert res[0][0] == res[1][0] and res[0][1] == res[1][1]
+    for a, b in zip(res[0][2], res[1][2]):
+        assert np.array_equal(a, b)
