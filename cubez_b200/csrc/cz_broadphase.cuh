@@ -8,11 +8,14 @@
 //   (default) ONE-PASS radix sort with radix = number of cells (counting sort):
 //     k_bp_count    key of body i, rank of i inside its cell (L2 atomic on the cell counter)
 //     scan          exclusive scan of the counters -> first sorted position of every cell
-//     k_bp_place    body i -> sorted[start[cell] + rank]: one 32-byte sector per body (float centre
-//                   relative to the grid origin, inflated radius, original index, cell coordinates)
-//     k_bp_sweep    every sorted body walks the forward half of its 27-cell neighbourhood as five
-//                   contiguous ranges of the sorted array (a row of cells = consecutive keys) in ONE
-//                   flattened loop, float sphere test, each unordered candidate emitted once
+//     k_bp_resolve  sorted position of body i = start[cell] + rank (the random table reads, kept apart
+//                   from the scatter below, which would evict the table from L2)
+//     k_bp_place    body i -> sorted[position]: one 32-byte sector per body, one 256-bit store (float
+//                   centre relative to the grid origin, inflated radius, original index, row key and
+//                   the x-cell interval that can hold a partner)
+//     k_bp_sweep    every sorted body walks the forward half of its neighbourhood as five contiguous
+//                   ranges of the sorted array (a row of cells = consecutive keys) in ONE flattened
+//                   loop, four partners per trip, float sphere test, each unordered candidate once
 //   (CUBEZ_BP_SORT=radix) the LSD 8-bit radix sort of cz_sort.cuh:
 //     k_bp_keys -> radix sort -> k_bp_gather -> k_bp_cells -> k_bp_pairs (f64 test)
 //   k_bp_narrow     both ordered checks (i,j) and (j,i) of every candidate through czn::check_pair
@@ -205,7 +208,10 @@ __global__ void __launch_bounds__(256) k_bp_pairs(const Bounds *sorted, const un
 // L2) and the sweep's test needs only the first 16 bytes.
 struct __align__(16) Entry {
     float x, y, z, r;          // centre relative to the grid origin; radius * BP_MARGIN + float slack, rounded up
-    unsigned idx, cx, cy, cz;  // original collider index, cell coordinates
+    unsigned idx;              // original collider index
+    unsigned rowOwn;           // key of cell 0 of the body's row of x-cells: (cz*ny + cy)*nx
+    unsigned xlf;              // first x-cell that can hold a partner | flags << 29 (1: row y+1 exists, 2: row y-1, 4: slab z+1)
+    unsigned xh;               // last x-cell that can hold a partner
 };
 static_assert(sizeof(Entry) == 32, "Entry must be one sector");
 
@@ -253,37 +259,54 @@ __device__ __forceinline__ bool cell_key(const Grid &g, const Bounds &b, int &cx
 }
 
 __global__ void __launch_bounds__(256) k_bp_count(const Bounds *__restrict__ bounds, long long n, Grid g, unsigned *__restrict__ cellCount,
-                                                  unsigned *__restrict__ rank) {
+                                                  uint2 *__restrict__ keyRank) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const Bounds b = ld_bounds_stream(bounds + i);
     int cx, cy, cz;
-    unsigned key;
-    if (cell_key(g, b, cx, cy, cz, key)) __stcs(rank + i, atom_add_keep(&cellCount[key], 1u, l2_evict_last()));
+    unsigned key = BP_INACTIVE, rank = 0;
+    if (cell_key(g, b, cx, cy, cz, key)) rank = atom_add_keep(&cellCount[key], 1u, l2_evict_last());
+    __stcs(keyRank + i, make_uint2(key, rank));
+}
+
+// sorted position of body i = first position of its cell + its rank.  A kernel of its own: the only
+// random access is the 4-byte table read, and the table stays in L2 as long as no scattered stores
+// run beside it (measured: next to the scatter of k_bp_place every table read missed, +1 GB of DRAM reads).
+__global__ void __launch_bounds__(256) k_bp_resolve(const uint2 *__restrict__ keyRank, long long n, const unsigned *__restrict__ cellStart,
+                                                    unsigned *__restrict__ pos) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint2 kr = __ldcs(keyRank + i);
+    __stcs(pos + i, kr.x == BP_INACTIVE ? BP_INACTIVE : ld_keep(cellStart + kr.x, l2_evict_last()) + kr.y);
 }
 
 // slack: float rounding of the relative centre is <= extent * 2^-24 per coordinate (Grid::e1); each
 // radius carries 4*e1, so the float test accepts every pair the exact inflated test accepts.
-__global__ void __launch_bounds__(256) k_bp_place(const Bounds *__restrict__ bounds, long long n, Grid g, const unsigned *__restrict__ cellStart,
-                                                  const unsigned *__restrict__ rank, Entry *__restrict__ sorted) {
+__global__ void __launch_bounds__(256) k_bp_place(const Bounds *__restrict__ bounds, long long n, Grid g, const unsigned *__restrict__ pos,
+                                                  Entry *__restrict__ sorted) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
+    const unsigned p = __ldcs(pos + i);
+    if (p == BP_INACTIVE) return;
     const Bounds b = ld_bounds_stream(bounds + i);
     int cx, cy, cz;
-    unsigned key;
-    if (!cell_key(g, b, cx, cy, cz, key)) return;
-    const unsigned p = ld_keep(cellStart + key, l2_evict_last()) + __ldcs(rank + i);
+    cell_of(g, b, cx, cy, cz);
     const float x = (float)((double)b.x - g.ox), y = (float)((double)b.y - g.oy), z = (float)((double)b.z - g.oz);
     const float r = __double2float_ru(((double)b.r * BP_MARGIN + 4.0 * g.e1) * 1.000002);   // 2e-6: the float roundings of the test itself
+    // x-cells that can hold a partner: every centre within my radius + the largest radius (+ rounding slack)
+    const double reach = ((double)r + g.rmaxInfl) * 1.000002 + 8.0 * g.e1;
+    const int xl = min(max((int)floor(((double)x - reach) * g.invx), 0), cx);
+    const int xh = max(min((int)floor(((double)x + reach) * g.invx), g.nx - 1), cx);
+    const unsigned flags = (cy + 1 < g.ny ? 1u : 0u) | (cy > 0 ? 2u : 0u) | (cz + 1 < g.nz ? 4u : 0u);
     // ONE 256-bit store: the scattered write fills its sector, so L2 never fetches it first
     const unsigned long long w0 = (unsigned long long)__float_as_uint(x) | ((unsigned long long)__float_as_uint(y) << 32);
     const unsigned long long w1 = (unsigned long long)__float_as_uint(z) | ((unsigned long long)__float_as_uint(r) << 32);
-    const unsigned long long w2 = (unsigned long long)(unsigned)i | ((unsigned long long)(unsigned)cx << 32);
-    const unsigned long long w3 = (unsigned long long)(unsigned)cy | ((unsigned long long)(unsigned)cz << 32);
+    const unsigned long long w2 = (unsigned long long)(unsigned)i | ((unsigned long long)(unsigned)((cz * g.ny + cy) * g.nx) << 32);
+    const unsigned long long w3 = (unsigned long long)((unsigned)xl | (flags << 29)) | ((unsigned long long)(unsigned)xh << 32);
     asm volatile("st.global.L2::cache_hint.v4.b64 [%0], {%1,%2,%3,%4}, %5;" ::"l"(sorted + p), "l"(w0), "l"(w1), "l"(w2), "l"(w3), "l"(l2_evict_first()) : "memory");
 }
 
-__global__ void __launch_bounds__(256) k_bp_sweep(const Entry *__restrict__ sorted, long long n, Grid g, const unsigned *__restrict__ cellStart,
+__global__ void __launch_bounds__(256, 4) k_bp_sweep(const Entry *__restrict__ sorted, long long n, Grid g, const unsigned *__restrict__ cellStart,
                                                   uint2 *pairs, unsigned long long *nPairs, unsigned long long capacity) {
     __shared__ uint2 stage[BP_STAGE];
     __shared__ unsigned nStage;
@@ -295,43 +318,52 @@ __global__ void __launch_bounds__(256) k_bp_sweep(const Entry *__restrict__ sort
     const unsigned nActive = cellStart[cells];
     if (p < (long long)nActive) {
         const float4 me = *reinterpret_cast<const float4 *>(sorted + p);
-        const uint4 mi = *(reinterpret_cast<const uint4 *>(sorted + p) + 1);
-        const int cx = (int)mi.y, cy = (int)mi.z, cz = (int)mi.w;
-        // x-cells that can hold a partner: every centre within my radius + the largest radius (+ rounding slack)
-        const double reach = ((double)me.w + g.rmaxInfl) * 1.000002 + 8.0 * g.e1;
-        const int xl = min(max((int)floor(((double)me.x - reach) * g.invx), 0), cx);
-        const int xh = max(min((int)floor(((double)me.x + reach) * g.invx), g.nx - 1), cx);
+        const uint4 mi = *(reinterpret_cast<const uint4 *>(sorted + p) + 1);   // idx, rowOwn, xl|flags, xh
+        const unsigned rowOwn = mi.y, xl = mi.z & 0x1fffffffu, fl = mi.z >> 29, xh1 = mi.w + 1u;
         // five contiguous ranges of the sorted array: the own row from the body after me to the end
         // of cell xh, and the rows (dz,dy) = (0,+1), (+1,-1), (+1,0), (+1,+1) over cells xl..xh
         unsigned a0, e0, a1 = 0, e1 = 0, a2 = 0, e2 = 0, a3 = 0, e3 = 0, a4 = 0, e4 = 0;
-        const unsigned rowOwn = (unsigned)((cz * g.ny + cy) * g.nx);
         a0 = (unsigned)p + 1u;
-        e0 = cellStart[rowOwn + xh + 1];
-        const bool yUp = cy + 1 < g.ny, yDn = cy > 0, zUp = cz + 1 < g.nz;
-        if (yUp) { const unsigned r = rowOwn + g.nx; a1 = cellStart[r + xl]; e1 = cellStart[r + xh + 1]; }
-        if (zUp) {
+        e0 = cellStart[rowOwn + xh1];
+        if (fl & 1u) { const unsigned r = rowOwn + g.nx; a1 = cellStart[r + xl]; e1 = cellStart[r + xh1]; }
+        if (fl & 4u) {
             const unsigned rz = rowOwn + (unsigned)(g.nx * g.ny);
-            a3 = cellStart[rz + xl]; e3 = cellStart[rz + xh + 1];
-            if (yDn) { const unsigned r = rz - g.nx; a2 = cellStart[r + xl]; e2 = cellStart[r + xh + 1]; }
-            if (yUp) { const unsigned r = rz + g.nx; a4 = cellStart[r + xl]; e4 = cellStart[r + xh + 1]; }
+            a3 = cellStart[rz + xl]; e3 = cellStart[rz + xh1];
+            if (fl & 2u) { const unsigned r = rz - g.nx; a2 = cellStart[r + xl]; e2 = cellStart[r + xh1]; }
+            if (fl & 1u) { const unsigned r = rz + g.nx; a4 = cellStart[r + xl]; e4 = cellStart[r + xh1]; }
         }
         // one flattened loop over the five ranges: a warp iterates to the longest TOTAL of its lanes,
         // not to the sum of the per-row maxima.  The flat counter k maps to a sorted position through a
-        // branch-free select chain (a divergent "next range" branch ran once per lane and range).
+        // branch-free select chain; four partners per trip, their loads issued together (the test is a
+        // dozen instructions: one load in flight per trip left the loop waiting on L1/L2 latency).
         const unsigned c1 = e0 - a0, c2 = c1 + (e1 - a1), c3 = c2 + (e2 - a2), c4 = c3 + (e3 - a3), total = c4 + (e4 - a4);
         const unsigned o0 = a0, o1 = a1 - c1, o2 = a2 - c2, o3 = a3 - c3, o4 = a4 - c4;
-        for (unsigned k = 0; k < total; k++) {
-            unsigned off = k < c1 ? o0 : o1;
-            off = k < c2 ? off : o2;
-            off = k < c3 ? off : o3;
-            off = k < c4 ? off : o4;
-            const unsigned q = off + k;
-            const float4 ob = *reinterpret_cast<const float4 *>(sorted + q);
-            const float dx = ob.x - me.x, dy = ob.y - me.y, dz = ob.z - me.z;
-            const float rr = ob.w + me.w;
-            const float d2 = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, dx * dx));
-            if (d2 <= rr * rr) {
-                const uint2 pr = make_uint2(mi.x, sorted[q].idx);
+        for (unsigned k0 = 0; k0 < total; k0 += 4) {
+            unsigned q[4];
+            float4 ob[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const unsigned k = k0 + j;
+                unsigned off = k < c1 ? o0 : o1;
+                off = k < c2 ? off : o2;
+                off = k < c3 ? off : o3;
+                off = k < c4 ? off : o4;
+                q[j] = k < total ? off + k : (unsigned)p;   // past the end: re-read myself (masked below)
+                ob[j] = *reinterpret_cast<const float4 *>(sorted + q[j]);
+            }
+            unsigned hits = 0;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const float dx = ob[j].x - me.x, dy = ob[j].y - me.y, dz = ob[j].z - me.z;
+                const float rr = ob[j].w + me.w;
+                const float d2 = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, dx * dx));
+                if (d2 <= rr * rr && k0 + j < total) hits |= 1u << j;
+            }
+            while (hits) {
+                const int j = __ffs(hits) - 1;
+                hits &= hits - 1;
+                const unsigned qq = j == 0 ? q[0] : (j == 1 ? q[1] : (j == 2 ? q[2] : q[3]));
+                const uint2 pr = make_uint2(mi.x, sorted[qq].idx);
                 const unsigned slot = atomicAdd(&nStage, 1u);
                 if (slot < BP_STAGE) stage[slot] = pr;
                 else {   // staging full: straight to global
@@ -444,7 +476,8 @@ struct Broadphase {
     unsigned *occ = nullptr;             // occupancy bit per cell
     long long cellCapacity = 0;
     Entry *entries = nullptr;            // counting path: one sector per sorted body
-    unsigned *rank = nullptr;            // counting path: rank of body i inside its cell
+    uint2 *keyRank = nullptr;            // counting path: cell key and rank of body i inside its cell
+    unsigned *pos = nullptr;             // counting path: sorted position of body i
     unsigned *scanScratch = nullptr;
     bool useRadix = false;               // CUBEZ_BP_SORT=radix
     uint2 *pairs = nullptr;
@@ -475,7 +508,8 @@ static inline cudaError_t bp_alloc(Broadphase &bp, long long n, unsigned long lo
     BPCK(cudaMalloc(&bp.cellRange, sizeof(uint2) * maxCells));
     BPCK(cudaMalloc(&bp.occ, sizeof(unsigned) * (maxCells / 32 + 1)));
     BPCK(cudaMalloc(&bp.entries, sizeof(Entry) * n));
-    BPCK(cudaMalloc(&bp.rank, sizeof(unsigned) * n));
+    BPCK(cudaMalloc(&bp.keyRank, sizeof(uint2) * n));
+    BPCK(cudaMalloc(&bp.pos, sizeof(unsigned) * n));
     BPCK(cudaMalloc(&bp.scanScratch, sizeof(unsigned) * (size_t)czs::scan_scratch_elems(maxCells + 1)));
     { const char *m = getenv("CUBEZ_BP_SORT"); bp.useRadix = m && m[0] == 'r'; }
     bp.pairCapacity = pairCap;
@@ -500,7 +534,8 @@ static inline void bp_free(Broadphase &bp) {
     if (bp.cellRange) cudaFree(bp.cellRange);
     if (bp.occ) cudaFree(bp.occ);
     if (bp.entries) cudaFree(bp.entries);
-    if (bp.rank) cudaFree(bp.rank);
+    if (bp.keyRank) cudaFree(bp.keyRank);
+    if (bp.pos) cudaFree(bp.pos);
     if (bp.scanScratch) cudaFree(bp.scanScratch);
     if (bp.pairs) cudaFree(bp.pairs);
     if (bp.counters) cudaFree(bp.counters);
@@ -579,7 +614,7 @@ static inline cudaError_t bp_candidates(Broadphase &bp, cudaStream_t st, long lo
         const double lx = mx[0] - mn[0];
         double nxd = floor(target / ((double)g.ny * g.nz));
         nxd = std::min(nxd, floor(lx / (minEdge * 0.25)) + 1.0);   // finer than a quarter of the reach buys nothing
-        g.nx = (int)std::max(1.0, std::min(nxd, 2147483647.0));
+        g.nx = (int)std::max(1.0, std::min(nxd, 268435455.0));   // Entry::xlf keeps 29 bits for an x-cell
         const double ex = lx > 0 ? lx / g.nx : 1.0;
         g.invx = 1.0 / ex;
         g.rmaxInfl = (double)(float)((rmax * BP_MARGIN + 4.0 * e1) * 1.000002) * 1.000001;
@@ -595,14 +630,15 @@ static inline cudaError_t bp_candidates(Broadphase &bp, cudaStream_t st, long lo
         if ((e = cudaMemsetAsync(cellStart, 0, sizeof(unsigned) * (cells + 1), st)) != cudaSuccess) return e;
         if ((e = cudaMemsetAsync(bp.counters, 0, sizeof(unsigned long long) * 2, st)) != cudaSuccess) return e;
         if (bp.trace) cudaEventRecord(bp.tev[1], st);
-        k_bp_count<<<nb, 256, 0, st>>>(bp.bounds, n, g, cellStart, bp.rank);
+        k_bp_count<<<nb, 256, 0, st>>>(bp.bounds, n, g, cellStart, bp.keyRank);
         if (bp.trace) cudaEventRecord(bp.tev[2], st);
         int l = czs::exclusive_scan_u32(cellStart, cells + 1, bp.scanScratch, st);
         if (bp.trace) cudaEventRecord(bp.tev[3], st);
-        k_bp_place<<<nb, 256, 0, st>>>(bp.bounds, n, g, cellStart, bp.rank, bp.entries);
+        k_bp_resolve<<<nb, 256, 0, st>>>(bp.keyRank, n, cellStart, bp.pos);
+        k_bp_place<<<nb, 256, 0, st>>>(bp.bounds, n, g, bp.pos, bp.entries);
         if (bp.trace) cudaEventRecord(bp.tev[4], st);
         k_bp_sweep<<<nb, 256, 0, st>>>(bp.entries, n, g, cellStart, bp.pairs, bp.counters, bp.pairCapacity);
-        if (launches) *launches += 3 + l;
+        if (launches) *launches += 4 + l;
         if (bp.trace) {
             cudaEventRecord(bp.tev[5], st);
             cudaEventSynchronize(bp.tev[5]);

@@ -568,7 +568,7 @@ __global__ void __launch_bounds__(1024) k_order_worlds(const int *kContacts, con
     __shared__ unsigned bucketStart[64];
     const int which = blockIdx.x;
     const int *key = which == 0 ? kContacts : (which == 1 ? kPos : kVel);
-    const int shift = which == 0 ? 0 : (which == 1 ? 1 : 2);
+    const int shift = which == 2 ? 1 : 0;   // contacts 0..63, position iterations 0..63+, velocity iterations in twos
     int *order = order3 + (size_t)which * W;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int per = ((count + 31) / 32 + 31) / 32 * 32;   // elements per warp, a multiple of 32

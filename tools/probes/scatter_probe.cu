@@ -45,6 +45,34 @@ __global__ void k_atom(unsigned *tab, unsigned tabN, unsigned *out, unsigned n) 
     if (i >= n) return;
     out[i] = atomicAdd(&tab[hash(i) % tabN], 1u);
 }
+// place-like kernel: flags 1 = stream-read 32 B/body (.cs), 2 = random table read (evict_last), 4 = random 256-bit store,
+// 8 = the store carries an evict_first hint, 16 = table read is a plain load
+__global__ void k_place_like(const double2 *in, const unsigned *tab, unsigned tabN, unsigned long long *out, unsigned *sink, unsigned n, int flags) {
+    unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    unsigned long long a = i, b = 2, c = 3, d = 4;
+    if (flags & 1) { double2 v0 = __ldcs(in + 2 * (size_t)i), v1 = __ldcs(in + 2 * (size_t)i + 1); a = __double_as_longlong(v0.x + v1.y); b = __double_as_longlong(v0.y + v1.x); }
+    unsigned p = perm24(i);
+    if (flags & 2) {
+        unsigned long long pol;
+        asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+        unsigned v;
+        const unsigned *ad = tab + hash(i) % tabN;
+        if (flags & 16) v = *ad;
+        else asm volatile("ld.global.nc.L2::cache_hint.u32 %0, [%1], %2;" : "=r"(v) : "l"(ad), "l"(pol));
+        p ^= (v & 1u);
+        c = v;
+    }
+    if (flags & 4) {
+        if (flags & 8) {
+            unsigned long long pol;
+            asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+            asm volatile("st.global.L2::cache_hint.v4.b64 [%0], {%1,%2,%3,%4}, %5;" ::"l"(out + 4 * (size_t)p), "l"(a), "l"(b), "l"(c), "l"(d), "l"(pol) : "memory");
+        } else {
+            asm volatile("st.global.v4.b64 [%0], {%1,%2,%3,%4};" ::"l"(out + 4 * (size_t)p), "l"(a), "l"(b), "l"(c), "l"(d) : "memory");
+        }
+    } else if ((a ^ b ^ c) == 0x123456789ull) sink[0] = 1;
+}
 int main() {
     const unsigned n = 1u << 24;
     void *buf, *tab, *out;
@@ -69,6 +97,12 @@ int main() {
         time(nm, [&] { k_read4<<<nb, 256>>>((unsigned *)tab, mb << 18, (unsigned *)out, n); }, n * 8.0);
         snprintf(nm, sizeof nm, "atomicAdd random, table %u MB", mb);
         time(nm, [&] { k_atom<<<nb, 256>>>((unsigned *)tab, mb << 18, (unsigned *)out, n); }, n * 8.0);
+    }
+    void *in; cudaMalloc(&in, (size_t)n * 32); cudaMemset(in, 0, (size_t)n * 32);
+    for (int flags : {1, 2, 4, 12, 5, 13, 6, 14, 7, 15, 31, 3}) {
+        char nm[64];
+        snprintf(nm, sizeof nm, "place-like flags=%d (64 MB table)", flags);
+        time(nm, [&] { k_place_like<<<nb, 256>>>((const double2 *)in, (const unsigned *)tab, 16u << 20, (unsigned long long *)buf, (unsigned *)out, n, flags); }, n * 32.0);
     }
     return 0;
 }
