@@ -349,4 +349,52 @@ func (w *World) ChecksumEnergy() (uint64, float64) {
 	check(C.cz_world_checksum_energy(w.h, &c, &e))
 	return uint64(c), float64(e)
 }
+// Observation is the part of the body state StepRL copies back each call; the slices view pinned
+// C memory (cz_host_alloc), so neither side copies.
+type Observation struct {
+	c                                          C.cz_bodies
+	Position, Orientation, Velocity, Rotation []m.Real
+}
+
+// NewObservation allocates pinned arrays for n bodies (position 3, orientation 4, velocity 3, rotation 3).
+func NewObservation(n int) *Observation {
+	o := new(Observation)
+	o.c.n = C.int32_t(n)
+	pin := func(count int) *C.cz_real {
+		var p unsafe.Pointer
+		check(C.cz_host_alloc(ctx, C.uint64_t(count)*C.uint64_t(unsafe.Sizeof(C.cz_real(0))), &p))
+		return (*C.cz_real)(p)
+	}
+	o.c.position, o.c.orientation, o.c.velocity, o.c.rotation = pin(3*n), pin(4*n), pin(3*n), pin(3*n)
+	o.Position, o.Orientation = reals(o.c.position, 3*n), reals(o.c.orientation, 4*n)
+	o.Velocity, o.Rotation = reals(o.c.velocity, 3*n), reals(o.c.rotation, 3*n)
+	return o
+}
+
+// PinnedReals returns a pinned []m.Real (action buffers of StepRL).
+func PinnedReals(count int) []m.Real {
+	var p unsafe.Pointer
+	check(C.cz_host_alloc(ctx, C.uint64_t(count)*C.uint64_t(unsafe.Sizeof(C.cz_real(0))), &p))
+	return reals((*C.cz_real)(p), count)
+}
+
+// StepRL is the RL loop's frame: AddVelocity(addVelocity[3i:]) and AddRotation(addRotation[3i:]) on every
+// body (rigidbody.go:195-202; either slice may be nil), n frames on the device, then obs filled.
+func (w *World) StepRL(addVelocity, addRotation []m.Real, obs *Observation, dt m.Real, n int) C.cz_step_stats {
+	var st C.cz_step_stats
+	var av, ar *C.cz_real
+	if addVelocity != nil {
+		av = (*C.cz_real)(unsafe.Pointer(&addVelocity[0]))
+	}
+	if addRotation != nil {
+		ar = (*C.cz_real)(unsafe.Pointer(&addRotation[0]))
+	}
+	var o *C.cz_bodies
+	if obs != nil {
+		o = &obs.c
+	}
+	check(C.cz_world_step_rl(w.h, av, ar, o, C.cz_real(dt), C.int32_t(n), &st))
+	return st
+}
+
 func (w *World) Close() { C.cz_world_destroy(w.h) }
