@@ -492,7 +492,7 @@ CZD void store_body_work(const czr::Ctx &x, const BodyStore &s, long long gi, in
 }
 
 template <int NT>
-__global__ void __launch_bounds__(NT) k_resolve(WorldParams p, ResolveScratch rs, int useSmem, int maxIterOverride, real dt) {
+__global__ void __launch_bounds__(NT) k_resolve(WorldParams p, ResolveScratch rs, int useSmem, int maxIterOverride, real dt, int hotCap) {
     using namespace czr;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ GroupScratch gs;
@@ -506,7 +506,7 @@ __global__ void __launch_bounds__(NT) k_resolve(WorldParams p, ResolveScratch rs
     x.bs = p.B; x.nC = nC; x.dt = dt; x.store = p.st; x.body_base = (long long)w * p.B;
     x.xb = nullptr; x.xbs = 0; x.mlist = nullptr;
     real *cwbase;
-    if (useSmem) {
+    if (useSmem == 1) {
         x.bw = (real *)smem_raw;
         cwbase = x.bw + BW_NF * p.B;
         x.cb0 = (int *)(cwbase + CW_NREAL * p.Cc);
@@ -536,6 +536,12 @@ __global__ void __launch_bounds__(NT) k_resolve(WorldParams p, ResolveScratch rs
         pi = resolve_loop<32, false>(x, true, maxIter, tid, &status);
         __syncthreads();
         vi = resolve_loop<32, true>(x, true, maxIter, tid, &status);
+    } else if (useSmem == 2 && nC <= hotCap) {   // one large world: hot value + 16-bit body ids in shared memory, cached arg-max
+        real *sHot = (real *)smem_raw;
+        unsigned short *sB0 = (unsigned short *)(sHot + hotCap), *sB1 = sB0 + hotCap;
+        pi = resolve_loop_cta_cached<(NT > 32 ? NT : 64), false>(x, maxIter, &gs, tid, &status, sHot, sB0, sB1);
+        __syncthreads();
+        vi = resolve_loop_cta_cached<(NT > 32 ? NT : 64), true>(x, maxIter, &gs, tid, &status, sHot, sB0, sB1);
     } else {
         pi = resolve_loop_cta<(NT > 32 ? NT : 64), false>(x, maxIter, &gs, tid, &status);
         __syncthreads();

@@ -603,4 +603,92 @@ __device__ __forceinline__ int resolve_loop_cta(const Ctx &x, int maxIterations,
     return used;
 }
 
+
+// The CTA-wide loop for ONE LARGE world (thousands of contacts; cfg3).  Every iteration of
+// resolve_loop_cta scans all contacts twice from L2 (arg-max, then the body-id match of the update):
+// at 14 k contacts that was ~13 of the 16 us of an iteration.  Here the phase's hot value
+// (penetration or desired delta-v) and the body ids (16 bit) of every contact are staged in shared
+// memory, and every thread keeps the arg-max of the contacts it owns (c = tid, tid+NT, ...) in
+// registers: an iteration is a block reduce of the cached maxima, the scalar resolve by warp 0,
+// and an update in which a thread rescans its own contacts only if one of them was touched.
+// Same worst-first order as the reference: ties go to the lowest index in every reduce.
+template <int NT, bool VELOCITY>
+__device__ __forceinline__ int resolve_loop_cta_cached(const Ctx &x0, int maxIterations, GroupScratch *gs, int tid, int *status, real *sHot,
+                                                       unsigned short *sB0, unsigned short *sB1) {
+    const int lane = tid & 31, warp = tid >> 5;
+    const unsigned full = 0xffffffffu;
+    Ctx x = x0;
+    real *gHot = VELOCITY ? x0.ddv : x0.pen;
+    for (int c = tid; c < x.nC; c += NT) {
+        sHot[c] = gHot[c];
+        const int b0 = x.cb0[c], b1 = x.cb1[c];
+        sB0[c] = (unsigned short)b0;
+        sB1[c] = b1 < 0 ? (unsigned short)0xffffu : (unsigned short)b1;
+    }
+    if (VELOCITY) x.ddv = sHot; else x.pen = sHot;
+    __syncthreads();
+    real myBest = R_(0.01);   // positionEpsilon / velocityEpsilon (contact.go:12-13)
+    int myIdx = 0x7fffffff;
+    for (int c = tid; c < x.nC; c += NT) {
+        const real v = sHot[c];
+        if (v > myBest) { myBest = v; myIdx = c; }
+    }
+    int used = 0;
+    while (used < maxIterations) {
+        real best = myBest;
+        int idx = myIdx;
+        warp_argmax<32>(best, idx, full);
+        if (lane == 0) { gs->redv[warp] = best; gs->redi[warp] = idx; }
+        __syncthreads();
+        best = lane < NT / 32 ? gs->redv[lane] : R_(0.01);
+        idx = lane < NT / 32 ? gs->redi[lane] : 0x7fffffff;
+        warp_argmax<32>(best, idx, full);
+        if (idx == 0x7fffffff) break;
+        Change ch;
+        if (warp == 0) {
+            PosCommit pc;
+            VelCommit vc;
+            if (VELOCITY) resolve_velocity(x, idx, ch, vc);
+            else resolve_position(x, idx, best, ch, pc);
+            __syncwarp();
+            if (lane == 0) {
+                if (VELOCITY) { commit_velocity(x, vc); if (vc.status) *status = vc.status; }
+                else commit_position(x, pc);
+#pragma unroll
+                for (int k = 0; k < 3; k++) { gs->chg[k] = ch.lin[0].c[k]; gs->chg[3 + k] = ch.lin[1].c[k]; gs->chg[6 + k] = ch.ang[0].c[k]; gs->chg[9 + k] = ch.ang[1].c[k]; }
+                gs->chb[0] = ch.b[0]; gs->chb[1] = ch.b[1];
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 3; k++) { ch.lin[0].c[k] = gs->chg[k]; ch.lin[1].c[k] = gs->chg[3 + k]; ch.ang[0].c[k] = gs->chg[6 + k]; ch.ang[1].c[k] = gs->chg[9 + k]; }
+        ch.b[0] = gs->chb[0]; ch.b[1] = gs->chb[1];
+        // -1 (no second body) never matches: body ids are < 0xffff and 0xffff marks "nil" in sB1
+        const unsigned m0 = (unsigned)ch.b[0] & 0xffffu, m1 = ch.b[1] < 0 ? 0x10000u : (unsigned)ch.b[1];
+        bool touched = false;
+        for (int c = tid; c < x.nC; c += NT) {
+            const unsigned c0 = sB0[c], c1 = sB1[c];
+            if (c0 == m0 || c0 == m1 || c1 == m0 || c1 == m1) {
+                if (VELOCITY) propagate_velocity(x, c, ch);
+                else propagate_position(x, c, ch);
+                touched = true;
+            }
+        }
+        if (touched) {
+            myBest = R_(0.01); myIdx = 0x7fffffff;
+            for (int c = tid; c < x.nC; c += NT) {
+                const real v = sHot[c];
+                if (v > myBest) { myBest = v; myIdx = c; }
+            }
+        }
+        used++;
+        // the next iteration's first __syncthreads (after the warp reduce) orders these shared-memory
+        // writes before warp 0 reads the winner's hot value
+    }
+    __syncthreads();
+    for (int c = tid; c < x.nC; c += NT) gHot[c] = sHot[c];
+    __syncthreads();
+    return used;
+}
+
 }  // namespace czr

@@ -620,10 +620,22 @@ int cz_world_synchronize(cz_world *w) {
 }  // extern "C"
 
 template <int NT>
-static void launch_resolve(cz_world *w, const WorldParams &p, int maxIterOverride, real dt, bool forceGlobal) {
+static void launch_resolve(cz_world *w, const WorldParams &p, int maxIterOverride, real dt, bool forceGlobal, long long contactsHint = -1) {
     int smem = forceGlobal ? 0 : w->resolveSmem;
-    if (smem > 48 * 1024) cudaFuncSetAttribute(k_resolve<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    k_resolve<NT><<<p.W, NT, smem, w->ctx->stream>>>(p, w->rs, smem > 0 ? 1 : 0, maxIterOverride, dt);
+    int mode = smem > 0 ? 1 : 0, hotCap = 0;
+    if (NT > 32 && mode == 0 && p.B < 0xffff && !czf::env_int("CUBEZ_RESOLVE_NO_CACHE", 0)) {
+        // one large world: stage the hot value (8 B) and 16-bit body ids (4 B) of every contact in shared memory.
+        // The host knows the contact count on the broadphase path; otherwise size for the capacity.
+        long long want = contactsHint >= 0 ? std::min<long long>(contactsHint, p.Cc) : p.Cc;
+        want = (want + 255) / 256 * 256;
+        const size_t bytes = (size_t)want * (sizeof(real) + 4);
+        const size_t limit = w->ctx->smem_optin > 4096 ? w->ctx->smem_optin - 4096 : 0;
+        if (want > 0 && bytes <= limit) { mode = 2; hotCap = (int)want; smem = (int)bytes; }
+    }
+    cudaError_t ea = cudaSuccess;
+    if (smem + 2048 > 48 * 1024) ea = cudaFuncSetAttribute(k_resolve<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    k_resolve<NT><<<p.W, NT, smem, w->ctx->stream>>>(p, w->rs, mode, maxIterOverride, dt, hotCap);
+    if (getenv("CUBEZ_RESOLVE_TRACE")) fprintf(stderr, "[resolve] NT %d mode %d smem %d hotCap %d hint %lld attr %s launch %s\n", NT, mode, smem, hotCap, contactsHint, cudaGetErrorString(ea), cudaGetErrorString(cudaPeekAtLastError()));
 }
 
 // one frame of updateCallback (examples/cubedrop.go:69-75) on the multi-kernel path
@@ -670,7 +682,7 @@ static int world_step_multi(cz_world *w, real dt, long long &launches) {
         launches++;
         CKL(ctx);
         if (w->resolveNT == 32) launch_resolve<32>(w, p, -1, dt, false);
-        else launch_resolve<256>(w, p, -1, dt, false);
+        else launch_resolve<256>(w, p, -1, dt, false, (long long)nCont);
         CKL(ctx);
         launches++;
     } else if (w->nchk > 0) {
