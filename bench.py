@@ -248,6 +248,23 @@ def main():
                        "peak_kind": peak_kind,
                        "ms_per_launch": ms, "body_steps_per_s": K1_BODIES / (ms * 1e-3), "bytes_per_body": K1_BYTES_F64}
 
+    roofline_k1_f32 = roofline_k2_f32 = None
+    if rank == 0 and not args.no_k1:
+        import ctypes as C
+        # the float32 build (the reference's tunable Real): 267 B per body-step for K1, 116 n + 8 q for K2
+        ctx32 = Context.get(local_rank, "f32")
+        ms32, _ = ctx32.bench_integrate(K1_BODIES, warmup=3, steps=50, dt=DT)
+        ach32 = K1_BODIES * 267 / (ms32 * 1e-3) / 1e9
+        roofline_k1_f32 = {"bound": "hbm", "kernel": "k_integrate<false>, float32 build", "achieved": ach32, "peak": peak, "unit": "GB/s",
+                           "frac": ach32 / peak, "traffic": None, "peak_kind": peak_kind, "ms_per_launch": ms32,
+                           "body_steps_per_s": K1_BODIES / (ms32 * 1e-3), "bytes_per_body": 267}
+        ms3, pairs3, sms3 = C.c_float(), C.c_int64(), C.c_float()
+        ctx32.check(ctx32.lib.cz_bench_broadphase(ctx32.h, K1_BODIES, 7, 0.05, 2, 5, C.byref(ms3), C.byref(pairs3), C.byref(sms3)))
+        alg3 = 116 * K1_BODIES + 8 * pairs3.value
+        ach3 = alg3 / (ms3.value * 1e-3) / 1e9
+        roofline_k2_f32 = {"bound": "hbm", "kernel": "K2 sort-based broadphase, float32 bounds", "achieved": ach3, "peak": peak, "unit": "GB/s",
+                           "frac": ach3 / peak, "traffic": None, "peak_kind": peak_kind, "ms_per_frame": ms3.value, "candidate_pairs": pairs3.value}
+
     roofline_k2 = None
     if rank == 0 and not args.no_k1:
         import ctypes as C
@@ -278,6 +295,8 @@ def main():
             "roofline": roofline,
             "roofline_k1": roofline_k1,
             "roofline_k2": roofline_k2,
+            "roofline_k1_f32": roofline_k1_f32,
+            "roofline_k2_f32": roofline_k2_f32,
             "cpu_baseline": {"value": cpu_value, "unit": "world-steps/s", "cores": 1, "kind": "port",
                              "sample": f"256 worlds x {EPISODE} frames, 1 thread, {cpu_s:.1f} s (C++ restatement of the Go loops)"},
             "checksum": hex(red["checksum"]), "energy": red["energy"],
