@@ -272,8 +272,10 @@ def main():
         ctx.check(ctx.lib.cz_bench_broadphase(ctx.h, K1_BODIES, 7, 0.05, 2, 5, C.byref(ms2), C.byref(pairs), C.byref(sms)))
         alg = 148 * K1_BODIES + 8 * pairs.value          # 148 n + 8 q bytes (f64 bounds, 4-pass radix sort)
         ach2 = alg / (ms2.value * 1e-3) / 1e9
-        roofline_k2 = {"bound": "hbm", "kernel": "K2 sort-based broadphase (one-pass counting sort by cell key: count, scan, place; neighbour sweep): 16Mi unit spheres, 5% fill",
-                       "achieved": ach2, "peak": peak, "unit": "GB/s", "frac": ach2 / peak, "traffic": None, "peak_kind": peak_kind,
+        roofline_k2 = {"bound": "hbm", "kernel": "K2 sort-based broadphase (one-pass counting sort by cell key: count, scan, resolve, place; neighbour sweep): 16Mi unit spheres, 5% fill",
+                       "achieved": ach2, "peak": peak, "unit": "GB/s", "frac": ach2 / peak,
+                       "traffic": 3.34e9,   # dram read+write of memset, count, scan, resolve, place, sweep per frame (ncu --set full, profiles/r01_k2_counting_sort.txt); algorithmic 2.51e9
+                       "peak_kind": peak_kind,
                        "ms_per_frame": ms2.value, "lsd_radix_sort_alone_ms": sms.value, "candidate_pairs": pairs.value}
 
     if rank == 0:
