@@ -269,13 +269,13 @@ struct cz_world {
         int chunks = 1;
         cudaStream_t sUp = nullptr, sDown = nullptr;
         int nComp = 1;                               // compute streams: chunk c runs on stream c % nComp, so kernel tails overlap
-        cudaStream_t sComp[4] = {nullptr, nullptr, nullptr, nullptr};   // [0] is the context stream
+        cudaStream_t sComp[16] = {};                 // own streams, earlier chunks at higher priority
         std::vector<cudaEvent_t> evUp, evComp;
         cudaEvent_t evBegin = nullptr, evDownDone = nullptr;
         real *dIn = nullptr, *dOut = nullptr;        // per-field device staging
         uint8_t *dFlags = nullptr;                   // awake_in, can_sleep_in, awake_out
         unsigned int *dNext = nullptr;               // per-chunk world counters
-        real *coldX[4] = {nullptr, nullptr, nullptr, nullptr};   // cold-contact scratch per extra compute stream (kernels of different chunks co-run)
+        real *coldX[16] = {};                        // cold-contact scratch per compute stream beyond the first (kernels of different chunks co-run)
     } pipe;
     real *h_pin = nullptr;
     size_t h_pin_bytes = 0;
@@ -484,11 +484,11 @@ int cz_world_destroy(cz_world *w) {
     if (w->h_stats) cudaFreeHost(w->h_stats);
     if (w->h_pin) cudaFreeHost(w->h_pin);
     if (w->pipe.ready) {
-        cudaStreamDestroy(w->pipe.sUp); cudaStreamDestroy(w->pipe.sDown); for (int k = 1; k < w->pipe.nComp; k++) cudaStreamDestroy(w->pipe.sComp[k]);
+        cudaStreamDestroy(w->pipe.sUp); cudaStreamDestroy(w->pipe.sDown); for (int k = 0; k < w->pipe.nComp; k++) if (w->pipe.sComp[k] != w->ctx->stream) cudaStreamDestroy(w->pipe.sComp[k]);
         for (auto e : w->pipe.evUp) cudaEventDestroy(e);
         for (auto e : w->pipe.evComp) cudaEventDestroy(e);
         cudaEventDestroy(w->pipe.evBegin); cudaEventDestroy(w->pipe.evDownDone);
-        cudaFree(w->pipe.dIn); cudaFree(w->pipe.dOut); cudaFree(w->pipe.dFlags); cudaFree(w->pipe.dNext); for (int k = 1; k < 4; k++) if (w->pipe.coldX[k]) cudaFree(w->pipe.coldX[k]);
+        cudaFree(w->pipe.dIn); cudaFree(w->pipe.dOut); cudaFree(w->pipe.dFlags); cudaFree(w->pipe.dNext); for (int k = 1; k < 16; k++) if (w->pipe.coldX[k]) cudaFree(w->pipe.coldX[k]);
     }
     delete w;
     return CZ_OK;
@@ -917,9 +917,19 @@ static int host_pipe_init(cz_world *w) {
     pp.chunks = chunks;
     CK(ctx, cudaStreamCreateWithFlags(&pp.sUp, cudaStreamNonBlocking));
     CK(ctx, cudaStreamCreateWithFlags(&pp.sDown, cudaStreamNonBlocking));
-    pp.nComp = w->useFused ? std::min(4, std::max(1, czf::env_int("CUBEZ_HOST_COMP_STREAMS", 3))) : 1;
-    pp.sComp[0] = ctx->stream;
-    for (int k = 1; k < pp.nComp; k++) CK(ctx, cudaStreamCreateWithFlags(&pp.sComp[k], cudaStreamNonBlocking));
+    // Chunk c computes on stream c % nComp, earlier streams at higher priority.  Measured (profiles/): 3 streams are
+    // enough to overlap kernel tails; one stream per chunk or priorities change nothing, because a chunk's four
+    // dependent launches (order, A, B, C) take ~1 ms however small the chunk is (per-world latency), and from the
+    // first download on the pipeline is bound by the D2H stream.
+    pp.nComp = w->useFused ? std::min(16, std::max(1, czf::env_int("CUBEZ_HOST_COMP_STREAMS", 3))) : 1;
+    int prLeast = 0, prGreatest = 0;
+    CK(ctx, cudaDeviceGetStreamPriorityRange(&prLeast, &prGreatest));   // numerically lower = higher priority
+    const bool usePrio = czf::env_int("CUBEZ_HOST_PRIO", 1) != 0;
+    for (int k = 0; k < pp.nComp; k++) {
+        if (!w->useFused) { pp.sComp[k] = ctx->stream; continue; }   // the multi-kernel path steps on the context stream
+        const int pr = usePrio ? std::min(prLeast, prGreatest + k) : prLeast;
+        CK(ctx, cudaStreamCreateWithPriority(&pp.sComp[k], cudaStreamNonBlocking, pr));
+    }
     pp.evUp.resize(chunks); pp.evComp.resize(chunks);
     for (int c = 0; c < chunks; c++) {
         CK(ctx, cudaEventCreateWithFlags(&pp.evUp[c], cudaEventDisableTiming));
@@ -970,7 +980,7 @@ int cz_world_step_host(cz_world *w, cz_bodies *io, cz_real dt, int32_t n_steps, 
     CK(ctx, cudaEventRecord(pp.evBegin, ctx->stream));
     CK(ctx, cudaStreamWaitEvent(pp.sUp, pp.evBegin, 0));     // staging buffers of the previous call are free
     CK(ctx, cudaStreamWaitEvent(pp.sDown, pp.evBegin, 0));
-    for (int k = 1; k < pp.nComp; k++) CK(ctx, cudaStreamWaitEvent(pp.sComp[k], pp.evBegin, 0));
+    for (int k = 0; k < pp.nComp; k++) CK(ctx, cudaStreamWaitEvent(pp.sComp[k], pp.evBegin, 0));
     long long launches = 0;
     std::vector<cudaEvent_t> trEv;   // trace only: [chunk][up end, compute begin, compute end, down end]
     if (hostTrace) { trEv.resize((size_t)pp.chunks * 4); for (auto &e : trEv) cudaEventCreate(&e); }
@@ -991,7 +1001,7 @@ int cz_world_step_host(cz_world *w, cz_bodies *io, cz_real dt, int32_t n_steps, 
             (io->angular_damping && std::memcmp(w->b.h_angd.data() + b0, io->angular_damping + b0, sizeof(real) * nb) != 0)) {
             // rare: the host changed damping.  Drain the compute streams, refresh every Pow factor, go on.
             CK(ctx, cudaStreamSynchronize(ctx->stream));
-            for (int k = 1; k < pp.nComp; k++) CK(ctx, cudaStreamSynchronize(pp.sComp[k]));
+            for (int k = 0; k < pp.nComp; k++) CK(ctx, cudaStreamSynchronize(pp.sComp[k]));
             if ((rc = upload_bodies(w->b, 0, io->n, &damp))) return rc;
             if ((rc = world_prepare_step(w, dt))) return rc;
             CK(ctx, cudaStreamSynchronize(ctx->stream));
@@ -1122,7 +1132,7 @@ int cz_world_step_rl(cz_world *w, const cz_real *add_velocity, const cz_real *ad
     CK(ctx, cudaEventRecord(pp.evBegin, ctx->stream));
     CK(ctx, cudaStreamWaitEvent(pp.sUp, pp.evBegin, 0));
     CK(ctx, cudaStreamWaitEvent(pp.sDown, pp.evBegin, 0));
-    for (int k = 1; k < pp.nComp; k++) CK(ctx, cudaStreamWaitEvent(pp.sComp[k], pp.evBegin, 0));
+    for (int k = 0; k < pp.nComp; k++) CK(ctx, cudaStreamWaitEvent(pp.sComp[k], pp.evBegin, 0));
     long long launches = 0;
     // observations are a third of the full state: fewer, larger chunks keep the fused kernels efficient
     const int chunks = std::max(1, std::min(pp.chunks, czf::env_int("CUBEZ_RL_CHUNKS", 4)));
