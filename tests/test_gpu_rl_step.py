@@ -94,3 +94,28 @@ def test_step_rl_with_episode_resets_f32():
         for f in BatchedWorld.OBS_FIELDS:
             assert np.array_equal(getattr(obs, f), getattr(c, f)), (frame, f)
     gpu.close()
+
+
+def test_step_rl_matches_golden_fixture():
+    """cz_world_step_rl against the committed fixture tests/golden/rl12_f64.npz (no oracle at run time)."""
+    from golden import make_golden_rl as rl
+    from golden_cases import load_golden
+    gold = load_golden("rl12_f64")
+    sc = rl.make_scene()
+    ctx = Context.get(0, "f64")
+    gpu = BatchedWorld.from_scene(sc, contacts_per_world=64)
+    nb = rl.N_WORLDS * sc.bodies_per_world
+    av, ar = ctx.pinned_array((nb, 3)), ctx.pinned_array((nb, 3))
+    obs = ctx.pinned_bodies(nb, fields=rl.OBS)
+    for call in range(rl.CALLS):
+        a, r = rl.actions(call, nb, np.float64)
+        if a is not None:
+            av[...] = a
+        if r is not None:
+            ar[...] = r
+        st = gpu.step_rl(av if a is not None else None, ar if r is not None else None, obs, sc.dt, rl.FRAMES_PER_CALL)
+        assert (st["contacts"], st["pos_iterations"], st["vel_iterations"]) == tuple(int(v) for v in gold["counts"][call]), call
+    for f in rl.OBS:
+        assert np.array_equal(getattr(obs, f), gold[f]), f
+    assert gpu.checksum_energy()[0] == int(gold["checksum"])
+    gpu.close()

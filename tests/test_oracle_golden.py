@@ -63,3 +63,14 @@ def test_oracle_object_api_matches_world_loop():
     ref = w.download()
     for f in STATE_FIELDS + ("transform", "inverse_inertia_tensor_world", "last_frame_acceleration"):
         assert np.array_equal(getattr(b, f), getattr(ref, f)), f
+
+
+def test_oracle_rl_loop_matches_golden():
+    """The RL-style loop (AddVelocity / AddRotation on every body, then frames) through the oracle
+    reproduces tests/golden/rl12_f64.npz (made by tests/golden/make_golden_rl.py)."""
+    from golden import make_golden_rl as rl
+    gold = load_golden("rl12_f64")
+    out = rl.run_oracle()
+    assert np.array_equal(out["counts"], gold["counts"]) and int(out["checksum"]) == int(gold["checksum"])
+    for f in rl.OBS:
+        assert np.array_equal(out[f], gold[f]), f
