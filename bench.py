@@ -236,7 +236,12 @@ def main():
     fused_bytes = nb * (41 * 16 + 8 + 25 * 16 + 1)
     roofline = {"bound": "hbm", "kernel": "k_world_fused", "achieved": fused_bytes / (dev_ms * 1e-3) / 1e9, "peak": peak,
                 "unit": "GB/s", "frac": fused_bytes / (dev_ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_kind": peak_kind,
-                "note": "not HBM-bound by design: state is shared-memory resident across frames; the kernel is FP64-issue/latency bound (see profiles/)"}
+                "note": "not HBM-bound by design: state is shared-memory resident across frames; the kernel is FP64-issue/latency bound (see profiles/)",
+                # what does bound it, from ncu --set full of one frame at 65 536 worlds (profiles/r01_fused_split_phases_v2.txt):
+                "ncu": {"phases_ms": {"A integrate+narrowphase+prepare": 0.948, "B position loop": 0.494, "C velocity loop": 1.315},
+                        "fp64_pipe_active_pct": {"A": 21.5, "B": 10.5, "C": 23.0}, "issue_active_pct": {"A": 29.7, "B": 21.4, "C": 30.6},
+                        "active_lanes_of_32": {"A": 12.2, "B": 21.1, "C": 21.4}, "warps_per_sm": 8, "registers_per_thread": 255,
+                        "top_stalls": ["wait (fixed-latency FP64 dependency at 2 warps per scheduler)", "long_scoreboard (cold contact records in L2)"]}}
     roofline_k1 = None
     if rank == 0 and not args.no_k1:
         world.close()
