@@ -60,8 +60,8 @@ struct FusedPlan {
 static inline size_t world_bytes(int B, int Cc, int nchk) {
     size_t reals = (size_t)FB_NF * B + 2 * (size_t)Cc;
     size_t ints = 2 * (size_t)Cc + 2 * (size_t)B;
-    size_t shorts = 2 * (size_t)nchk;          // per-check info + the queue of checks that need a full pair test
-    size_t bytes = reals * sizeof(real) + ints * sizeof(int) + shorts * sizeof(unsigned short) + (size_t)nchk + (size_t)Cc;
+    size_t shorts = 3 * (size_t)nchk;          // per-check info + the queues of checks that need a full test + plane-check base slots
+    size_t bytes = reals * sizeof(real) + ints * sizeof(int) + shorts * sizeof(unsigned short) + 2 * (size_t)nchk + (size_t)Cc;
     return (bytes + 15) / 16 * 16;
 }
 
@@ -128,8 +128,10 @@ struct Staged {
     int *flags, *active;  // [B]
     real *cold;           // global scratch, AoS [contact][CW_NCOLD]
     real *pairGen;        // global scratch: contact of queued pair test q, [q][8]
-    unsigned short *info, *queue;   // [nchk] per-check vertex mask / queue slot; queue of check ids
+    unsigned short *info, *queue;   // [nchk] per-check queue slot; queue of check ids (pair tests from the front, plane checks from the back)
+    unsigned short *pbase;          // [nchk] first contact slot of queued plane check q
     unsigned char *cnt;   // [nchk] contacts produced by check k
+    unsigned char *pmask; // [nchk] vertex mask of queued plane check q
 };
 
 __device__ __forceinline__ ColliderView staged_collider(const Staged &s, int i) {
@@ -239,8 +241,10 @@ __global__ void __launch_bounds__(128, MINB) k_world_fused(WorldParams p, FusedP
     s.active = s.flags + B;
     s.info = (unsigned short *)(s.active + B);
     s.queue = s.info + p.nchk;
-    s.cnt = (unsigned char *)(s.queue + p.nchk);
-    unsigned char *mlist = s.cnt + p.nchk;
+    s.pbase = s.queue + p.nchk;
+    s.cnt = (unsigned char *)(s.pbase + p.nchk);
+    s.pmask = s.cnt + p.nchk;
+    unsigned char *mlist = s.pmask + p.nchk;
     real *const groupScratch = fp.cold + ((size_t)blockIdx.x * fp.groupsPerBlock + grp) * fp.coldReals;
     s.cold = groupScratch;
     s.pairGen = groupScratch + (size_t)Cc * CW_NCOLD;
@@ -348,33 +352,28 @@ __global__ void __launch_bounds__(128, MINB) k_world_fused(WorldParams p, FusedP
             __syncwarp(mask);
             if (LOCKSTEP && fp.lockstep >= 2) __syncthreads();
 
-            // ---- generateContacts (cubedrop.go:42-67), three passes --------------------------------
-            // A: every check gets its cheap test: plane checks are evaluated (vertex mask), pair
-            //    checks that survive the bounding-sphere rejection are queued.  B: the queued pair
-            //    tests (15-axis SAT etc.) run densely, one per lane — in a spread scene only a few
-            //    of the all-pairs checks reach this pass, and running them in place left ~3 of 32
-            //    lanes busy.  C: order-preserving emission in check order (the reference's append
-            //    order): prefix scan of the per-check contact counts.
-            int nQ = 0;
+            // ---- generateContacts (cubedrop.go:42-67) -----------------------------------------------------
+            // A: every check is classified with cheap tests only: plane checks are queued (from the back of
+            //    the queue), pair checks that survive the bounding-sphere rejection are queued (from the
+            //    front).  B1 / B2: the queued plane checks (8 vertex transforms) and pair tests (15-axis SAT
+            //    etc.) run densely, one per lane — in the all-pairs schedule one check in nine is a plane
+            //    check and a few pair checks reach the full test; evaluated in place they left 1 of 8 lanes
+            //    busy (ncu: 3.5 of 32 lanes active on those lines).  C: order-preserving slot assignment in
+            //    check order (the reference's append order): prefix scan of the per-check contact counts; pair
+            //    contacts are copied to their slot.  D: plane contacts are produced densely, one (check,
+            //    vertex) per lane, at slot = base of the check + rank of the vertex among the set bits.
+            int nQ = 0, nP = 0;
             const unsigned gshift = (threadIdx.x & 31u) & ~(unsigned)(G - 1);
             const unsigned gbits = G == 32 ? 0xffffffffu : ((1u << G) - 1u);
+            unsigned short *const queueP = s.queue + (p.nchk - 1);   // queueP[-q]
             for (int k0 = 0; k0 < p.nchk; k0 += G) {
                 const int k = k0 + tid;
-                bool need = false;
+                bool need = false, plane = false;
                 if (live && k < p.nchk) {
                     int a = 0, b2 = 0;
-                    unsigned cnt = 0, info = 0;
                     if (decode_check(p, k, a, b2) && !(a < 0 && b2 < 0) && (a < 0 || staged_active(s, a, step)) && (b2 < 0 || staged_active(s, b2, step))) {
                         if (a < 0 || b2 < 0) {
-                            const int ci = a < 0 ? b2 : a, pi = a < 0 ? -a - 1 : -b2 - 1;
-                            ColliderView c = staged_collider(s, ci);
-                            if (c.shape == CZ_SHAPE_SPHERE) {
-                                GenContact gc;
-                                cnt = czn::sphere_halfspace(c, p.planes[pi], gc) ? 1u : 0u;
-                            } else if (c.shape == CZ_SHAPE_CUBE) {
-                                info = czn::cube_halfspace_mask(c, p.planes[pi]);
-                                cnt = (unsigned)cz_popc(info);
-                            }
+                            plane = (s.flags[a < 0 ? b2 : a] & FF_SHAPE_MASK) != CZ_SHAPE_NONE;
                         } else {
                             // bounding-sphere rejection needs only the centres and sizes
                             ColliderView one, two;
@@ -388,15 +387,38 @@ __global__ void __launch_bounds__(128, MINB) k_world_fused(WorldParams p, FusedP
                             need = !czn::bounding_reject(one, two);
                         }
                     }
-                    s.cnt[k] = (unsigned char)cnt;
-                    s.info[k] = (unsigned short)info;
+                    s.cnt[k] = 0;
+                    s.info[k] = 0;
                 }
-                const unsigned ball = (__ballot_sync(mask, need) >> gshift) & gbits;
-                if (need) s.queue[nQ + __popc(ball & ((1u << tid) - 1u))] = (unsigned short)k;
-                nQ += __popc(ball);
+                const unsigned ballQ = (__ballot_sync(mask, need) >> gshift) & gbits;
+                const unsigned ballP = (__ballot_sync(mask, plane) >> gshift) & gbits;
+                if (need) s.queue[nQ + __popc(ballQ & ((1u << tid) - 1u))] = (unsigned short)k;
+                if (plane) {
+                    const int qp = nP + __popc(ballP & ((1u << tid) - 1u));
+                    queueP[-qp] = (unsigned short)k;
+                    s.info[k] = (unsigned short)qp;
+                }
+                nQ += __popc(ballQ);
+                nP += __popc(ballP);
             }
             __syncwarp(mask);
-            for (int q = tid; q < nQ; q += G) {   // pass B: dense pair tests
+            for (int qp = tid; qp < nP; qp += G) {   // pass B1: dense plane checks
+                const int k = queueP[-qp];
+                int a = 0, b2 = 0;
+                decode_check(p, k, a, b2);
+                const int ci = a < 0 ? b2 : a, pi = a < 0 ? -a - 1 : -b2 - 1;
+                ColliderView c = staged_collider(s, ci);
+                unsigned vm = 0;
+                if (c.shape == CZ_SHAPE_SPHERE) {
+                    GenContact gc;
+                    vm = czn::sphere_halfspace(c, p.planes[pi], gc) ? 1u : 0u;
+                } else if (c.shape == CZ_SHAPE_CUBE) {
+                    vm = czn::cube_halfspace_mask(c, p.planes[pi]);
+                }
+                s.cnt[k] = (unsigned char)cz_popc(vm);
+                s.pmask[qp] = (unsigned char)vm;
+            }
+            for (int q = tid; q < nQ; q += G) {   // pass B2: dense pair tests
                 const int k = s.queue[q];
                 int a = 0, b2 = 0;
                 decode_check(p, k, a, b2);
@@ -416,7 +438,7 @@ __global__ void __launch_bounds__(128, MINB) k_world_fused(WorldParams p, FusedP
                 }
             }
             __syncwarp(mask);
-            for (int k0 = 0; k0 < p.nchk; k0 += G) {   // pass C: ordered emission (uniform trip count: warp-wide scan)
+            for (int k0 = 0; k0 < p.nchk; k0 += G) {   // pass C: ordered slots (uniform trip count: warp-wide scan)
                 const int k = k0 + tid;
                 const int cnt = (live && k < p.nchk) ? (int)s.cnt[k] : 0;
                 int incl = cnt;
@@ -426,29 +448,12 @@ __global__ void __launch_bounds__(128, MINB) k_world_fused(WorldParams p, FusedP
                     if (tid >= o) incl += t;
                 }
                 const int total = __shfl_sync(mask, incl, G - 1, G);
-                int slot = nC + incl - cnt;
+                const int slot = nC + incl - cnt;
                 if (cnt > 0) {
                     int a = 0, b2 = 0;
                     decode_check(p, k, a, b2);
                     if (a < 0 || b2 < 0) {
-                        const int ci = a < 0 ? b2 : a, pi = a < 0 ? -a - 1 : -b2 - 1;
-                        ColliderView c = staged_collider(s, ci);
-                        if (c.shape == CZ_SHAPE_SPHERE) {
-                            GenContact gc;
-                            czn::sphere_halfspace(c, p.planes[pi], gc);
-                            if (slot < Cc) stage_gen(s, slot, gc);
-                        } else {
-                            const unsigned vm = s.info[k];
-#pragma unroll 1
-                            for (int v = 0; v < 8; v++) {
-                                if (vm & (1u << v)) {
-                                    GenContact gc;
-                                    czn::cube_halfspace_contact(c, p.planes[pi], v, gc);
-                                    if (slot < Cc) stage_gen(s, slot, gc);
-                                    slot++;
-                                }
-                            }
-                        }
+                        s.pbase[s.info[k]] = (unsigned short)min(slot, 0xffff);
                     } else if (slot < Cc) {
                         const real *r = s.pairGen + (size_t)s.info[k] * 8;
                         GenContact gc;
@@ -461,6 +466,23 @@ __global__ void __launch_bounds__(128, MINB) k_world_fused(WorldParams p, FusedP
                     }
                 }
                 nC += total;
+            }
+            __syncwarp(mask);
+            for (int item = tid; item < nP * 8; item += G) {   // pass D: dense plane contacts, one (check, vertex) per lane
+                const int qp = item >> 3, v = item & 7;
+                const unsigned vm = s.pmask[qp];
+                if (!((vm >> v) & 1u)) continue;
+                const int slot = (int)s.pbase[qp] + cz_popc(vm & ((1u << v) - 1u));
+                if (slot >= Cc) continue;
+                const int k = queueP[-qp];
+                int a = 0, b2 = 0;
+                decode_check(p, k, a, b2);
+                const int ci = a < 0 ? b2 : a, pi = a < 0 ? -a - 1 : -b2 - 1;
+                ColliderView c = staged_collider(s, ci);
+                GenContact gc;
+                if (c.shape == CZ_SHAPE_SPHERE) czn::sphere_halfspace(c, p.planes[pi], gc);
+                else czn::cube_halfspace_contact(c, p.planes[pi], v, gc);
+                stage_gen(s, slot, gc);
             }
             __syncwarp(mask);
             accContacts += (unsigned long long)nC;
