@@ -289,7 +289,14 @@ CZD ColliderView load_collider(const BodyStore &s, long long gi, int local) {
 CZD bool decode_check(const WorldParams &p, int k, int &a, int &b) {
     if (p.schedule == CZ_SCHED_ALL_PAIRS_ORDERED) {
         int per = p.P + p.B;
+#ifdef __CUDA_ARCH__
+        // k / per without the ~20-instruction integer division: (k + 0.5) / per is at least 0.5 / per away from an
+        // integer, far more than the float rounding for k < 2^16, per < 2^10 (exact; checked exhaustively in the tests)
+        int i = (k < 65536 && per < 1024) ? (int)(((float)k + 0.5f) * __frcp_rn((float)per)) : k / per;
+        int slot = k - i * per;
+#else
         int i = k / per, slot = k - i * per;
+#endif
         a = i;
         if (slot < p.P) { b = -(slot + 1); return true; }
         b = slot - p.P;

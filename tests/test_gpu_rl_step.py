@@ -119,3 +119,29 @@ def test_step_rl_matches_golden_fixture():
         assert np.array_equal(getattr(obs, f), gold[f]), f
     assert gpu.checksum_energy()[0] == int(gold["checksum"])
     gpu.close()
+
+
+@pytest.mark.parametrize("n_worlds", [1, 3, 9])
+def test_step_rl_tiny_batches_and_zero_frames(n_worlds):
+    """Fewer worlds than pipeline chunks; n_steps = 0 applies the actions and returns the observation."""
+    sc = scenes.batched_cubedrop(n_worlds=n_worlds)
+    ctx = Context.get(0, "f64")
+    gpu = BatchedWorld.from_scene(sc, contacts_per_world=64)
+    cpu = OracleWorld.from_scene(sc)
+    nb = n_worlds * 8
+    av = ctx.pinned_array((nb, 3))
+    av[...] = np.random.default_rng(n_worlds).uniform(-1, 1, (nb, 3))
+    obs = ctx.pinned_bodies(nb, fields=BatchedWorld.OBS_FIELDS)
+    gpu.step_rl(av, None, obs, sc.dt, 0)
+    oracle_apply(cpu, av, None)
+    c = cpu.download()
+    for f in BatchedWorld.OBS_FIELDS:
+        assert np.array_equal(getattr(obs, f), getattr(c, f)), f
+    for _ in range(20):
+        gpu.step_rl(av, None, obs, sc.dt, 6)
+        oracle_apply(cpu, av, None)
+        cpu.step(sc.dt, 6)
+    c = cpu.download()
+    for f in BatchedWorld.OBS_FIELDS:
+        assert np.array_equal(getattr(obs, f), getattr(c, f)), f
+    gpu.close()
