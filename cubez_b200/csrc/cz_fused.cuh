@@ -46,6 +46,7 @@ struct FusedPlan {
     size_t worldBytes;   // shared memory per group
     size_t smemBytes;    // per CTA
     int keepContacts;
+    int bodyMasks;       // per-body contact bitmasks drive the propagation (contact capacity <= 64)
     int lockstep;        // CTA barriers between the phases of a frame (instruction-cache locality)
     real *cold;          // [grid*groupsPerBlock][Cc*CW_NCOLD]
     size_t coldReals;    // per group
@@ -58,7 +59,7 @@ struct FusedPlan {
 };
 
 static inline size_t world_bytes(int B, int Cc, int nchk) {
-    size_t reals = (size_t)FB_NF * B + 2 * (size_t)Cc;
+    size_t reals = (size_t)FB_NF * B + 2 * (size_t)Cc + (size_t)B;   // + one 64-bit contact mask per body
     size_t ints = 2 * (size_t)Cc + 2 * (size_t)B;
     size_t shorts = 3 * (size_t)nchk;          // per-check info + the queues of checks that need a full test + plane-check base slots
     size_t bytes = reals * sizeof(real) + ints * sizeof(int) + shorts * sizeof(unsigned short) + 2 * (size_t)nchk + (size_t)Cc;
@@ -104,6 +105,7 @@ static inline bool plan(FusedPlan &fp, int B, int P, int Cc, int nchk, int sched
     fp.worldBytes = wb;
     fp.smemBytes = smem;
     fp.keepContacts = env_int("CUBEZ_FUSED_KEEP_CONTACTS", 1);
+    fp.bodyMasks = env_int("CUBEZ_FUSED_BODY_MASKS", 1);
     // Large batches run one launch per phase of the frame (every warp of the GPU is then in the same
     // code region: +15 % on 65 536 worlds); small batches keep the single persistent launch.
     fp.split = env_int("CUBEZ_FUSED_SPLIT", W >= 8192 ? 1 : 0);
@@ -235,7 +237,8 @@ __global__ void __launch_bounds__(128, MINB) k_world_fused(WorldParams p, FusedP
     s.fb = (real *)base; s.bs = B;
     s.pen = s.fb + (size_t)FB_NF * B;
     s.ddv = s.pen + Cc;
-    s.cb0 = (int *)(s.ddv + Cc);
+    unsigned long long *const bmask = (unsigned long long *)(s.ddv + Cc);   // [B]
+    s.cb0 = (int *)(bmask + B);
     s.cb1 = s.cb0 + Cc;
     s.flags = s.cb1 + Cc;
     s.active = s.flags + B;
@@ -256,6 +259,7 @@ __global__ void __launch_bounds__(128, MINB) k_world_fused(WorldParams p, FusedP
     x.pen = s.pen; x.ddv = s.ddv; x.fric = nullptr; x.rest = nullptr;
     x.cb0 = s.cb0; x.cb1 = s.cb1; x.nC = 0; x.dt = dt;
     x.mlist = Cc <= 256 ? mlist : nullptr;
+    x.bmask = (Cc <= 64 && fp.bodyMasks) ? bmask : nullptr;
     x.xb = nullptr; x.xbs = 0; x.store = st;
     GenView gv;
     gv.pn = s.cold; gv.fs = 1; gv.cs = CW_NCOLD; gv.pen = s.pen; gv.fric = nullptr; gv.rest = nullptr; gv.b0 = s.cb0; gv.b1 = s.cb1;
@@ -516,6 +520,7 @@ __global__ void __launch_bounds__(128, MINB) k_world_fused(WorldParams p, FusedP
                 x.nC = nC;
             }
             int st2 = 0;
+            if ((PH & (PH_B | PH_C)) && x.bmask) build_body_masks<G>(x, B, tid);   // group-uniform: every lane of a group has the same x.nC
             if (PH & PH_B) {
                 lastPos = resolve_loop<G, false>(x, nC > 0, nC * 8, tid, &st2);
                 accPos += (unsigned long long)lastPos;

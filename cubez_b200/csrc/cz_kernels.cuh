@@ -511,7 +511,7 @@ __global__ void __launch_bounds__(NT) k_resolve(WorldParams p, ResolveScratch rs
     }
     Ctx x;
     x.bs = p.B; x.nC = nC; x.dt = dt; x.store = p.st; x.body_base = (long long)w * p.B;
-    x.xb = nullptr; x.xbs = 0; x.mlist = nullptr;
+    x.xb = nullptr; x.xbs = 0; x.mlist = nullptr; x.bmask = nullptr;
     real *cwbase;
     if (useSmem == 1) {
         x.bw = (real *)smem_raw;

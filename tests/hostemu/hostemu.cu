@@ -180,7 +180,7 @@ int cze_run(cz_bodies *io, const cz_colliders *col, const cz_planes *planes, int
             // cold fields laid out AoS here (the fused kernel's layout); k_resolve uses SoA
             x.cold = cw.data(); x.cfs = 1; x.ccs = CW_NCOLD;
             x.pen = cw.data() + (size_t)CW_NCOLD * contact_cap; x.ddv = x.pen + contact_cap; x.fric = x.ddv + contact_cap; x.rest = x.fric + contact_cap;
-            x.nC = nC; x.dt = dt; x.xb = nullptr; x.xbs = 0; x.mlist = nullptr; x.store = h.st; x.body_base = 0;
+            x.nC = nC; x.dt = dt; x.xb = nullptr; x.xbs = 0; x.mlist = nullptr; x.bmask = nullptr; x.store = h.st; x.body_base = 0;
             GenView g;
             g.pn = gen.data(); g.fs = contact_cap; g.cs = 1; g.pen = gen.data() + (size_t)G_PEN * contact_cap;
             g.fric = gen.data() + (size_t)G_FRIC * contact_cap; g.rest = gen.data() + (size_t)G_REST * contact_cap;
