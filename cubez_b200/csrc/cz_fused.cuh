@@ -672,7 +672,7 @@ static inline int launch(const FusedPlan &fp, const WorldParams &p, real dt, rea
             else CZF_LAUNCH(GG, 3, false, PH_ALL);                                                                  \
         }                                                                                                           \
     } while (0)
-    if (fp.G == 8) CZF_LAUNCH_G(8);
+if (fp.G == 8) CZF_LAUNCH_G(8);
     else if (fp.G == 16) CZF_LAUNCH_G(16);
     else CZF_LAUNCH_G(32);
 #undef CZF_LAUNCH_G

@@ -468,15 +468,15 @@ __device__ __forceinline__ void warp_argmax(real &v, int &i, unsigned mask) {
 // touches body b.  Called by the NT lanes that own the world, after the contact body ids are final
 // (prepare_contact may swap them).  Contacts do not change bodies inside the loops.
 template <int NT>
-__device__ __forceinline__ void build_body_masks(const Ctx &x, int nBodies, int tid) {
+__device__ __forceinline__ void build_body_masks(const Ctx &x, int nBodies, int tid, unsigned lanes = 0xffffffffu) {
     for (int b = tid; b < nBodies; b += NT) x.bmask[b] = 0ull;
-    __syncwarp();
+    __syncwarp(lanes);
     for (int c = tid; c < x.nC; c += NT) {
         atomicOr(&x.bmask[x.cb0[c]], 1ull << c);
         const int b1 = x.cb1[c];
         if (b1 >= 0) atomicOr(&x.bmask[b1], 1ull << c);
     }
-    __syncwarp();
+    __syncwarp(lanes);
 }
 
 // The worst-first loop of one phase for worlds owned by (sub-)warp groups of NT <= 32 lanes.
