@@ -36,6 +36,7 @@ EPISODE = 600
 DT = 1.0 / 60.0
 WORLDS_PER_GPU = int(os.environ.get("CUBEZ_BENCH_WORLDS", 65536))
 BODIES_PER_WORLD = 8
+WORKLOAD = "cfg4 batched RL-style: independent perturbed 8-cube cubedrop worlds, 600-frame episodes, phases staggered uniformly, reset at episode end"
 K1_BODIES = 1 << 24
 K1_BYTES_F64 = 531          # algorithmic bytes per awake body-step
 
@@ -113,10 +114,12 @@ def run_reference(args, rank):
         "impl": "reference", "metric": "world_steps_per_s", "value": value, "unit": "world-steps/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * el / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "cfg4 batched RL-style cubedrop-8, 600-frame episodes (CPU sample)", "dt": DT,
-                   "bodies_per_world": BODIES_PER_WORLD},
+        # the arm's own config (same workload as --impl ours); what one step samples of it is in cpu_baseline.sample
+        "config": {"workload": WORKLOAD, "worlds_per_gpu": args.worlds, "bodies_per_world": BODIES_PER_WORLD, "dt": DT,
+                   "contact_capacity": int(os.environ.get("CUBEZ_BENCH_CONTACT_CAP", 64)),
+                   "parallelism": f"worlds partitioned over {threads} host threads (the reference is single-threaded; no GPU on this arm)"},
         "cpu_baseline": {"value": value, "unit": "world-steps/s", "cores": threads, "kind": "port",
-                         "sample": f"each step = {per_step_worlds} worlds x {EPISODE} frames on {threads} threads (C++ restatement of the Go loops; no Go toolchain in this image)"},
+                         "sample": f"each step = {per_step_worlds} worlds x one whole {EPISODE}-frame episode (the same frame mix as the staggered phases) on {threads} threads (C++ restatement of the Go loops; no Go toolchain in this image)"},
         "e2e": {"value": value, "unit": "world-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "body_steps_per_s": value * BODIES_PER_WORLD,
     }
@@ -289,7 +292,7 @@ def main():
             "metric": "world_steps_per_s", "value": value, "unit": "world-steps/s", "n_gpus": world_size, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": max_ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "cfg4 batched RL-style: independent perturbed 8-cube cubedrop worlds, 600-frame episodes, phases staggered uniformly, reset at episode end",
+            "config": {"workload": WORKLOAD,
                        "worlds_per_gpu": W, "bodies_per_world": BODIES_PER_WORLD, "dt": DT, "contact_capacity": contact_cap,
                        "parallelism": f"worlds sharded over {world_size} GPU(s), no per-step collective",
                        "l2": "state (%.0f MB/GPU) larger than L2; frames of one call run from shared memory" % (nb * 84 * 16 / 1e6)},

@@ -588,24 +588,32 @@ __global__ void __launch_bounds__(128, MINB) k_world_fused(WorldParams p, FusedP
 // only a few world-rounds long), and the worlds that share a warp run for a similar number of
 // iterations (the groups of a warp iterate in lockstep to the longest of them).
 // Counting sort of world ids into 64 buckets, one CTA per key; result-neutral: worlds are independent.
-__global__ void __launch_bounds__(1024) k_order_worlds(const int *kContacts, const int *kPos, const int *kVel, int first, int count, int W, int *order3) {
+// ORDER_SLICES CTAs per key: CTA j sorts the worlds first + j, first + j + S, ... (a round-robin slice: the
+// slices are statistically alike) and writes its r-th world to position r*S + j, so the merged order is sorted up
+// to the differences between slices and no CTA waits for another.  The same launch zeroes the world counters of
+// the phase kernels (counters[0..3]: phases A, B, C, all), saving one memset node per phase launch.
+constexpr int ORDER_SLICES = 8;
+__global__ void __launch_bounds__(1024) k_order_worlds(const int *kContacts, const int *kPos, const int *kVel, int first, int count, int W, int *order3,
+                                                       unsigned int *counters) {
     // per-warp histograms (a few buckets hold most worlds: one shared counter per bucket would serialise),
-    // warp w owns the contiguous slice [w*per, (w+1)*per) of the range -> stable, deterministic order
+    // warp w owns a contiguous run of the slice -> stable, deterministic order
     __shared__ unsigned hist[32][64];
     __shared__ unsigned bucketStart[64];
-    const int which = blockIdx.x;
+    const int which = blockIdx.x / ORDER_SLICES, slice = blockIdx.x % ORDER_SLICES;
+    if (slice == 0 && threadIdx.x == 0) { counters[which] = 0; if (which == 2) counters[3] = 0; }
     const int *key = which == 0 ? kContacts : (which == 1 ? kPos : kVel);
     const int shift = which == 2 ? 1 : 0;   // contacts 0..63, position iterations 0..63+, velocity iterations in twos
     int *order = order3 + (size_t)which * W;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int per = ((count + 31) / 32 + 31) / 32 * 32;   // elements per warp, a multiple of 32
-    const int lo = warp * per, hi = min(count, lo + per);
+    const int len = count > slice ? (count - slice + ORDER_SLICES - 1) / ORDER_SLICES : 0;   // worlds of this slice
+    const int per = ((len + 31) / 32 + 31) / 32 * 32;   // elements per warp, a multiple of 32
+    const int lo = warp * per, hi = min(len, lo + per);
     for (int b = lane; b < 64; b += 32) hist[warp][b] = 0;
     __syncwarp();
     for (int k0 = lo; k0 < hi; k0 += 32) {
         const int k = k0 + lane;
         const bool valid = k < hi;
-        const unsigned b = valid ? 63u - min(63u, (unsigned)max(key[first + k], 0) >> shift) : 64u;
+        const unsigned b = valid ? 63u - min(63u, (unsigned)max(key[first + slice + k * ORDER_SLICES], 0) >> shift) : 64u;
         const unsigned peers = __match_any_sync(0xffffffffu, b);
         if (valid && lane == __ffs(peers) - 1) hist[warp][b] += __popc(peers);
         __syncwarp();
@@ -625,11 +633,11 @@ __global__ void __launch_bounds__(1024) k_order_worlds(const int *kContacts, con
     for (int k0 = lo; k0 < hi; k0 += 32) {
         const int k = k0 + lane;
         const bool valid = k < hi;
-        const unsigned b = valid ? 63u - min(63u, (unsigned)max(key[first + k], 0) >> shift) : 64u;
+        const unsigned b = valid ? 63u - min(63u, (unsigned)max(key[first + slice + k * ORDER_SLICES], 0) >> shift) : 64u;
         const unsigned peers = __match_any_sync(0xffffffffu, b);
         if (valid) {
-            const unsigned pos = bucketStart[b] + hist[warp][b] + __popc(peers & ((1u << lane) - 1u));
-            order[first + pos] = first + k;
+            const unsigned r = bucketStart[b] + hist[warp][b] + __popc(peers & ((1u << lane) - 1u));   // rank inside the slice
+            order[first + (int)r * ORDER_SLICES + slice] = first + slice + k * ORDER_SLICES;
         }
         __syncwarp();
         if (valid && lane == __ffs(peers) - 1) hist[warp][b] += __popc(peers);
@@ -638,9 +646,12 @@ __global__ void __launch_bounds__(1024) k_order_worlds(const int *kContacts, con
 }
 
 // returns 0 or a cudaError_t.  phases = PH_ALL (persistent over nSteps frames) or one of PH_A/B/C.
-static inline int launch(const FusedPlan &fp, const WorldParams &p, real dt, real bias, int nSteps, unsigned int *nextWorld, cudaStream_t stream,
-                         int phases = PH_ALL) {
-    cudaError_t e = cudaMemsetAsync(nextWorld, 0, sizeof(unsigned int), stream);   // stream-ordered before the launch
+// `counters` holds four world counters (phases A, B, C, all); countersZeroed: k_order_worlds of this frame cleared them.
+static inline int launch(const FusedPlan &fp, const WorldParams &p, real dt, real bias, int nSteps, unsigned int *counters, cudaStream_t stream,
+                         int phases = PH_ALL, bool countersZeroed = false) {
+    unsigned int *nextWorld = counters + (phases == PH_A ? 0 : (phases == PH_B ? 1 : (phases == PH_C ? 2 : 3)));
+    cudaError_t e = cudaSuccess;
+    if (!countersZeroed) e = cudaMemsetAsync(nextWorld, 0, sizeof(unsigned int), stream);   // stream-ordered before the launch
     if (e != cudaSuccess) return (int)e;
     int grid = fp.grid;
     const int needed = (p.wCount + fp.groupsPerBlock - 1) / fp.groupsPerBlock;

@@ -301,10 +301,12 @@ static WorldParams world_params(cz_world *w) {
 
 
 // launch the per-phase world ordering for a world range and return the order pointer of a phase
-static inline void order_worlds(cz_world *w, const WorldParams &p, cudaStream_t st, long long &launches) {
-    if (!w->useOrder) return;
-    czf::k_order_worlds<<<3, 1024, 0, st>>>(p.nContacts, p.posIters, p.velIters, p.wFirst, p.wCount, p.W, w->order3);
+// (also zeroes the four world counters at `counters`; returns whether it ran)
+static inline bool order_worlds(cz_world *w, const WorldParams &p, cudaStream_t st, long long &launches, unsigned int *counters) {
+    if (!w->useOrder) return false;
+    czf::k_order_worlds<<<3 * czf::ORDER_SLICES, 1024, 0, st>>>(p.nContacts, p.posIters, p.velIters, p.wFirst, p.wCount, p.W, w->order3, counters);
     launches++;
+    return true;
 }
 static inline const int *phase_order(cz_world *w, int ph) {
     if (!w->useOrder) return nullptr;
@@ -365,7 +367,7 @@ static int world_plan(cz_world *w) {
         w->useFused = !w->useBP && czf::plan(w->fused, B, w->P, Cc, w->nchk, w->d.schedule, ctx->smem_optin, ctx->sm_count, W);
         if (w->useFused) {
             CK(ctx, cudaMalloc(&w->fused.cold, sizeof(real) * w->fused.coldReals * (size_t)w->fused.grid * w->fused.groupsPerBlock));
-            if (!w->d_next) CK(ctx, cudaMalloc(&w->d_next, sizeof(unsigned int)));
+            if (!w->d_next) CK(ctx, cudaMalloc(&w->d_next, sizeof(unsigned int) * 4));
             if (!w->order3) CK(ctx, cudaMalloc(&w->order3, sizeof(int) * 3 * (size_t)W));
             w->useOrder = czf::env_int("CUBEZ_FUSED_ORDER", 1) != 0 && W >= 64;
             if (w->fused.split) {
@@ -765,18 +767,18 @@ int cz_world_step(cz_world *w, cz_real dt, int32_t n_steps, cz_step_stats *stats
         if (w->fused.split) {   // one launch per phase and frame: every warp of the GPU runs the same code region
             for (int s = 0; s < n_steps && !rc; s++) {
                 p.step_index = w->step_index + s;
-                order_worlds(w, p, ctx->stream, launches);
+                const bool zeroed = order_worlds(w, p, ctx->stream, launches, w->d_next);
                 for (int ph : {czf::PH_A, czf::PH_B, czf::PH_C}) {
                     p.order = phase_order(w, ph);
-                    rc = czf::launch(w->fused, p, dt, w->bias, 1, w->d_next, ctx->stream, ph);
+                    rc = czf::launch(w->fused, p, dt, w->bias, 1, w->d_next, ctx->stream, ph, zeroed);
                     if (rc) break;
                     launches++;
                 }
             }
         } else {
-            order_worlds(w, p, ctx->stream, launches);
+            const bool zeroed = order_worlds(w, p, ctx->stream, launches, w->d_next);
             p.order = phase_order(w, czf::PH_C);
-            rc = czf::launch(w->fused, p, dt, w->bias, n_steps, w->d_next, ctx->stream);
+            rc = czf::launch(w->fused, p, dt, w->bias, n_steps, w->d_next, ctx->stream, czf::PH_ALL, zeroed);
             launches++;
         }
         if (rc) return fail(ctx, CZ_ERR_CUDA, std::string("fused launch: ") + cudaGetErrorString((cudaError_t)rc));
@@ -940,7 +942,7 @@ static int host_pipe_init(cz_world *w) {
     CK(ctx, cudaMalloc(&pp.dIn, sizeof(real) * NB * 26));    // pos3 ori4 vel3 rot3 acc3 iitb9 motion1
     CK(ctx, cudaMalloc(&pp.dOut, sizeof(real) * NB * 38));   // pos3 ori4 vel3 rot3 motion1 lacc3 tr12 iitw9
     CK(ctx, cudaMalloc(&pp.dFlags, 3 * (size_t)NB));
-    CK(ctx, cudaMalloc(&pp.dNext, sizeof(unsigned int) * chunks));
+    CK(ctx, cudaMalloc(&pp.dNext, sizeof(unsigned int) * 4 * chunks));
     for (int k = 1; k < pp.nComp; k++) CK(ctx, cudaMalloc(&pp.coldX[k], sizeof(real) * w->fused.coldReals * (size_t)w->fused.grid * w->fused.groupsPerBlock));
     pp.ready = true;
     return CZ_OK;
@@ -975,7 +977,7 @@ int cz_world_step_host(cz_world *w, cz_bodies *io, cz_real dt, int32_t n_steps, 
     static const bool hostTrace = getenv("CUBEZ_HOST_TRACE") != nullptr;
     const auto tc0 = std::chrono::steady_clock::now();
     CK(ctx, cudaMemsetAsync(w->stats, 0, sizeof(unsigned long long) * ST_N, ctx->stream));
-    CK(ctx, cudaMemsetAsync(pp.dNext, 0, sizeof(unsigned int) * pp.chunks, ctx->stream));
+    CK(ctx, cudaMemsetAsync(pp.dNext, 0, sizeof(unsigned int) * 4 * pp.chunks, ctx->stream));
     CK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
     CK(ctx, cudaEventRecord(pp.evBegin, ctx->stream));
     CK(ctx, cudaStreamWaitEvent(pp.sUp, pp.evBegin, 0));     // staging buffers of the previous call are free
@@ -1020,18 +1022,18 @@ int cz_world_step_host(cz_world *w, cz_bodies *io, cz_real dt, int32_t n_steps, 
             if (w->fused.split && !czf::env_int("CUBEZ_HOST_NO_SPLIT", 0)) {   // one launch per phase and frame, as cz_world_step does for large batches
                 for (int s2 = 0; s2 < n_steps && !rc; s2++) {
                     p.step_index = w->step_index + s2;
-                    order_worlds(w, p, cs, launches);
+                    const bool zeroed = order_worlds(w, p, cs, launches, pp.dNext + 4 * c);
                     for (int ph : {czf::PH_A, czf::PH_B, czf::PH_C}) {
                         p.order = phase_order(w, ph);
-                        rc = czf::launch(fpl, p, dt, w->bias, 1, pp.dNext + c, cs, ph);
+                        rc = czf::launch(fpl, p, dt, w->bias, 1, pp.dNext + 4 * c, cs, ph, zeroed);
                         if (rc) break;
                         launches++;
                     }
                 }
             } else {
-                order_worlds(w, p, cs, launches);
+                const bool zeroed = order_worlds(w, p, cs, launches, pp.dNext + 4 * c);
                 p.order = phase_order(w, czf::PH_C);
-                rc = czf::launch(fpl, p, dt, w->bias, n_steps, pp.dNext + c, cs);
+                rc = czf::launch(fpl, p, dt, w->bias, n_steps, pp.dNext + 4 * c, cs, czf::PH_ALL, zeroed);
                 launches++;
             }
             if (rc) return fail(ctx, CZ_ERR_CUDA, std::string("fused launch: ") + cudaGetErrorString((cudaError_t)rc));
@@ -1127,7 +1129,7 @@ int cz_world_step_rl(cz_world *w, const cz_real *add_velocity, const cz_real *ad
     const bool anyOut = hout.pos || hout.ori || hout.vel || hout.rot || hout.motion || hout.lacc || hout.tr || hout.iitw || hout.awake;
     const bool anyIn = add_velocity || add_rotation;
     CK(ctx, cudaMemsetAsync(w->stats, 0, sizeof(unsigned long long) * ST_N, ctx->stream));
-    CK(ctx, cudaMemsetAsync(pp.dNext, 0, sizeof(unsigned int) * pp.chunks, ctx->stream));
+    CK(ctx, cudaMemsetAsync(pp.dNext, 0, sizeof(unsigned int) * 4 * pp.chunks, ctx->stream));
     CK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
     CK(ctx, cudaEventRecord(pp.evBegin, ctx->stream));
     CK(ctx, cudaStreamWaitEvent(pp.sUp, pp.evBegin, 0));
@@ -1160,18 +1162,18 @@ int cz_world_step_rl(cz_world *w, const cz_real *add_velocity, const cz_real *ad
         if (w->fused.split) {
             for (int s2 = 0; s2 < n_steps && !rc; s2++) {
                 p.step_index = w->step_index + s2;
-                order_worlds(w, p, cs, launches);
+                const bool zeroed = order_worlds(w, p, cs, launches, pp.dNext + 4 * c);
                 for (int ph : {czf::PH_A, czf::PH_B, czf::PH_C}) {
                     p.order = phase_order(w, ph);
-                    rc = czf::launch(fpl, p, dt, w->bias, 1, pp.dNext + c, cs, ph);
+                    rc = czf::launch(fpl, p, dt, w->bias, 1, pp.dNext + 4 * c, cs, ph, zeroed);
                     if (rc) break;
                     launches++;
                 }
             }
         } else if (n_steps > 0) {
-            order_worlds(w, p, cs, launches);
+            const bool zeroed = order_worlds(w, p, cs, launches, pp.dNext + 4 * c);
             p.order = phase_order(w, czf::PH_C);
-            rc = czf::launch(fpl, p, dt, w->bias, n_steps, pp.dNext + c, cs);
+            rc = czf::launch(fpl, p, dt, w->bias, n_steps, pp.dNext + 4 * c, cs, czf::PH_ALL, zeroed);
             launches++;
         }
         if (rc) return fail(ctx, CZ_ERR_CUDA, std::string("fused launch: ") + cudaGetErrorString((cudaError_t)rc));
