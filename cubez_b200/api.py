@@ -187,6 +187,8 @@ class BatchedWorld:
             af = None if scene.active_from is None else np.tile(scene.active_from, scene.n_worlds) if scene.active_from.shape[0] == scene.bodies_per_world else scene.active_from
             ig = None if scene.integrate is None else np.tile(scene.integrate, scene.n_worlds) if scene.integrate.shape[0] == scene.bodies_per_world else scene.integrate
             w.set_activation(af, ig)
+        if getattr(scene, "materials", None):
+            w.set_materials(**scene.materials)
         return w
 
     # ---- uploads ---------------------------------------------------------------------
@@ -231,6 +233,40 @@ class BatchedWorld:
         """RL-style episodes: snapshot now; world k is at frame phase0[k] and resets on wrap."""
         ph = np.zeros(self.n_worlds, dtype=np.int32) if phase0 is None else np.ascontiguousarray(phase0, dtype=np.int32)
         self.ctx.check(self.lib.cz_world_set_episodes(self.h, length, ph.ctypes.data_as(C.POINTER(C.c_int32))))
+
+    def set_materials(self, friction, restitution, body_material=None, plane_material=None, first_world: int = 0):
+        """Per-pair surface materials (new API; replaces the hard-wired `c.Friction = 0.9` /
+        `c.Restitution = 0.1` test constants, colliders.go:199-202 and five more sites).  friction /
+        restitution: M x M tables indexed [material(one)][material(two)]; body_material: ids for the
+        worlds from first_world on; plane_material: one id per plane.  friction=None restores the constants."""
+        PR, P32 = C.POINTER(self.prec.ctype), C.POINTER(C.c_int32)
+        if friction is None:
+            self.ctx.check(self.lib.cz_world_set_materials(self.h, 0, None, None, 0, 0, None, None))
+            return
+        f = np.ascontiguousarray(friction, dtype=self.prec.dtype)
+        r = np.ascontiguousarray(restitution, dtype=self.prec.dtype)
+        m = f.shape[0]
+        assert f.shape == (m, m) and r.shape == (m, m)
+        bm = None if body_material is None else np.ascontiguousarray(body_material, dtype=np.int32).reshape(-1)
+        pm = None if plane_material is None else np.ascontiguousarray(plane_material, dtype=np.int32).reshape(-1)
+        n = 0 if bm is None else bm.shape[0] // self.B
+        self.ctx.check(self.lib.cz_world_set_materials(
+            self.h, m, f.ctypes.data_as(PR), r.ctypes.data_as(PR), first_world, n,
+            None if bm is None else bm.ctypes.data_as(P32), None if pm is None else pm.ctypes.data_as(P32)))
+
+    def export_gl(self, first_world: int = 0, n_worlds: Optional[int] = None, model: bool = False):
+        """Renderer-side export (examples/cubedrop.go:35-37, SetGlVector3 / SetGlQuat of
+        examples/exampleapp.go:146-159): float32 Location (n,3) and LocalRotation (n,4 as W,V0,V1,V2) of
+        every body, converted on the device; model=True adds the body transform as a column-major 4x4."""
+        n_worlds = self.n_worlds - first_world if n_worlds is None else n_worlds
+        n = n_worlds * self.B
+        loc = np.empty((n, 3), dtype=np.float32)
+        rot = np.empty((n, 4), dtype=np.float32)
+        mdl = np.empty((n, 16), dtype=np.float32) if model else None
+        PF = C.POINTER(C.c_float)
+        self.ctx.check(self.lib.cz_world_export_gl(self.h, first_world, n_worlds, loc.ctypes.data_as(PF), rot.ctypes.data_as(PF),
+                                                   None if mdl is None else mdl.ctypes.data_as(PF), 0))
+        return (loc, rot, mdl) if model else (loc, rot)
 
     # ---- stepping --------------------------------------------------------------------
     def step(self, dt, n_steps: int = 1, stats: bool = True) -> Optional[dict]:

@@ -440,7 +440,8 @@ __global__ void __launch_bounds__(128) k_bp_planes(WorldParams p, KeyedContacts 
 }
 
 // sorted contacts -> the world's as-generated arrays (world 0)
-__global__ void k_bp_emit(WorldParams p, const unsigned *sortedVals, const real *payload, const int2 *idsArr, const unsigned long long *count) {
+__global__ void k_bp_emit(WorldParams p, const unsigned long long *sortedKeys, const unsigned *sortedVals, const real *payload, const int2 *idsArr,
+                          const unsigned long long *count) {
     using namespace czr;
     const unsigned long long n = *count;
     const unsigned long long c = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -456,8 +457,14 @@ __global__ void k_bp_emit(WorldParams p, const unsigned *sortedVals, const real 
 #pragma unroll
     for (int k = 0; k < 3; k++) { p.gen[(G_POINT + k) * gs + c] = r[k]; p.gen[(G_NORMAL + k) * gs + c] = r[3 + k]; }
     p.gen[G_PEN * gs + c] = r[6];
-    p.gen[G_FRIC * gs + c] = R_(0.9);
-    p.gen[G_REST * gs + c] = R_(0.1);
+    real fric = R_(0.9), rest = R_(0.1);
+    if (p.matFric) {   // the canonical key names the check: (a, b) = (check / (P+B), check % (P+B))
+        const unsigned long long check = sortedKeys[c] >> 3, per = (unsigned long long)(p.P + p.B);
+        const int a = (int)(check / per), slot = (int)(check % per);
+        check_material(p, 0, a, slot < p.P ? -(slot + 1) : slot - p.P, fric, rest);
+    }
+    p.gen[G_FRIC * gs + c] = fric;
+    p.gen[G_REST * gs + c] = rest;
     const int2 ids = idsArr[sortedVals[c]];
     p.gb0[c] = ids.x;
     p.gb1[c] = ids.y;

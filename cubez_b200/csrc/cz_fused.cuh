@@ -225,7 +225,10 @@ __device__ __forceinline__ void stage_world(const Staged &s, const BodyStore &st
 // code region at the same time (the kernel is ~7 k SASS instructions, far larger than the
 // instruction caches; without this every warp is in a different region and fetch-bound).
 enum { PH_A = 1, PH_B = 2, PH_C = 4, PH_ALL = 7 };
-template <int G, int MINB, bool LOCKSTEP, int PH>
+// MAT: per-pair surface materials (cz_world_set_materials): Friction / Restitution of every contact live in the
+// world's as-generated arrays (global, read for the winner and the contacts it touches); without MAT they are
+// the compile-time constants 0.9 / 0.1 of the reference.
+template <int G, int MINB, bool LOCKSTEP, int PH, bool MAT>
 __global__ void __launch_bounds__(128, MINB) k_world_fused(WorldParams p, FusedPlan fp, real dt, real bias, int nSteps, unsigned int *nextWorld) {
     using namespace czr;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -281,6 +284,12 @@ __global__ void __launch_bounds__(128, MINB) k_world_fused(WorldParams p, FusedP
         const int w = live ? (p.order ? p.order[p.wFirst + (int)wu] : p.wFirst + (int)wu) : 0;
         const long long gbase = (long long)w * B;
         x.body_base = gbase;
+        if (MAT) {
+            const long long gsAll = (long long)p.W * Cc;
+            x.fric = p.gen + G_FRIC * gsAll + (long long)w * Cc;
+            x.rest = p.gen + G_REST * gsAll + (long long)w * Cc;
+            gv.fric = x.fric; gv.rest = x.rest;
+        }
         if (live) stage_world<G>(s, st, gbase, B, tid);
         int lastC = 0, lastPos = 0, lastVel = 0;
         if (PH != PH_ALL) {   // split mode: contact state of this world lives in global memory between launches
@@ -467,6 +476,7 @@ __global__ void __launch_bounds__(128, MINB) k_world_fused(WorldParams p, FusedP
                         const int code = (int)r[7];
                         gc.b0 = code / 128; gc.b1 = code % 128 - 1;
                         stage_gen(s, slot, gc);
+                        if (MAT) check_material(p, gbase, a, b2, x.fric[slot], x.rest[slot]);
                     }
                 }
                 nC += total;
@@ -487,6 +497,7 @@ __global__ void __launch_bounds__(128, MINB) k_world_fused(WorldParams p, FusedP
                 if (c.shape == CZ_SHAPE_SPHERE) czn::sphere_halfspace(c, p.planes[pi], gc);
                 else czn::cube_halfspace_contact(c, p.planes[pi], v, gc);
                 stage_gen(s, slot, gc);
+                if (MAT) check_material(p, gbase, a, b2, x.fric[slot], x.rest[slot]);
             }
             __syncwarp(mask);
             accContacts += (unsigned long long)nC;
@@ -503,8 +514,7 @@ __global__ void __launch_bounds__(128, MINB) k_world_fused(WorldParams p, FusedP
 #pragma unroll
                     for (int f = 0; f < 6; f++) gen[f * gs + c] = r[f];
                     gen[G_PEN * gs + c] = s.pen[c];
-                    gen[G_FRIC * gs + c] = R_(0.9);
-                    gen[G_REST * gs + c] = R_(0.1);
+                    if (!MAT) { gen[G_FRIC * gs + c] = R_(0.9); gen[G_REST * gs + c] = R_(0.1); }
                     p.gb0[(long long)w * Cc + c] = s.cb0[c];
                     p.gb1[(long long)w * Cc + c] = s.cb1[c];
                 }
@@ -656,31 +666,36 @@ static inline int launch(const FusedPlan &fp, const WorldParams &p, real dt, rea
     int grid = fp.grid;
     const int needed = (p.wCount + fp.groupsPerBlock - 1) / fp.groupsPerBlock;
     if (grid > needed) grid = needed;
-#define CZF_LAUNCH(GG, MB, LS, PHS)                                                                                   \
+#define CZF_LAUNCH(GG, MB, LS, PHS, MT)                                                                               \
     do {                                                                                                            \
         if (fp.smemBytes > 48 * 1024)                                                                               \
-            e = cudaFuncSetAttribute(k_world_fused<GG, MB, LS, PHS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fp.smemBytes); \
-        if (e == cudaSuccess) k_world_fused<GG, MB, LS, PHS><<<grid, fp.threads, fp.smemBytes, stream>>>(p, fp, dt, bias, nSteps, nextWorld); \
+            e = cudaFuncSetAttribute(k_world_fused<GG, MB, LS, PHS, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fp.smemBytes); \
+        if (e == cudaSuccess) k_world_fused<GG, MB, LS, PHS, MT><<<grid, fp.threads, fp.smemBytes, stream>>>(p, fp, dt, bias, nSteps, nextWorld); \
     } while (0)
 #define CZF_LAUNCH_G(GG)                                                                                            \
     do {                                                                                                            \
-        if (phases != PH_ALL && GG == 8 && fp.splitMinb == 3) {                                                     \
-            if (phases == PH_A) CZF_LAUNCH(8, 3, false, PH_A);                                                      \
-            else if (phases == PH_B) CZF_LAUNCH(8, 3, false, PH_B);                                                 \
-            else CZF_LAUNCH(8, 3, false, PH_C);                                                                     \
+        if (p.matFric) {   /* materials: the default register budget only */                                        \
+            if (phases == PH_A) CZF_LAUNCH(GG, 2, false, PH_A, true);                                               \
+            else if (phases == PH_B) CZF_LAUNCH(GG, 2, false, PH_B, true);                                          \
+            else if (phases == PH_C) CZF_LAUNCH(GG, 2, false, PH_C, true);                                          \
+            else CZF_LAUNCH(GG, 2, true, PH_ALL, true);                                                             \
+        } else if (phases != PH_ALL && GG == 8 && fp.splitMinb == 3) {                                              \
+            if (phases == PH_A) CZF_LAUNCH(8, 3, false, PH_A, false);                                               \
+            else if (phases == PH_B) CZF_LAUNCH(8, 3, false, PH_B, false);                                          \
+            else CZF_LAUNCH(8, 3, false, PH_C, false);                                                              \
         } else if (phases != PH_ALL && GG == 8 && fp.splitMinb == 4) {                                              \
-            if (phases == PH_A) CZF_LAUNCH(8, 4, false, PH_A);                                                      \
-            else if (phases == PH_B) CZF_LAUNCH(8, 4, false, PH_B);                                                 \
-            else CZF_LAUNCH(8, 4, false, PH_C);                                                                     \
-        } else if (phases == PH_A) CZF_LAUNCH(GG, 2, false, PH_A);                                                  \
-        else if (phases == PH_B) CZF_LAUNCH(GG, 2, false, PH_B);                                                    \
-        else if (phases == PH_C) CZF_LAUNCH(GG, 2, false, PH_C);                                                    \
+            if (phases == PH_A) CZF_LAUNCH(8, 4, false, PH_A, false);                                               \
+            else if (phases == PH_B) CZF_LAUNCH(8, 4, false, PH_B, false);                                          \
+            else CZF_LAUNCH(8, 4, false, PH_C, false);                                                              \
+        } else if (phases == PH_A) CZF_LAUNCH(GG, 2, false, PH_A, false);                                           \
+        else if (phases == PH_B) CZF_LAUNCH(GG, 2, false, PH_B, false);                                             \
+        else if (phases == PH_C) CZF_LAUNCH(GG, 2, false, PH_C, false);                                             \
         else if (fp.lockstep) {                                                                                     \
-            if (fp.minb <= 2) CZF_LAUNCH(GG, 2, true, PH_ALL);                                                      \
-            else CZF_LAUNCH(GG, 3, true, PH_ALL);                                                                   \
+            if (fp.minb <= 2) CZF_LAUNCH(GG, 2, true, PH_ALL, false);                                               \
+            else CZF_LAUNCH(GG, 3, true, PH_ALL, false);                                                            \
         } else {                                                                                                    \
-            if (fp.minb <= 2) CZF_LAUNCH(GG, 2, false, PH_ALL);                                                     \
-            else CZF_LAUNCH(GG, 3, false, PH_ALL);                                                                  \
+            if (fp.minb <= 2) CZF_LAUNCH(GG, 2, false, PH_ALL, false);                                              \
+            else CZF_LAUNCH(GG, 3, false, PH_ALL, false);                                                           \
         }                                                                                                           \
     } while (0)
 if (fp.G == 8) CZF_LAUNCH_G(8);

@@ -36,7 +36,22 @@ struct WorldParams {
     long long episodeStep0;
     const int *phase0;
     BodyStore snap;
+    // Per-pair surface materials (cz_world_set_materials).  matFric == NULL: the
+    // reference's constants 0.9 / 0.1 (colliders.go:199-202 and the five other FIXME sites).
+    const real *matFric, *matRest;   // [nMat * nMat], row = material of check operand `one`, column = `two`
+    const uint8_t *bodyMat;          // [W * B]
+    int nMat;
+    uint8_t planeMat[CZ_MAX_PLANES];
 };
+// Friction / Restitution of the contacts produced by check (a, b) of the world whose body 0 is `base`
+// (a, b: >= 0 collider, < 0 plane -(p+1), as the schedule names them)
+CZD void check_material(const WorldParams &p, long long base, int a, int b, real &fric, real &rest) {
+    if (!p.matFric) { fric = R_(0.9); rest = R_(0.1); return; }
+    const int ma = a >= 0 ? (int)p.bodyMat[base + a] : (int)p.planeMat[-a - 1];
+    const int mb = b >= 0 ? (int)p.bodyMat[base + b] : (int)p.planeMat[-b - 1];
+    fric = p.matFric[ma * p.nMat + mb];
+    rest = p.matRest[ma * p.nMat + mb];
+}
 CZD bool episode_wraps(const WorldParams &p, int w, long long step) {
     return p.episodeLen > 0 && (p.phase0[w] + (step - p.episodeStep0)) % p.episodeLen == 0;
 }
@@ -242,6 +257,28 @@ __global__ void k_apply_actions(czb::BodyStore s, long long first, long long n, 
     s.st(C_V01, i, v01); s.st(C_V2R0, i, v2r0); s.st(C_R12, i, r12);
 }
 
+// Renderer-side export: what the example loop does per body and frame on the host,
+// SetGlVector3(&Node.Location, &body.Position) / SetGlQuat(&Node.LocalRotation, &body.Orientation)
+// (examples/cubedrop.go:35-37, examples/exampleapp.go:146-159): float32(x) of every component, quaternion as
+// (W, V[0], V[1], V[2]).  model (optional): the body transform (rigidbody.go:88) as a column-major 4x4.
+__global__ void k_export_gl(czb::BodyStore s, long long first, long long n, float *loc, float *rot, float *model) {
+    using namespace czb;
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const long long i = first + t;
+    if (loc) { V3 v = ld_position(s, i); for (int k = 0; k < 3; k++) loc[t * 3 + k] = (float)v.c[k]; }
+    if (rot) { Q4 q = ld_orientation(s, i); for (int k = 0; k < 4; k++) rot[t * 4 + k] = (float)q.c[k]; }
+    if (model) {
+        M34 tr = ld_transform(s, i);
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+#pragma unroll
+            for (int r = 0; r < 3; r++) model[t * 16 + c * 4 + r] = (float)tr.c[c * 3 + r];
+            model[t * 16 + c * 4 + 3] = c == 3 ? 1.0f : 0.0f;
+        }
+    }
+}
+
 __global__ void k_fill_u8(uint8_t *p, long long n, uint8_t v) {
     long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (t < n) p[t] = v;
@@ -338,13 +375,13 @@ CZD void eval_check(const WorldParams &p, long long base, int a, int b, CheckEva
     if (czn::check_pair(one, two, v1, v2, e.gc)) { e.count = 1; e.kind = 1; }
 }
 
-CZD void store_gen(real *gen, long long gs, int *gb0, int *gb1, long long slot, const GenContact &c) {
+CZD void store_gen(real *gen, long long gs, int *gb0, int *gb1, long long slot, const GenContact &c, real fric, real rest) {
     using namespace czr;
 #pragma unroll
     for (int k = 0; k < 3; k++) { gen[(G_POINT + k) * gs + slot] = c.point.c[k]; gen[(G_NORMAL + k) * gs + slot] = c.normal.c[k]; }
     gen[G_PEN * gs + slot] = c.pen;
-    gen[G_FRIC * gs + slot] = R_(0.9);   // test constants of colliders.go:201-202 etc.
-    gen[G_REST * gs + slot] = R_(0.1);
+    gen[G_FRIC * gs + slot] = fric;   // 0.9 / 0.1 (the test constants of colliders.go:201-202 etc.) unless materials are set
+    gen[G_REST * gs + slot] = rest;
     gb0[slot] = c.b0;
     gb1[slot] = c.b1;
 }
@@ -421,8 +458,10 @@ __global__ void __launch_bounds__(256) k_narrow(WorldParams p, int tiles, int *t
     real *gen = p.gen + (long long)w * p.Cc;
     int *gb0 = p.gb0 + (long long)w * p.Cc, *gb1 = p.gb1 + (long long)w * p.Cc;
     int slot = tb + off;
+    real fric, rest;
+    check_material(p, base, a, b, fric, rest);
     if (e.kind == 1) {
-        if (slot < p.Cc) store_gen(gen, gs, gb0, gb1, slot, e.gc);
+        if (slot < p.Cc) store_gen(gen, gs, gb0, gb1, slot, e.gc, fric, rest);
     } else {
         ColliderView c = load_collider(p.st, base + e.cubeLocal, e.cubeLocal);
 #pragma unroll 1
@@ -430,7 +469,7 @@ __global__ void __launch_bounds__(256) k_narrow(WorldParams p, int tiles, int *t
             if (e.mask & (1u << v)) {
                 GenContact gc;
                 czn::cube_halfspace_contact(c, p.planes[e.plane], v, gc);
-                if (slot < p.Cc) store_gen(gen, gs, gb0, gb1, slot, gc);
+                if (slot < p.Cc) store_gen(gen, gs, gb0, gb1, slot, gc, fric, rest);
                 slot++;
             }
         }

@@ -279,6 +279,13 @@ struct cz_world {
     } pipe;
     real *h_pin = nullptr;
     size_t h_pin_bytes = 0;
+    // per-pair surface materials (cz_world_set_materials); nMat == 0: the reference's constants
+    int nMat = 0;
+    real *d_matFric = nullptr, *d_matRest = nullptr;   // [nMat * nMat]
+    uint8_t *d_bodyMat = nullptr;                      // [W * B]
+    uint8_t planeMat[CZ_MAX_PLANES] = {};
+    float *d_export = nullptr;                         // staging of cz_world_export_gl
+    size_t exportFloats = 0;
 };
 
 static WorldParams world_params(cz_world *w) {
@@ -296,6 +303,9 @@ static WorldParams world_params(cz_world *w) {
     p.nContacts = w->nContacts; p.posIters = w->posIters; p.velIters = w->velIters;
     p.stats = w->stats;
     p.episodeLen = w->episodeLen; p.episodeStep0 = w->episodeStep0; p.phase0 = w->d_phase0; p.snap = w->snap.st;
+    p.nMat = w->nMat;
+    p.matFric = w->nMat > 0 ? w->d_matFric : nullptr; p.matRest = w->nMat > 0 ? w->d_matRest : nullptr; p.bodyMat = w->d_bodyMat;
+    for (int i = 0; i < CZ_MAX_PLANES; i++) p.planeMat[i] = w->planeMat[i];
     return p;
 }
 
@@ -481,7 +491,7 @@ int cz_world_destroy(cz_world *w) {
     if (w->d_phase0) cudaFree(w->d_phase0);
     void *ptrs[] = {w->d_one, w->d_two, w->gen, w->gb0, w->gb1, w->nContacts, w->posIters, w->velIters, w->stats,
                     w->tileCount, w->tileBase, w->hitCount, w->rs.bw, w->rs.cw, w->rs.cb, w->fused.cold, w->d_next, w->order3,
-                    w->fused.coldW, w->fused.hotPen, w->fused.hotDdv, w->fused.hotCb0, w->fused.hotCb1};
+                    w->fused.coldW, w->fused.hotPen, w->fused.hotDdv, w->fused.hotCb0, w->fused.hotCb1, w->d_matFric, w->d_matRest, w->d_bodyMat, w->d_export};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (w->h_stats) cudaFreeHost(w->h_stats);
     if (w->h_pin) cudaFreeHost(w->h_pin);
@@ -578,6 +588,42 @@ int cz_world_set_pow(cz_world *w, cz_real dt, const cz_real *lin_pow, const cz_r
     w->b.pow_dt = dt;
     w->b.pow_user = true;
     w->bias = bias;
+    return CZ_OK;
+}
+int cz_world_set_materials(cz_world *w, int32_t n_materials, const cz_real *friction, const cz_real *restitution, int32_t first, int32_t n,
+                           const int32_t *body_material, const int32_t *plane_material) {
+    int rc = world_range(w, first, n);
+    if (rc) return rc;
+    cz_ctx *ctx = w->ctx;
+    CK(ctx, cudaSetDevice(ctx->device));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    if (n_materials <= 0) { w->nMat = 0; return CZ_OK; }
+    if (n_materials > 255 || !friction || !restitution) return fail(ctx, CZ_ERR_INVALID, "cz_world_set_materials: 1..255 materials with both tables");
+    const long long B = w->d.bodies_per_world, NB = w->b.n;
+    if (body_material)
+        for (long long i = 0; i < n * B; i++)
+            if (body_material[i] < 0 || body_material[i] >= n_materials) return fail(ctx, CZ_ERR_INVALID, "body material id out of range");
+    if (plane_material)
+        for (int i = 0; i < w->P; i++)
+            if (plane_material[i] < 0 || plane_material[i] >= n_materials) return fail(ctx, CZ_ERR_INVALID, "plane material id out of range");
+    if (w->nMat != n_materials) {   // a new table size resets every id to material 0
+        if (w->d_matFric) { cudaFree(w->d_matFric); w->d_matFric = nullptr; }
+        if (w->d_matRest) { cudaFree(w->d_matRest); w->d_matRest = nullptr; }
+        CK(ctx, cudaMalloc(&w->d_matFric, sizeof(real) * n_materials * n_materials));
+        CK(ctx, cudaMalloc(&w->d_matRest, sizeof(real) * n_materials * n_materials));
+        if (!w->d_bodyMat) CK(ctx, cudaMalloc(&w->d_bodyMat, (size_t)NB));
+        CK(ctx, cudaMemset(w->d_bodyMat, 0, (size_t)NB));
+        for (int i = 0; i < CZ_MAX_PLANES; i++) w->planeMat[i] = 0;
+    }
+    CK(ctx, cudaMemcpy(w->d_matFric, friction, sizeof(real) * n_materials * n_materials, cudaMemcpyHostToDevice));
+    CK(ctx, cudaMemcpy(w->d_matRest, restitution, sizeof(real) * n_materials * n_materials, cudaMemcpyHostToDevice));
+    if (body_material && n > 0) {
+        std::vector<uint8_t> ids((size_t)(n * B));
+        for (long long i = 0; i < n * B; i++) ids[i] = (uint8_t)body_material[i];
+        CK(ctx, cudaMemcpy(w->d_bodyMat + first * B, ids.data(), ids.size(), cudaMemcpyHostToDevice));
+    }
+    if (plane_material) for (int i = 0; i < w->P; i++) w->planeMat[i] = (uint8_t)plane_material[i];
+    w->nMat = n_materials;
     return CZ_OK;
 }
 int cz_world_set_step_index(cz_world *w, int64_t s) {
@@ -680,7 +726,7 @@ static int world_step_multi(cz_world *w, real dt, long long &launches) {
         const unsigned long long maxKey = ((unsigned long long)p.B * (unsigned long long)(p.P + p.B) + 1ull) * 8ull;
         while (bits < 64 && (1ull << bits) <= maxKey) bits += 8;
         int cur = czs::radix_sort(bp.sortContacts, (long long)nCont, bits, ctx->stream, &launches);
-        czbp::k_bp_emit<<<nblk(std::max<long long>((long long)nCont, 1), 128), 128, 0, ctx->stream>>>(p, bp.sortContacts.vals[cur], bp.payload, bp.ids, bp.counters + 1);
+        czbp::k_bp_emit<<<nblk(std::max<long long>((long long)nCont, 1), 128), 128, 0, ctx->stream>>>(p, bp.sortContacts.keys[cur], bp.sortContacts.vals[cur], bp.payload, bp.ids, bp.counters + 1);
         launches++;
         CKL(ctx);
         if (w->resolveNT == 32) launch_resolve<32>(w, p, -1, dt, false);
@@ -849,6 +895,33 @@ int cz_world_download_contacts(cz_world *w, int32_t world, cz_contacts *out) {
     if (out->restitution && (rc = getf(czr::G_REST, out->restitution, 0, 1))) return rc;
     if (out->body0) CK(ctx, cudaMemcpy(out->body0, w->gb0 + off, sizeof(int) * nC, cudaMemcpyDeviceToHost));
     if (out->body1) CK(ctx, cudaMemcpy(out->body1, w->gb1 + off, sizeof(int) * nC, cudaMemcpyDeviceToHost));
+    return CZ_OK;
+}
+int cz_world_export_gl(cz_world *w, int32_t first, int32_t n, float *location, float *rotation, float *model, int32_t dst_on_device) {
+    int rc = world_range(w, first, n);
+    if (rc) return rc;
+    cz_ctx *ctx = w->ctx;
+    CK(ctx, cudaSetDevice(ctx->device));
+    const long long B = w->d.bodies_per_world, nb = (long long)n * B;
+    if (nb == 0 || (!location && !rotation && !model)) return CZ_OK;
+    if (dst_on_device) {   // e.g. a mapped GL buffer: written in place, asynchronous on the context stream
+        k_export_gl<<<nblk(nb, 256), 256, 0, ctx->stream>>>(w->b.st, first * B, nb, location, rotation, model);
+        CKL(ctx);
+        return CZ_OK;
+    }
+    const size_t need = (size_t)nb * 23;
+    if (w->exportFloats < need) {
+        if (w->d_export) { cudaFree(w->d_export); w->d_export = nullptr; }
+        CK(ctx, cudaMalloc(&w->d_export, sizeof(float) * need));
+        w->exportFloats = need;
+    }
+    float *dl = w->d_export, *dr = dl + nb * 3, *dm = dr + nb * 4;
+    k_export_gl<<<nblk(nb, 256), 256, 0, ctx->stream>>>(w->b.st, first * B, nb, location ? dl : nullptr, rotation ? dr : nullptr, model ? dm : nullptr);
+    CKL(ctx);
+    if (location) CK(ctx, cudaMemcpyAsync(location, dl, sizeof(float) * nb * 3, cudaMemcpyDeviceToHost, ctx->stream));
+    if (rotation) CK(ctx, cudaMemcpyAsync(rotation, dr, sizeof(float) * nb * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    if (model) CK(ctx, cudaMemcpyAsync(model, dm, sizeof(float) * nb * 16, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
     return CZ_OK;
 }
 int cz_world_last_step_counts(cz_world *w, int32_t *n_contacts, int32_t *pos_it, int32_t *vel_it) {

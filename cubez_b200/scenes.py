@@ -37,6 +37,8 @@ class Scene:
     dt: float = 1.0 / 60.0
     steps: int = 600
     notes: dict = field(default_factory=dict)
+    # optional per-pair surface materials: dict(friction=MxM, restitution=MxM, body_material=[n_bodies], plane_material=[P])
+    materials: Optional[dict] = None
 
     @property
     def n_bodies(self):
@@ -220,3 +222,19 @@ def free_bodies(prec=_abi.F64, n: int = 1 << 16, seed: int = 5) -> Scene:
     b.inverse_mass[:] = R(1.0)
     return Scene("free_bodies", prec, 1, n, b, c, _abi.Planes(np.zeros((0, 3)), np.zeros(0), prec),
                  contacts_per_world=1)
+
+
+def with_materials(scene: Scene, seed: int = 7) -> Scene:
+    """Three surface materials on any scene (0: the reference's 0.9 / 0.1, 1: slippery, 2: bouncy) with a
+    deliberately asymmetric table, ids drawn per body from splitmix64; the first plane is slippery."""
+    R = scene.prec.dtype
+    fr = np.array([[0.9, 0.35, 0.8], [0.3, 0.05, 0.5], [0.8, 0.45, 1.1]], dtype=R)
+    re = np.array([[0.1, 0.2, 0.55], [0.25, 0.0, 0.4], [0.6, 0.35, 0.7]], dtype=R)
+    u = splitmix64_draws(np.uint64(seed) + np.arange(scene.n_bodies, dtype=np.uint64), 1).reshape(-1)
+    ids = np.minimum((uniform(u, 0.0, 3.0)).astype(np.int32), 2)
+    pm = np.zeros(scene.planes.n, dtype=np.int32)
+    if pm.shape[0]:
+        pm[0] = 1
+    scene.materials = dict(friction=fr, restitution=re, body_material=ids, plane_material=pm)
+    scene.name += "+materials"
+    return scene

@@ -229,6 +229,18 @@ int cz_world_set_activation(cz_world *w, int32_t first_world, int32_t n_worlds, 
 /* Override the Pow factors (rigidbody.go:233,234,250) for duration dt with host-language values. */
 int cz_world_set_pow(cz_world *w, cz_real dt, const cz_real *lin_pow, const cz_real *ang_pow, cz_real bias);
 int cz_world_set_step_index(cz_world *w, int64_t step_index);
+/* Per-pair surface materials (new API).  The reference hard-wires Friction = 0.9 and
+ * Restitution = 0.1 into every generated contact ("test constants", the FIXME at colliders.go:199-202 and
+ * :246-249, :358-361, :435-438, :509-512, :702-705); this replaces the constants with a table lookup.  Every
+ * collider and every plane carries a material id in [0, n_materials); the contacts produced by
+ * CheckForCollisions(one, two) take Friction = friction[m(one) * n_materials + m(two)] and Restitution likewise
+ * (operands as the schedule names them; a symmetric table makes the order irrelevant).  body_material holds
+ * n_worlds * bodies_per_world ids for worlds [first_world, first_world + n_worlds) (NULL: unchanged),
+ * plane_material one id per uploaded plane (NULL: unchanged; upload the planes first).  A new n_materials resets
+ * every id to 0.  n_materials = 0 restores the constants.  Friction 0 selects calculateFrictionlessImpulse with
+ * the reference's defect mirrored (contact.go:498-531: CZ_ERR_NIL_BODY for a one-body contact). */
+int cz_world_set_materials(cz_world *w, int32_t n_materials, const cz_real *friction, const cz_real *restitution,
+                           int32_t first_world, int32_t n_worlds, const int32_t *body_material, const int32_t *plane_material);
 /* RL-style episodes (new API): snapshot the current device state as the episode start; world k
  * is at frame phase0[k] (0 <= phase0[k] < length) of its episode now and is restored to the
  * snapshot at the start of every frame on which its phase wraps to 0.  length <= 0 disables. */
@@ -240,6 +252,14 @@ int cz_world_download_bodies(cz_world *w, int32_t first_world, int32_t n_worlds,
 int cz_world_download_colliders(cz_world *w, int32_t first_world, int32_t n_worlds, cz_colliders *out);
 /* contacts of the last step of one world, as generated (before ResolveContacts), canonical order */
 int cz_world_download_contacts(cz_world *w, int32_t world, cz_contacts *out);
+/* Renderer-side export: the per-body copy the example loop makes each frame,
+ * SetGlVector3(&Node.Location, &body.Position) and SetGlQuat(&Node.LocalRotation, &body.Orientation)
+ * (examples/cubedrop.go:35-37, examples/exampleapp.go:146-159), done on the device: float32(x) of every
+ * component.  location: n*3, rotation: n*4 as (W, V[0], V[1], V[2]), model (optional extra): the body transform
+ * as a column-major 4x4; n = n_worlds * bodies_per_world; any pointer may be NULL.  dst_on_device != 0: the
+ * pointers are device pointers (a mapped GL buffer) written in place, asynchronously on the context stream. */
+int cz_world_export_gl(cz_world *w, int32_t first_world, int32_t n_worlds, float *location, float *rotation, float *model,
+                       int32_t dst_on_device);
 /* per-world counters of the last step (each array n_worlds long, any may be NULL) */
 int cz_world_last_step_counts(cz_world *w, int32_t *n_contacts, int32_t *pos_iterations, int32_t *vel_iterations);
 /* FNV-1a-64 of each world's state summed mod 2^64, and total energy. */

@@ -861,6 +861,7 @@ enum Schedule { SCHED_ALL_PAIRS_ORDERED = 0, SCHED_EXPLICIT = 1 };
 template <class R> struct ContactRecord {   // a contact as generated, before ResolveContacts
     int32_t body[2];
     R point[3], normal[3], penetration;
+    R friction, restitution;
 };
 
 template <class R> struct World {
@@ -882,6 +883,24 @@ template <class R> struct World {
     std::vector<ContactRecord<R>> lastContacts;
     int posIters = 0, velIters = 0, status = 0;
     int64_t totalContacts = 0, totalPosIters = 0, totalVelIters = 0;
+    // Per-pair surface materials (no reference counterpart — the reference
+    // hard-wires Friction 0.9 / Restitution 0.1 at every `c.Friction = 0.9` FIXME site,
+    // colliders.go:199-202, :246-249, :358-361, :435-438, :509-512, :702-705).  nMaterials == 0
+    // keeps the constants.  A contact produced by CheckForCollisions(one, two) takes
+    // table[material(one)][material(two)], the operands as the schedule names them.
+    int nMaterials = 0;
+    std::vector<R> matFriction, matRestitution;   // [nMaterials * nMaterials], row = one, column = two
+    std::vector<int32_t> bodyMaterial, planeMaterial;
+
+    void tag_materials(Contacts<R> &cs, size_t from, int a, int b) const {
+        if (nMaterials <= 0) return;
+        const int ma = a >= 0 ? bodyMaterial[a] : planeMaterial[-a - 1];
+        const int mb = b >= 0 ? bodyMaterial[b] : planeMaterial[-b - 1];
+        for (size_t k = from; k < cs.size(); k++) {
+            cs[k]->friction = matFriction[(size_t)ma * nMaterials + mb];
+            cs[k]->restitution = matRestitution[(size_t)ma * nMaterials + mb];
+        }
+    }
 
     void fix_pointers() { for (size_t i = 0; i < colliders.size(); i++) colliders[i].body = &bodies[i]; }
     bool active(int i) const { return stepIndex >= activeFrom[i]; }
@@ -904,10 +923,16 @@ template <class R> struct World {
         if (schedule == SCHED_ALL_PAIRS_ORDERED) {
             for (int i = 0; i < n; i++) {
                 if (!active(i) || colliders[i].shape == SHAPE_NONE) continue;
-                for (size_t p = 0; p < planes.size(); p++) check_for_collisions<R>(&colliders[i], nullptr, nullptr, &planes[p], contacts);
+                for (size_t p = 0; p < planes.size(); p++) {
+                    const size_t from = contacts.size();
+                    check_for_collisions<R>(&colliders[i], nullptr, nullptr, &planes[p], contacts);
+                    tag_materials(contacts, from, i, -(int)p - 1);
+                }
                 for (int j = 0; j < n; j++) {
                     if (j == i || !active(j) || colliders[j].shape == SHAPE_NONE) continue;
+                    const size_t from = contacts.size();
                     check_for_collisions<R>(&colliders[i], nullptr, &colliders[j], nullptr, contacts);
+                    tag_materials(contacts, from, i, j);
                 }
             }
         } else {
@@ -917,7 +942,9 @@ template <class R> struct World {
                 const Plane<R> *pa = nullptr, *pb = nullptr;
                 if (a >= 0) { if (!active(a) || colliders[a].shape == SHAPE_NONE) continue; ca = &colliders[a]; } else pa = &planes[-a - 1];
                 if (b >= 0) { if (!active(b) || colliders[b].shape == SHAPE_NONE) continue; cb = &colliders[b]; } else pb = &planes[-b - 1];
+                const size_t from = contacts.size();
                 check_for_collisions<R>(ca, pa, cb, pb, contacts);
+                tag_materials(contacts, from, a, b);
             }
         }
         lastContacts.clear();
@@ -927,6 +954,7 @@ template <class R> struct World {
             r.body[1] = c->bodies[1] ? (int32_t)(c->bodies[1] - bodies.data()) : -1;
             for (int k = 0; k < 3; k++) { r.point[k] = c->contactPoint[k]; r.normal[k] = c->contactNormal[k]; }
             r.penetration = c->penetration;
+            r.friction = c->friction; r.restitution = c->restitution;
             lastContacts.push_back(r);
         }
         int iters[2] = {0, 0};

@@ -309,6 +309,25 @@ int czo_world_set_episodes(void *h, int32_t length, const int32_t *phase0) {
     }
     return 0;
 }
+// per-pair surface materials (cz_world_set_materials); n_materials == 0 restores the constants
+int czo_world_set_materials(void *h, int32_t n_materials, const R *friction, const R *restitution, int32_t first, int32_t n,
+                            const int32_t *body_material, const int32_t *plane_material) {
+    OracleWorlds *w = (OracleWorlds *)h;
+    const int B = w->desc.bodies_per_world;
+    for (auto &wd : w->worlds) {
+        if (wd.nMaterials != n_materials) { wd.bodyMaterial.assign(B, 0); wd.planeMaterial.assign(16, 0); }
+        wd.nMaterials = n_materials;
+        if (n_materials > 0) {
+            wd.matFriction.assign(friction, friction + (size_t)n_materials * n_materials);
+            wd.matRestitution.assign(restitution, restitution + (size_t)n_materials * n_materials);
+            if (plane_material) for (size_t p = 0; p < w->planes.size(); p++) wd.planeMaterial[p] = plane_material[p];
+        }
+    }
+    if (n_materials > 0 && body_material)
+        for (int k = 0; k < n; k++)
+            for (int i = 0; i < B; i++) w->worlds[first + k].bodyMaterial[i] = body_material[k * B + i];
+    return 0;
+}
 int czo_world_set_step_index(void *h, int64_t s) { for (auto &wd : ((OracleWorlds *)h)->worlds) wd.stepIndex = s; return 0; }
 
 // n_threads > 1 partitions the worlds over std::threads (worlds are independent).
@@ -370,8 +389,8 @@ int czo_world_download_contacts(void *h, int32_t world, cz_contacts *out) {
     for (size_t i = 0; i < cs.size(); i++) {
         if (out->body0) out->body0[i] = cs[i].body[0];
         if (out->body1) out->body1[i] = cs[i].body[1];
-        if (out->friction) out->friction[i] = (R)0.9;
-        if (out->restitution) out->restitution[i] = (R)0.1;
+        if (out->friction) out->friction[i] = cs[i].friction;
+        if (out->restitution) out->restitution[i] = cs[i].restitution;
         for (int k = 0; k < 3; k++) {
             if (out->point) out->point[i * 3 + k] = cs[i].point[k];
             if (out->normal) out->normal[i * 3 + k] = cs[i].normal[k];

@@ -26,6 +26,10 @@ CASES = {
     "ballistic16_f64": (lambda: scenes.ballistic(_abi.F64, n_bullets=16), 300),
     "batched8_f64": (lambda: scenes.batched_cubedrop(_abi.F64, n_worlds=8), 150),
     "pile27_f64": (lambda: scenes.pile(_abi.F64, side=3), 150),
+    # per-pair surface materials (cz_world_set_materials): asymmetric 3x3 tables, ids per body, slippery ground
+    "cubedrop_materials_f64": (lambda: scenes.with_materials(scenes.cubedrop(_abi.F64), seed=3), 220),
+    "batched6_materials_f64": (lambda: scenes.with_materials(scenes.batched_cubedrop(_abi.F64, n_worlds=6)), 200),
+    "pile27_materials_f32": (lambda: scenes.with_materials(scenes.pile(_abi.F32, side=3), seed=11), 150),
 }
 
 
@@ -51,6 +55,9 @@ def run_case(make, n_steps):
 
 
 if __name__ == "__main__":
+    only = sys.argv[1:]
     for name, (make, n) in CASES.items():
+        if only and name not in only:
+            continue
         np.savez_compressed(os.path.join(HERE, name + ".npz"), **run_case(make, n))
         print("wrote", name)

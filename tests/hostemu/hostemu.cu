@@ -76,6 +76,19 @@ extern "C" {
 
 // One world.  Steps n_steps frames; per step writes the contact count, the two iteration
 // counts and an FNV hash of the (body0, body1) sequence.  State is returned in `io`.
+// materials for the next cze_run calls (n == 0: the constants); copies are kept
+static std::vector<real> g_matFric, g_matRest;
+static std::vector<uint8_t> g_bodyMat, g_planeMat;
+int cze_set_materials(int n, const cz_real *fric, const cz_real *rest, int n_bodies, const int32_t *body_mat, int n_planes, const int32_t *plane_mat) {
+    g_matFric.clear(); g_matRest.clear(); g_bodyMat.clear(); g_planeMat.assign(CZ_MAX_PLANES, 0);
+    if (n <= 0) return 0;
+    g_matFric.assign(fric, fric + n * n); g_matRest.assign(rest, rest + n * n);
+    g_bodyMat.assign(n_bodies, 0);
+    if (body_mat) for (int i = 0; i < n_bodies; i++) g_bodyMat[i] = (uint8_t)body_mat[i];
+    if (plane_mat) for (int i = 0; i < n_planes && i < CZ_MAX_PLANES; i++) g_planeMat[i] = (uint8_t)plane_mat[i];
+    return 0;
+}
+
 int cze_run(cz_bodies *io, const cz_colliders *col, const cz_planes *planes, int schedule, int n_checks, const int32_t *one,
             const int32_t *two, const int32_t *active_from, const uint8_t *integ, cz_real dt, int n_steps, int contact_cap,
             int32_t *out_counts, int32_t *out_pos, int32_t *out_vel, uint64_t *out_pairhash, cz_contacts *last_contacts) {
@@ -109,6 +122,11 @@ int cze_run(cz_bodies *io, const cz_colliders *col, const cz_planes *planes, int
     p.schedule = schedule; p.chk_one = one; p.chk_two = two;
     p.nchk = schedule == CZ_SCHED_ALL_PAIRS_ORDERED ? B * (p.P + B) : n_checks;
     for (int i = 0; i < p.P; i++) { p.planes[i].n = mk3(planes->normal[i * 3], planes->normal[i * 3 + 1], planes->normal[i * 3 + 2]); p.planes[i].offset = planes->offset[i]; }
+    if (!g_matFric.empty() && (int)g_bodyMat.size() == B) {
+        p.matFric = g_matFric.data(); p.matRest = g_matRest.data(); p.bodyMat = g_bodyMat.data();
+        p.nMat = 1; while (p.nMat * p.nMat < (int)g_matFric.size()) p.nMat++;
+        for (int i = 0; i < CZ_MAX_PLANES; i++) p.planeMat[i] = g_planeMat[i];
+    }
     std::vector<real> gen((size_t)G_NF * contact_cap), bw((size_t)BW_NF * B), cw((size_t)CW_NREAL * contact_cap);
     std::vector<int> gb0(contact_cap), gb1(contact_cap), cb(2 * (size_t)contact_cap);
     int lastC = 0;
@@ -149,13 +167,15 @@ int cze_run(cz_bodies *io, const cz_colliders *col, const cz_planes *planes, int
             if (!decode_check(p, k, a, b)) continue;
             CheckEval e;
             eval_check(p, 0, a, b, e);
-            if (e.kind == 1) { if (nC < contact_cap) store_gen(gen.data(), contact_cap, gb0.data(), gb1.data(), nC, e.gc); nC++; }
+            real fric, rest;
+            check_material(p, 0, a, b, fric, rest);
+            if (e.kind == 1) { if (nC < contact_cap) store_gen(gen.data(), contact_cap, gb0.data(), gb1.data(), nC, e.gc, fric, rest); nC++; }
             else if (e.kind == 2) {
                 ColliderView c = load_collider(p.st, e.cubeLocal, e.cubeLocal);
                 for (int v = 0; v < 8; v++) if (e.mask & (1u << v)) {
                     GenContact gc;
                     czn::cube_halfspace_contact(c, p.planes[e.plane], v, gc);
-                    if (nC < contact_cap) store_gen(gen.data(), contact_cap, gb0.data(), gb1.data(), nC, gc);
+                    if (nC < contact_cap) store_gen(gen.data(), contact_cap, gb0.data(), gb1.data(), nC, gc, fric, rest);
                     nC++;
                 }
             }
@@ -171,6 +191,8 @@ int cze_run(cz_bodies *io, const cz_colliders *col, const cz_planes *planes, int
                 last_contacts->body0[c] = gb0[c]; last_contacts->body1[c] = gb1[c];
                 for (int k = 0; k < 3; k++) { last_contacts->point[c * 3 + k] = gen[(G_POINT + k) * contact_cap + c]; last_contacts->normal[c * 3 + k] = gen[(G_NORMAL + k) * contact_cap + c]; }
                 last_contacts->penetration[c] = gen[G_PEN * contact_cap + c];
+                if (last_contacts->friction) last_contacts->friction[c] = gen[G_FRIC * contact_cap + c];
+                if (last_contacts->restitution) last_contacts->restitution[c] = gen[G_REST * contact_cap + c];
             }
         }
         // K4

@@ -26,6 +26,9 @@ def load(prec="f64"):
     lib.cze_run.argtypes = [C.POINTER(p.Bodies), C.POINTER(p.Colliders), C.POINTER(p.Planes), C.c_int, C.c_int, P32, P32, P32, PU8,
                             p.ctype, C.c_int, C.c_int, P32, P32, P32, C.POINTER(C.c_uint64), C.POINTER(p.Contacts)]
     lib.cze_run.restype = C.c_int
+    PR = C.POINTER(p.ctype)
+    lib.cze_set_materials.argtypes = [C.c_int, PR, PR, C.c_int, P32, C.c_int, P32]
+    lib.cze_set_materials.restype = C.c_int
     _LIBS[prec] = lib
     return lib
 
@@ -52,6 +55,16 @@ def run_scene(scene, n_steps, oracle_initial: Bodies, colliders_initial):
     af = scene.active_from if scene.active_from is not None else np.zeros(scene.bodies_per_world, dtype=np.int32)
     ig = scene.integrate if scene.integrate is not None else np.ones(scene.bodies_per_world, dtype=np.uint8)
     ist, cst, pst, lst = io.struct(), col.struct(), scene.planes.struct(), last.struct()
+    mat = getattr(scene, "materials", None)
+    if mat:
+        PR = C.POINTER(prec.ctype)
+        f = np.ascontiguousarray(mat["friction"], dtype=prec.dtype)
+        r = np.ascontiguousarray(mat["restitution"], dtype=prec.dtype)
+        bm = np.ascontiguousarray(mat["body_material"], dtype=np.int32)
+        pm = np.ascontiguousarray(mat["plane_material"], dtype=np.int32)
+        lib.cze_set_materials(f.shape[0], f.ctypes.data_as(PR), r.ctypes.data_as(PR), bm.shape[0], bm.ctypes.data_as(P32), pm.shape[0], pm.ctypes.data_as(P32))
+    else:
+        lib.cze_set_materials(0, None, None, 0, None, 0, None)
     rc = lib.cze_run(C.byref(ist), C.byref(cst), C.byref(pst), scene.schedule, 0 if scene.check_one is None else one.shape[0],
                      one.ctypes.data_as(P32), two.ctypes.data_as(P32), af.ctypes.data_as(P32), ig.ctypes.data_as(PU8),
                      prec.ctype(scene.dt), n_steps, scene.contacts_per_world, counts.ctypes.data_as(P32), pos.ctypes.data_as(P32),

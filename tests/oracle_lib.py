@@ -46,6 +46,7 @@ def load(prec: str = "f64") -> C.CDLL:
         "czo_world_set_activation": ([VP, C.c_int32, C.c_int32, P32, PU8], C.c_int),
         "czo_world_set_step_index": ([VP, C.c_int64], C.c_int),
         "czo_world_set_episodes": ([VP, C.c_int32, P32], C.c_int),
+        "czo_world_set_materials": ([VP, C.c_int32, PR, PR, C.c_int32, C.c_int32, P32, P32], C.c_int),
         "czo_world_step": ([VP, R, C.c_int32, C.c_int32, C.POINTER(CzStepStats)], C.c_int),
         "czo_world_download_bodies": ([VP, C.c_int32, C.c_int32, PB], C.c_int),
         "czo_world_download_colliders": ([VP, C.c_int32, C.c_int32, PC], C.c_int),
@@ -160,6 +161,8 @@ class OracleWorld:
             ig = None if ig is None else np.ascontiguousarray(ig, dtype=np.uint8)
             w.lib.czo_world_set_activation(w.h, 0, scene.n_worlds, None if af is None else af.ctypes.data_as(P32),
                                            None if ig is None else ig.ctypes.data_as(C.POINTER(C.c_uint8)))
+        if getattr(scene, "materials", None):
+            w.set_materials(**scene.materials)
         return w
 
     def upload_bodies(self, bodies: Bodies, first_world: int = 0, derive: bool = False):
@@ -176,6 +179,19 @@ class OracleWorld:
     def set_episodes(self, length: int, phase0=None):
         ph = np.zeros(self.n_worlds, dtype=np.int32) if phase0 is None else np.ascontiguousarray(phase0, dtype=np.int32)
         self.lib.czo_world_set_episodes(self.h, length, ph.ctypes.data_as(C.POINTER(C.c_int32)))
+
+    def set_materials(self, friction, restitution, body_material=None, plane_material=None, first_world: int = 0):
+        PR, P32 = C.POINTER(self.prec.ctype), C.POINTER(C.c_int32)
+        if friction is None:
+            self.lib.czo_world_set_materials(self.h, 0, None, None, 0, 0, None, None)
+            return
+        f = np.ascontiguousarray(friction, dtype=self.prec.dtype)
+        r = np.ascontiguousarray(restitution, dtype=self.prec.dtype)
+        bm = None if body_material is None else np.ascontiguousarray(body_material, dtype=np.int32).reshape(-1)
+        pm = None if plane_material is None else np.ascontiguousarray(plane_material, dtype=np.int32).reshape(-1)
+        n = 0 if bm is None else bm.shape[0] // self.B
+        self.lib.czo_world_set_materials(self.h, f.shape[0], f.ctypes.data_as(PR), r.ctypes.data_as(PR), first_world, n,
+                                         None if bm is None else bm.ctypes.data_as(P32), None if pm is None else pm.ctypes.data_as(P32))
 
     def step(self, dt, n_steps: int = 1, n_threads: int = 1) -> dict:
         st = CzStepStats()

@@ -16,7 +16,8 @@ def test_oracle_matches_golden(name):
     check_against_golden(OracleWorld.from_scene(scene), scene, load_golden(name), n, he.pair_hash)
 
 
-@pytest.mark.parametrize("name", ["cubedrop_f64", "cubedrop_f32", "cubedrop_staggered_f64", "ballistic16_f64", "pile27_f64"])
+@pytest.mark.parametrize("name", ["cubedrop_f64", "cubedrop_f32", "cubedrop_staggered_f64", "ballistic16_f64", "pile27_f64",
+                                  "cubedrop_materials_f64", "pile27_materials_f32"])
 def test_device_functions_on_host_match_golden(name):
     """cz_math/cz_body/cz_narrow/cz_resolve .cuh run on the CPU == golden (no GPU involved)."""
     make, n = CASES[name]
