@@ -79,6 +79,9 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.samples)}
 
 
+CPU_SAMPLE_WORLDS = 2048   # bounded cpu_baseline sample: 2048 whole episodes, about 10 s of one core
+
+
 def cpu_oracle_sample(n_worlds: int, n_threads: int):
     """World-steps/s of the CPU oracle on full 600-frame episodes of the first n_worlds worlds
     (the stationary population's average cost per frame equals the episode average)."""
@@ -287,7 +290,7 @@ def main():
                        "ms_per_frame": ms2.value, "lsd_radix_sort_alone_ms": sms.value, "candidate_pairs": pairs.value}
 
     if rank == 0:
-        cpu_value, cpu_s = cpu_oracle_sample(256, 1)
+        cpu_value, cpu_s = cpu_oracle_sample(CPU_SAMPLE_WORLDS, 1)   # ~10 s of one host core
         line = {
             "metric": "world_steps_per_s", "value": value, "unit": "world-steps/s", "n_gpus": world_size, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": max_ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -308,7 +311,7 @@ def main():
             "roofline_k1_f32": roofline_k1_f32,
             "roofline_k2_f32": roofline_k2_f32,
             "cpu_baseline": {"value": cpu_value, "unit": "world-steps/s", "cores": 1, "kind": "port",
-                             "sample": f"256 worlds x {EPISODE} frames, 1 thread, {cpu_s:.1f} s (C++ restatement of the Go loops)"},
+                             "sample": f"{CPU_SAMPLE_WORLDS} worlds x {EPISODE} frames, 1 thread, {cpu_s:.1f} s (C++ restatement of the Go loops)"},
             "checksum": hex(red["checksum"]), "energy": red["energy"],
             "contacts_per_world_step": red["counters"]["contacts"] / total_world_steps,
             "vel_iterations_per_world_step": red["counters"]["vel_iterations"] / total_world_steps,

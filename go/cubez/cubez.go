@@ -397,4 +397,41 @@ func (w *World) StepRL(addVelocity, addRotation []m.Real, obs *Observation, dt m
 	return st
 }
 
+// SetMaterials replaces the hard-wired `c.Friction = 0.9` / `c.Restitution = 0.1` test constants
+// (colliders.go:199-202 and five more FIXME sites) by a table lookup: friction and restitution are
+// nMaterials x nMaterials tables, row = material of CheckForCollisions' `one`, column = `two`;
+// bodyMaterial holds one id per body of every world, planeMaterial one id per plane.
+// nMaterials = 0 restores the constants.
+func (w *World) SetMaterials(nMaterials int, friction, restitution []m.Real, nWorlds int, bodyMaterial, planeMaterial []int32) {
+	var f, r *C.cz_real
+	var bm, pm *C.int32_t
+	if nMaterials > 0 {
+		f, r = (*C.cz_real)(unsafe.Pointer(&friction[0])), (*C.cz_real)(unsafe.Pointer(&restitution[0]))
+	}
+	if bodyMaterial != nil {
+		bm = (*C.int32_t)(unsafe.Pointer(&bodyMaterial[0]))
+	}
+	if planeMaterial != nil {
+		pm = (*C.int32_t)(unsafe.Pointer(&planeMaterial[0]))
+	}
+	check(C.cz_world_set_materials(w.h, C.int32_t(nMaterials), f, r, 0, C.int32_t(nWorlds), bm, pm))
+}
+
+// ExportGL fills float32 Location (3 per body) and LocalRotation (4 per body: W, V[0], V[1], V[2]) of every body —
+// the per-frame SetGlVector3 / SetGlQuat copy of examples/cubedrop.go:35-37 and examples/exampleapp.go:146-159,
+// converted on the device.  model may be nil; otherwise it receives the body transform as a column-major 4x4.
+func (w *World) ExportGL(nWorlds int, location, rotation, model []float32) {
+	var l, q, md *C.float
+	if location != nil {
+		l = (*C.float)(unsafe.Pointer(&location[0]))
+	}
+	if rotation != nil {
+		q = (*C.float)(unsafe.Pointer(&rotation[0]))
+	}
+	if model != nil {
+		md = (*C.float)(unsafe.Pointer(&model[0]))
+	}
+	check(C.cz_world_export_gl(w.h, 0, C.int32_t(nWorlds), l, q, md, 0))
+}
+
 func (w *World) Close() { C.cz_world_destroy(w.h) }
