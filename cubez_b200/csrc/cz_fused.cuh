@@ -53,6 +53,15 @@ struct FusedPlan {
     // split mode: one launch per phase of the frame (A: integrate + narrowphase + prepare, B: position
     // loop, C: velocity loop); contact state lives in per-WORLD global arrays between the launches
     int split, splitMinb;
+    // the loop phases (B, C) of split mode stage only what the loops touch (no collider data, no narrowphase
+    // queues): a smaller world record -> more resident CTAs per SM (the loops are latency-bound: 168 registers at
+    // 3 CTAs of 128 threads per SM without spills, 128 at 4)
+    size_t loopWorldBytes, loopSmemBytes;
+    size_t phaseAWorldBytes, phaseASmemBytes;   // split mode: phase A keeps the hot contact fields in the per-world global arrays
+    int phaseAGrid;
+    int maxGrid;         // largest grid of any launch: sizes the per-group scratch
+    int loopBlocksPerSM, loopGrid;
+    int phaseAMinb;      // register budget of the phase-A launch
     real *coldW;         // [W][Cc*CW_NCOLD]
     real *hotPen, *hotDdv;   // [W][Cc]
     int *hotCb0, *hotCb1;    // [W][Cc]
@@ -63,6 +72,20 @@ static inline size_t world_bytes(int B, int Cc, int nchk) {
     size_t ints = 2 * (size_t)Cc + 2 * (size_t)B;
     size_t shorts = 3 * (size_t)nchk;          // per-check info + the queues of checks that need a full test + plane-check base slots
     size_t bytes = reals * sizeof(real) + ints * sizeof(int) + shorts * sizeof(unsigned short) + 2 * (size_t)nchk + (size_t)Cc;
+    return (bytes + 15) / 16 * 16;
+}
+
+// world record of the loop phases: body work record, hot contact fields, body masks, contact ids, flags, match list
+static inline size_t world_bytes_loops(int B, int Cc) {
+    size_t reals = (size_t)czr::BW_NF * B + 2 * (size_t)Cc + (size_t)B;
+    size_t ints = 2 * (size_t)Cc + 2 * (size_t)B;
+    size_t bytes = reals * sizeof(real) + ints * sizeof(int) + (size_t)Cc;
+    return (bytes + 15) / 16 * 16;
+}
+
+// world record of the phase-A launch of split mode: body + collider record, flags, check queues
+static inline size_t world_bytes_phase_a(int B, int nchk) {
+    size_t bytes = (size_t)FB_NF * B * sizeof(real) + 2 * (size_t)B * sizeof(int) + 3 * (size_t)nchk * sizeof(unsigned short) + 2 * (size_t)nchk;
     return (bytes + 15) / 16 * 16;
 }
 
@@ -109,12 +132,31 @@ static inline bool plan(FusedPlan &fp, int B, int P, int Cc, int nchk, int sched
     // Large batches run one launch per phase of the frame (every warp of the GPU is then in the same
     // code region: +15 % on 65 536 worlds); small batches keep the single persistent launch.
     fp.split = env_int("CUBEZ_FUSED_SPLIT", W >= 8192 ? 1 : 0);
-    fp.splitMinb = env_int("CUBEZ_FUSED_SPLIT_MINB", 2);
-    if (fp.split && G == 8 && fp.splitMinb > 2) {   // more resident blocks for the (smaller) per-phase kernels
-        int b2 = (int)(perSM / (smem + 1024));
-        if (b2 > fp.splitMinb * (128 / threads)) b2 = fp.splitMinb * (128 / threads);
-        if (b2 > bps) bps = b2;
+    fp.splitMinb = env_int("CUBEZ_FUSED_SPLIT_MINB", 3);
+    if (fp.splitMinb < 2 || fp.splitMinb > 4 || G != 8) fp.splitMinb = 2;   // instantiated for G = 8 only
+    fp.phaseAMinb = env_int("CUBEZ_FUSED_PHASE_A_MINB", 3);
+    if (fp.phaseAMinb < 2 || fp.phaseAMinb > 4 || G != 8) fp.phaseAMinb = 2;
+    fp.loopWorldBytes = world_bytes_loops(B, Cc);
+    fp.loopSmemBytes = fp.loopWorldBytes * gpb;
+    {
+        int lb = (int)(perSM / (fp.loopSmemBytes + 1024));
+        if (lb > maxByThreads) lb = maxByThreads;
+        if (lb > fp.splitMinb * (128 / threads)) lb = fp.splitMinb * (128 / threads);
+        if (lb < 1) lb = 1;
+        fp.loopBlocksPerSM = lb;
+        fp.loopGrid = smCount * lb;
     }
+    fp.phaseAWorldBytes = world_bytes_phase_a(B, nchk);
+    fp.phaseASmemBytes = fp.phaseAWorldBytes * gpb;
+    {
+        int ab = (int)(perSM / (fp.phaseASmemBytes + 1024));
+        if (ab > maxByThreads) ab = maxByThreads;
+        if (ab > fp.phaseAMinb * (128 / threads)) ab = fp.phaseAMinb * (128 / threads);
+        if (ab < 1) ab = 1;
+        fp.phaseAGrid = smCount * ab;
+    }
+    fp.maxGrid = fp.grid > fp.phaseAGrid ? fp.grid : fp.phaseAGrid;
+    if (fp.loopGrid > fp.maxGrid) fp.maxGrid = fp.loopGrid;
     fp.coldW = nullptr; fp.hotPen = fp.hotDdv = nullptr; fp.hotCb0 = fp.hotCb1 = nullptr;
     fp.lockstep = env_int("CUBEZ_FUSED_LOCKSTEP", 3);   // 0 none, 1 frame start, 2 + before narrowphase/resolve, 3 + between the two loops
     fp.coldReals = (size_t)Cc * czr::CW_NCOLD + (size_t)nchk * 8;   // + staging of pair-test contacts
@@ -189,7 +231,7 @@ __device__ __forceinline__ void stage_gen(const Staged &s, int slot, const GenCo
 }
 
 // copy one world's hot state from a chunked store into the staged record
-template <int G>
+template <int G, bool FULL>
 __device__ __forceinline__ void stage_world(const Staged &s, const BodyStore &st, long long gbase, int B, int tid) {
     using namespace czr;
     for (int b = tid; b < B; b += G) {
@@ -208,11 +250,13 @@ __device__ __forceinline__ void stage_world(const Staged &s, const BodyStore &st
         for (int k = 0; k < 3; k++) s.fb[(BW_LACC + k) * B + b] = la.c[k];
 #pragma unroll
         for (int k = 0; k < 9; k++) s.fb[(BW_IITW + k) * B + b] = iw.c[k];
-        M34 ctr = czb::ld_m34(st, czb::C_X01, gi);
+        if (FULL) {
+            M34 ctr = czb::ld_m34(st, czb::C_X01, gi);
 #pragma unroll
-        for (int k = 0; k < 12; k++) s.fb[(FB_CTR + k) * B + b] = ctr.c[k];
-        c = st.ld(czb::C_H01, gi); s.fb[(FB_HALF + 0) * B + b] = c.x; s.fb[(FB_HALF + 1) * B + b] = c.y;
-        c = st.ld(czb::C_H2R, gi); s.fb[(FB_HALF + 2) * B + b] = c.x; s.fb[FB_RADIUS * B + b] = c.y;
+            for (int k = 0; k < 12; k++) s.fb[(FB_CTR + k) * B + b] = ctr.c[k];
+            c = st.ld(czb::C_H01, gi); s.fb[(FB_HALF + 0) * B + b] = c.x; s.fb[(FB_HALF + 1) * B + b] = c.y;
+            c = st.ld(czb::C_H2R, gi); s.fb[(FB_HALF + 2) * B + b] = c.x; s.fb[FB_RADIUS * B + b] = c.y;
+        }
         s.fb[BW_INVM * B + b] = st.ld(czb::C_MD, gi).x;
         s.fb[BW_AWAKE * B + b] = st.awake[gi] ? R_(1) : R_(0);
         s.flags[b] = (int)st.shape[gi] | (st.can_sleep[gi] ? FF_CANSLEEP : 0) | (st.integ[gi] ? FF_INTEG : 0) | (st.ident[gi] ? FF_IDENT : 0);
@@ -236,21 +280,30 @@ __global__ void __launch_bounds__(128, MINB) k_world_fused(WorldParams p, FusedP
     const unsigned mask = 0xffffffffu;   // all collectives are warp-wide with width G: the groups of a warp stay converged
     const int B = p.B, Cc = p.Cc;
     Staged s;
-    unsigned char *base = smem_raw + (size_t)grp * fp.worldBytes;
+    // FULL: the launch runs phase A (integrate + narrowphase) and needs collider data and the check queues; the loop
+    // phases of split mode use the short record of world_bytes_loops
+    constexpr bool FULL = (PH & PH_A) != 0;
+    // A_ONLY: the phase-A launch of split mode hands the hot contact fields to the loop launches through the
+    // per-world global arrays anyway, so it writes them there directly (each is touched two or three times per
+    // contact, never scanned) and keeps no copy in shared memory: a 3.4 KB record instead of 5 KB, 3 CTAs per SM
+    constexpr bool A_ONLY = PH == PH_A;
+    unsigned char *base = smem_raw + (size_t)grp * (A_ONLY ? fp.phaseAWorldBytes : (FULL ? fp.worldBytes : fp.loopWorldBytes));
     s.fb = (real *)base; s.bs = B;
-    s.pen = s.fb + (size_t)FB_NF * B;
-    s.ddv = s.pen + Cc;
-    unsigned long long *const bmask = (unsigned long long *)(s.ddv + Cc);   // [B]
-    s.cb0 = (int *)(bmask + B);
-    s.cb1 = s.cb0 + Cc;
-    s.flags = s.cb1 + Cc;
+    const int ch = A_ONLY ? 0 : Cc;   // hot contact fields held in shared memory
+    s.pen = s.fb + (size_t)(FULL ? (int)FB_NF : (int)BW_NF) * B;
+    s.ddv = s.pen + ch;
+    unsigned long long *const bmask = (unsigned long long *)(s.ddv + ch);   // [B]
+    s.cb0 = (int *)(bmask + (A_ONLY ? 0 : B));
+    s.cb1 = s.cb0 + ch;
+    s.flags = s.cb1 + ch;
     s.active = s.flags + B;
+    const int nq = FULL ? p.nchk : 0;
     s.info = (unsigned short *)(s.active + B);
-    s.queue = s.info + p.nchk;
-    s.pbase = s.queue + p.nchk;
-    s.cnt = (unsigned char *)(s.pbase + p.nchk);
-    s.pmask = s.cnt + p.nchk;
-    unsigned char *mlist = s.pmask + p.nchk;
+    s.queue = s.info + nq;
+    s.pbase = s.queue + nq;
+    s.cnt = (unsigned char *)(s.pbase + nq);
+    s.pmask = s.cnt + nq;
+    unsigned char *mlist = s.pmask + nq;
     real *const groupScratch = fp.cold + ((size_t)blockIdx.x * fp.groupsPerBlock + grp) * fp.coldReals;
     s.cold = groupScratch;
     s.pairGen = groupScratch + (size_t)Cc * CW_NCOLD;
@@ -261,8 +314,8 @@ __global__ void __launch_bounds__(128, MINB) k_world_fused(WorldParams p, FusedP
     x.cold = s.cold; x.cfs = 1; x.ccs = CW_NCOLD;       // AoS
     x.pen = s.pen; x.ddv = s.ddv; x.fric = nullptr; x.rest = nullptr;
     x.cb0 = s.cb0; x.cb1 = s.cb1; x.nC = 0; x.dt = dt;
-    x.mlist = Cc <= 256 ? mlist : nullptr;
-    x.bmask = (Cc <= 64 && fp.bodyMasks) ? bmask : nullptr;
+    x.mlist = (Cc <= 256 && !A_ONLY) ? mlist : nullptr;                      // the loops' scratch: absent from the phase-A record
+    x.bmask = (Cc <= 64 && fp.bodyMasks && !A_ONLY) ? bmask : nullptr;
     x.xb = nullptr; x.xbs = 0; x.store = st;
     GenView gv;
     gv.pn = s.cold; gv.fs = 1; gv.cs = CW_NCOLD; gv.pen = s.pen; gv.fric = nullptr; gv.rest = nullptr; gv.b0 = s.cb0; gv.b1 = s.cb1;
@@ -290,11 +343,17 @@ __global__ void __launch_bounds__(128, MINB) k_world_fused(WorldParams p, FusedP
             x.rest = p.gen + G_REST * gsAll + (long long)w * Cc;
             gv.fric = x.fric; gv.rest = x.rest;
         }
-        if (live) stage_world<G>(s, st, gbase, B, tid);
+        if (live) stage_world<G, FULL>(s, st, gbase, B, tid);
         int lastC = 0, lastPos = 0, lastVel = 0;
         if (PH != PH_ALL) {   // split mode: contact state of this world lives in global memory between launches
             s.cold = fp.coldW + (size_t)w * Cc * CW_NCOLD;
             x.cold = s.cold; gv.pn = s.cold;
+            if (A_ONLY) {
+                const size_t o = (size_t)w * Cc;
+                s.pen = fp.hotPen + o; s.ddv = fp.hotDdv + o; s.cb0 = fp.hotCb0 + o; s.cb1 = fp.hotCb1 + o;
+                x.pen = s.pen; x.ddv = s.ddv; x.cb0 = s.cb0; x.cb1 = s.cb1;
+                gv.pen = s.pen; gv.b0 = s.cb0; gv.b1 = s.cb1;
+            }
             if (!(PH & PH_A) && live) {
                 lastC = p.nContacts[w];
                 const int nL = lastC > Cc ? 0 : lastC;
@@ -314,7 +373,7 @@ __global__ void __launch_bounds__(128, MINB) k_world_fused(WorldParams p, FusedP
             int nC = 0;
             if (PH & PH_A) {
             if (live && episode_wraps(p, w, step)) {   // RL-style episode reset: restore the snapshot
-                stage_world<G>(s, p.snap, gbase, B, tid);
+                stage_world<G, FULL>(s, p.snap, gbase, B, tid);
                 for (int b = tid; b < B; b += G) {   // the body transform lives in the global store
 #pragma unroll
                     for (int k = czb::C_L2T0; k <= czb::C_T11W0; k++) st.st(k, gbase + b, p.snap.ld(k, gbase + b));
@@ -560,16 +619,19 @@ __global__ void __launch_bounds__(128, MINB) k_world_fused(WorldParams p, FusedP
 #pragma unroll
             for (int k = 0; k < 9; k++) iw.c[k] = s.fb[(BW_IITW + k) * B + b];
             czb::st_derived(st, gi, s.fb[(BW_LACC + 2) * B + b], tr, iw);
-            M34 ctr;
+            if (FULL) {   // the collider transform changes in updateObjects only
+                M34 ctr;
 #pragma unroll
-            for (int k = 0; k < 12; k++) ctr.c[k] = s.fb[(FB_CTR + k) * B + b];
-            czb::st_m34(st, czb::C_X01, gi, ctr);
+                for (int k = 0; k < 12; k++) ctr.c[k] = s.fb[(FB_CTR + k) * B + b];
+                czb::st_m34(st, czb::C_X01, gi, ctr);
+            }
             st.awake[gi] = s.fb[BW_AWAKE * B + b] != R_(0) ? 1 : 0;
         }
         if (PH != PH_ALL && live) {   // hand the contact state to the next phase's launch
             const int nS = lastC > Cc ? 0 : lastC;
             const size_t o = (size_t)w * Cc;
             for (int c = tid; c < nS; c += G) {
+                if (A_ONLY) break;   // written in place
                 if (PH & PH_A) { fp.hotCb0[o + c] = s.cb0[c]; fp.hotCb1[o + c] = s.cb1[c]; fp.hotDdv[o + c] = s.ddv[c]; }
                 if (PH & (PH_A | PH_B)) fp.hotPen[o + c] = s.pen[c];
             }
@@ -663,14 +725,16 @@ static inline int launch(const FusedPlan &fp, const WorldParams &p, real dt, rea
     cudaError_t e = cudaSuccess;
     if (!countersZeroed) e = cudaMemsetAsync(nextWorld, 0, sizeof(unsigned int), stream);   // stream-ordered before the launch
     if (e != cudaSuccess) return (int)e;
-    int grid = fp.grid;
+    const bool loops = phases == PH_B || phases == PH_C;
+    int grid = loops ? fp.loopGrid : (phases == PH_A ? fp.phaseAGrid : fp.grid);
+    const size_t smemBytes = loops ? fp.loopSmemBytes : (phases == PH_A ? fp.phaseASmemBytes : fp.smemBytes);
     const int needed = (p.wCount + fp.groupsPerBlock - 1) / fp.groupsPerBlock;
     if (grid > needed) grid = needed;
 #define CZF_LAUNCH(GG, MB, LS, PHS, MT)                                                                               \
     do {                                                                                                            \
-        if (fp.smemBytes > 48 * 1024)                                                                               \
-            e = cudaFuncSetAttribute(k_world_fused<GG, MB, LS, PHS, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fp.smemBytes); \
-        if (e == cudaSuccess) k_world_fused<GG, MB, LS, PHS, MT><<<grid, fp.threads, fp.smemBytes, stream>>>(p, fp, dt, bias, nSteps, nextWorld); \
+        if (smemBytes > 48 * 1024)                                                                                  \
+            e = cudaFuncSetAttribute(k_world_fused<GG, MB, LS, PHS, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemBytes); \
+        if (e == cudaSuccess) k_world_fused<GG, MB, LS, PHS, MT><<<grid, fp.threads, smemBytes, stream>>>(p, fp, dt, bias, nSteps, nextWorld); \
     } while (0)
 #define CZF_LAUNCH_G(GG)                                                                                            \
     do {                                                                                                            \
@@ -679,13 +743,13 @@ static inline int launch(const FusedPlan &fp, const WorldParams &p, real dt, rea
             else if (phases == PH_B) CZF_LAUNCH(GG, 2, false, PH_B, true);                                          \
             else if (phases == PH_C) CZF_LAUNCH(GG, 2, false, PH_C, true);                                          \
             else CZF_LAUNCH(GG, 2, true, PH_ALL, true);                                                             \
-        } else if (phases != PH_ALL && GG == 8 && fp.splitMinb == 3) {                                              \
-            if (phases == PH_A) CZF_LAUNCH(8, 3, false, PH_A, false);                                               \
-            else if (phases == PH_B) CZF_LAUNCH(8, 3, false, PH_B, false);                                          \
+        } else if (phases == PH_A && GG == 8 && fp.phaseAMinb == 3) { CZF_LAUNCH(8, 3, false, PH_A, false);             \
+        } else if (phases == PH_A && GG == 8 && fp.phaseAMinb == 4) { CZF_LAUNCH(8, 4, false, PH_A, false);             \
+        } else if (loops && GG == 8 && fp.splitMinb == 3) {                                                         \
+            if (phases == PH_B) CZF_LAUNCH(8, 3, false, PH_B, false);                                               \
             else CZF_LAUNCH(8, 3, false, PH_C, false);                                                              \
-        } else if (phases != PH_ALL && GG == 8 && fp.splitMinb == 4) {                                              \
-            if (phases == PH_A) CZF_LAUNCH(8, 4, false, PH_A, false);                                               \
-            else if (phases == PH_B) CZF_LAUNCH(8, 4, false, PH_B, false);                                          \
+        } else if (loops && GG == 8 && fp.splitMinb == 4) {                                                         \
+            if (phases == PH_B) CZF_LAUNCH(8, 4, false, PH_B, false);                                               \
             else CZF_LAUNCH(8, 4, false, PH_C, false);                                                              \
         } else if (phases == PH_A) CZF_LAUNCH(GG, 2, false, PH_A, false);                                           \
         else if (phases == PH_B) CZF_LAUNCH(GG, 2, false, PH_B, false);                                             \

@@ -376,7 +376,7 @@ static int world_plan(cz_world *w) {
           for (void *q : sp) if (q) cudaFree(q); }
         w->useFused = !w->useBP && czf::plan(w->fused, B, w->P, Cc, w->nchk, w->d.schedule, ctx->smem_optin, ctx->sm_count, W);
         if (w->useFused) {
-            CK(ctx, cudaMalloc(&w->fused.cold, sizeof(real) * w->fused.coldReals * (size_t)w->fused.grid * w->fused.groupsPerBlock));
+            CK(ctx, cudaMalloc(&w->fused.cold, sizeof(real) * w->fused.coldReals * (size_t)w->fused.maxGrid * w->fused.groupsPerBlock));
             if (!w->d_next) CK(ctx, cudaMalloc(&w->d_next, sizeof(unsigned int) * 4));
             if (!w->order3) CK(ctx, cudaMalloc(&w->order3, sizeof(int) * 3 * (size_t)W));
             w->useOrder = czf::env_int("CUBEZ_FUSED_ORDER", 1) != 0 && W >= 64;
@@ -622,7 +622,7 @@ int cz_world_set_materials(cz_world *w, int32_t n_materials, const cz_real *fric
         for (long long i = 0; i < n * B; i++) ids[i] = (uint8_t)body_material[i];
         CK(ctx, cudaMemcpy(w->d_bodyMat + first * B, ids.data(), ids.size(), cudaMemcpyHostToDevice));
     }
-    if (plane_material) for (int i = 0; i < w->P; i++) w->planeMat[i] = (uint8_t)plane_material[i];
+    if (plane_material) for (int i = 0; i < w->P && i < CZ_MAX_PLANES; i++) w->planeMat[i] = (uint8_t)plane_material[i];
     w->nMat = n_materials;
     return CZ_OK;
 }
@@ -1016,7 +1016,7 @@ static int host_pipe_init(cz_world *w) {
     CK(ctx, cudaMalloc(&pp.dOut, sizeof(real) * NB * 38));   // pos3 ori4 vel3 rot3 motion1 lacc3 tr12 iitw9
     CK(ctx, cudaMalloc(&pp.dFlags, 3 * (size_t)NB));
     CK(ctx, cudaMalloc(&pp.dNext, sizeof(unsigned int) * 4 * chunks));
-    for (int k = 1; k < pp.nComp; k++) CK(ctx, cudaMalloc(&pp.coldX[k], sizeof(real) * w->fused.coldReals * (size_t)w->fused.grid * w->fused.groupsPerBlock));
+    for (int k = 1; k < pp.nComp; k++) CK(ctx, cudaMalloc(&pp.coldX[k], sizeof(real) * w->fused.coldReals * (size_t)w->fused.maxGrid * w->fused.groupsPerBlock));
     pp.ready = true;
     return CZ_OK;
 }
