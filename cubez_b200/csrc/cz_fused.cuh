@@ -230,6 +230,19 @@ __device__ __forceinline__ void stage_gen(const Staged &s, int slot, const GenCo
     s.cb1[slot] = c.b1;
 }
 
+// Split mode: the as-generated record goes straight into the world's download arrays (point, normal,
+// penetration, body ids: what cz_world_download_contacts returns) and prepare_contact reads it from there —
+// the copy into those arrays after generation cost a dependent L2 round trip per world and frame
+// (ncu: 21 % of the stall samples of the phase-A launch).
+__device__ __forceinline__ void stage_gen_direct(const czr::GenView &g, int slot, const GenContact &c) {
+    real *r = g.pn + (size_t)slot * g.cs;
+#pragma unroll
+    for (int k = 0; k < 3; k++) { r[(size_t)(czr::G_POINT + k) * g.fs] = c.point.c[k]; r[(size_t)(czr::G_NORMAL + k) * g.fs] = c.normal.c[k]; }
+    g.pen[slot] = c.pen;
+    g.b0[slot] = c.b0;
+    g.b1[slot] = c.b1;
+}
+
 // copy one world's hot state from a chunked store into the staged record
 template <int G, bool FULL>
 __device__ __forceinline__ void stage_world(const Staged &s, const BodyStore &st, long long gbase, int B, int tid) {
@@ -287,6 +300,7 @@ __global__ void __launch_bounds__(128, MINB) k_world_fused(WorldParams p, FusedP
     // per-world global arrays anyway, so it writes them there directly (each is touched two or three times per
     // contact, never scanned) and keeps no copy in shared memory: a 3.4 KB record instead of 5 KB, 3 CTAs per SM
     constexpr bool A_ONLY = PH == PH_A;
+    constexpr bool DIRECT = PH != PH_ALL;   // as-generated contacts are written in place (stage_gen_direct)
     unsigned char *base = smem_raw + (size_t)grp * (A_ONLY ? fp.phaseAWorldBytes : (FULL ? fp.worldBytes : fp.loopWorldBytes));
     s.fb = (real *)base; s.bs = B;
     const int ch = A_ONLY ? 0 : Cc;   // hot contact fields held in shared memory
@@ -348,11 +362,15 @@ __global__ void __launch_bounds__(128, MINB) k_world_fused(WorldParams p, FusedP
         if (PH != PH_ALL) {   // split mode: contact state of this world lives in global memory between launches
             s.cold = fp.coldW + (size_t)w * Cc * CW_NCOLD;
             x.cold = s.cold; gv.pn = s.cold;
+            if (DIRECT && (PH & PH_A)) {
+                const long long gsAll = (long long)p.W * Cc, o = (long long)w * Cc;
+                gv.pn = p.gen + o; gv.fs = (int)gsAll; gv.cs = 1;
+                gv.pen = p.gen + G_PEN * gsAll + o; gv.b0 = p.gb0 + o; gv.b1 = p.gb1 + o;
+            }
             if (A_ONLY) {
                 const size_t o = (size_t)w * Cc;
                 s.pen = fp.hotPen + o; s.ddv = fp.hotDdv + o; s.cb0 = fp.hotCb0 + o; s.cb1 = fp.hotCb1 + o;
                 x.pen = s.pen; x.ddv = s.ddv; x.cb0 = s.cb0; x.cb1 = s.cb1;
-                gv.pen = s.pen; gv.b0 = s.cb0; gv.b1 = s.cb1;
             }
             if (!(PH & PH_A) && live) {
                 lastC = p.nContacts[w];
@@ -534,7 +552,8 @@ __global__ void __launch_bounds__(128, MINB) k_world_fused(WorldParams p, FusedP
                         gc.pen = r[6];
                         const int code = (int)r[7];
                         gc.b0 = code / 128; gc.b1 = code % 128 - 1;
-                        stage_gen(s, slot, gc);
+                        if (DIRECT) stage_gen_direct(gv, slot, gc);
+                        else stage_gen(s, slot, gc);
                         if (MAT) check_material(p, gbase, a, b2, x.fric[slot], x.rest[slot]);
                     }
                 }
@@ -555,7 +574,8 @@ __global__ void __launch_bounds__(128, MINB) k_world_fused(WorldParams p, FusedP
                 GenContact gc;
                 if (c.shape == CZ_SHAPE_SPHERE) czn::sphere_halfspace(c, p.planes[pi], gc);
                 else czn::cube_halfspace_contact(c, p.planes[pi], v, gc);
-                stage_gen(s, slot, gc);
+                if (DIRECT) stage_gen_direct(gv, slot, gc);
+                else stage_gen(s, slot, gc);
                 if (MAT) check_material(p, gbase, a, b2, x.fric[slot], x.rest[slot]);
             }
             __syncwarp(mask);
@@ -564,7 +584,7 @@ __global__ void __launch_bounds__(128, MINB) k_world_fused(WorldParams p, FusedP
             lastC = nC;
             lastPos = lastVel = 0;
             if (nC > Cc) { status = CZ_ERR_CAPACITY; nC = 0; }
-            if (fp.keepContacts && stepNo == nSteps - 1 && nC > 0) {
+            if (!DIRECT && fp.keepContacts && stepNo == nSteps - 1 && nC > 0) {
                 // dump the as-generated contacts of the last frame for cz_world_download_contacts
                 const long long gs = (long long)p.W * Cc;
                 real *gen = p.gen + (long long)w * Cc;

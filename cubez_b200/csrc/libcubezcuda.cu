@@ -891,8 +891,15 @@ int cz_world_download_contacts(cz_world *w, int32_t world, cz_contacts *out) {
         if (out->normal && (rc = getf(czr::G_NORMAL + k, out->normal, k, 3))) return rc;
     }
     if (out->penetration && (rc = getf(czr::G_PEN, out->penetration, 0, 1))) return rc;
-    if (out->friction && (rc = getf(czr::G_FRIC, out->friction, 0, 1))) return rc;
-    if (out->restitution && (rc = getf(czr::G_REST, out->restitution, 0, 1))) return rc;
+    if (w->nMat > 0) {
+        if (out->friction && (rc = getf(czr::G_FRIC, out->friction, 0, 1))) return rc;
+        if (out->restitution && (rc = getf(czr::G_REST, out->restitution, 0, 1))) return rc;
+    } else {   // the reference's constants (colliders.go:201-202 etc.)
+        for (int i = 0; i < nC; i++) {
+            if (out->friction) out->friction[i] = (real)0.9;
+            if (out->restitution) out->restitution[i] = (real)0.1;
+        }
+    }
     if (out->body0) CK(ctx, cudaMemcpy(out->body0, w->gb0 + off, sizeof(int) * nC, cudaMemcpyDeviceToHost));
     if (out->body1) CK(ctx, cudaMemcpy(out->body1, w->gb1 + off, sizeof(int) * nC, cudaMemcpyDeviceToHost));
     return CZ_OK;
