@@ -237,17 +237,26 @@ def main():
 
     # ---- roofline of the dominant kernel (fused world step) ---------------------------------
     peak, peak_kind = measured_peaks()
-    # algorithmic HBM bytes of one k_world_fused launch: stage 41 chunks (16 B) + 5 flag/int fields per body in,
-    # 25 chunks + 1 flag out; independent of the number of frames (state stays in shared memory)
-    fused_bytes = nb * (41 * 16 + 8 + 25 * 16 + 1)
-    roofline = {"bound": "hbm", "kernel": "k_world_fused", "achieved": fused_bytes / (dev_ms * 1e-3) / 1e9, "peak": peak,
-                "unit": "GB/s", "frac": fused_bytes / (dev_ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_kind": peak_kind,
-                "note": "not HBM-bound by design: state is shared-memory resident across frames; the kernel is FP64-issue/latency bound (see profiles/)",
-                # what does bound it, from ncu --set full of one frame at 65 536 worlds (profiles/r01_fused_split_phases_v2.txt):
-                "ncu": {"phases_ms": {"A integrate+narrowphase+prepare": 0.948, "B position loop": 0.494, "C velocity loop": 1.315},
-                        "fp64_pipe_active_pct": {"A": 21.5, "B": 10.5, "C": 23.0}, "issue_active_pct": {"A": 29.7, "B": 21.4, "C": 30.6},
-                        "active_lanes_of_32": {"A": 12.2, "B": 21.1, "C": 21.4}, "warps_per_sm": 8, "registers_per_thread": 255,
-                        "top_stalls": ["wait (fixed-latency FP64 dependency at 2 warps per scheduler)", "long_scoreboard (cold contact records in L2)"]}}
+    # Algorithmic HBM bytes of ONE FRAME of the fused step in split mode (three launches per frame at this batch size:
+    # A integrate + narrowphase + prepare | B position loop | C velocity loop):
+    #   A stages the whole body + collider record (41 chunks of 16 B + 8 flag bytes in, 25 chunks + 1 flag out);
+    #   B and C each stage the loops' body record (15 chunks + 8 flag bytes in, 20 chunks + 1 flag out);
+    #   every contact is written once by A (as-generated 64 B, cold record 144 B, hot fields 24 B) and its hot
+    #   fields cross twice more (B: 16 B in, 8 B out; C: 16 B in) — the loops' cold-record reads hit L2.
+    contacts_per_frame = st["contacts"] / max(1, args.steps)
+    fused_bytes = nb * ((41 * 16 + 8 + 25 * 16 + 1) + 2 * (15 * 16 + 8 + 20 * 16 + 1)) + contacts_per_frame * (232 + 24 + 16)
+    frame_ms = dev_ms / max(1, args.steps)
+    roofline = {"bound": "hbm", "kernel": "k_world_fused, split mode: phases A | B | C, one launch each per frame",
+                "achieved": fused_bytes / (frame_ms * 1e-3) / 1e9, "peak": peak,
+                "unit": "GB/s", "frac": fused_bytes / (frame_ms * 1e-3) / 1e9 / peak,
+                "traffic": 1.979e9,   # dram__bytes_read+write of the three launches of one frame, ncu --set full (profiles/r01_fused_split_phases_v4.txt)
+                "algorithmic_bytes_per_frame": fused_bytes, "peak_kind": peak_kind,
+                "note": "not HBM-bound by design: a frame's working state is shared-memory resident inside each launch; the kernels are bound by FP64 dependency latency and L2 latency of the cold contact records at 12 warps per SM (see profiles/)",
+                # what does bound it, from ncu --set full of one frame at 65 536 worlds (profiles/r01_fused_split_phases_v4.txt):
+                "ncu": {"phases_ms": {"A integrate+narrowphase+prepare": 0.641, "B position loop": 0.383, "C velocity loop": 1.034},
+                        "fp64_pipe_active_pct": {"A": 21.6, "B": 14.8, "C": 31.6}, "issue_active_pct": {"A": 34.4, "B": 28.4, "C": 39.0},
+                        "active_lanes_of_32": {"A": 16.3, "B": 18.4, "C": 20.0}, "warps_per_sm": 12, "registers_per_thread": 168,
+                        "top_stalls": ["long_scoreboard (cold contact records and staged state in L2)", "wait (fixed-latency FP64 dependency at 3 warps per scheduler)"]}}
     roofline_k1 = None
     if rank == 0 and not args.no_k1:
         world.close()
