@@ -162,6 +162,25 @@ def test_gpu_materials_through_the_sort_based_broadphase():
 
 
 @pytest.mark.gpu
+def test_gpu_materials_on_the_explicit_ballistic_schedule():
+    """cfg2's explicit check list (examples/ballistic.go:47-97; 1 058 checks with 16 bullets, planes and colliders on
+    either side of a check): the table is indexed by the operands as the schedule names them."""
+    sc = scenes.with_materials(scenes.ballistic(_abi.F64, n_bullets=16), seed=9)
+    gpu, cpu = _gpu_world(sc, _abi.WORLD_NO_FUSED), OracleWorld.from_scene(sc)
+    for s in range(0, 300, 25):
+        gs, cs = gpu.step(sc.dt, 25), cpu.step(sc.dt, 25)
+        for k in ("contacts", "pos_iterations", "vel_iterations"):
+            assert gs[k] == cs[k], (s, k)
+        gc, cc = gpu.contacts(0), cpu.contacts(0)
+        for f in ("body0", "body1", "friction", "restitution", "penetration"):
+            assert np.array_equal(gc.valid(f), cc.valid(f)), (s, f)
+    g, c = gpu.download(), cpu.download()
+    for f in STATE_FIELDS:
+        assert np.array_equal(getattr(g, f), getattr(c, f)), f
+    gpu.close()
+
+
+@pytest.mark.gpu
 def test_gpu_rl_step_with_materials_and_episodes():
     sc = scenes.with_materials(scenes.batched_cubedrop(n_worlds=300))
     gpu, cpu = _gpu_world(sc, contacts_per_world=64), OracleWorld.from_scene(sc)
