@@ -310,7 +310,7 @@ def main():
                        "l2": "state (%.0f MB/GPU) larger than L2; frames of one call run from shared memory" % (nb * 84 * 16 / 1e6)},
             "body_steps_per_s": value * BODIES_PER_WORLD,
             "e2e": {"value": e2e_value, "unit": "world-steps/s", "h2d_bytes_per_step": h2d * world_size, "d2h_bytes_per_step": d2h * world_size,
-                    "ms_per_step": e2e_ms, "api": "cz_world_step_host: pinned host arrays (full body state in, full body state out), 1 frame per call, 8-chunk H2D | pack+step+unpack | D2H pipeline, 3 compute streams"},
+                    "ms_per_step": e2e_ms, "api": "cz_world_step_host: pinned host arrays (full body state in, full body state out), 1 frame per call, 6-chunk H2D | pack+step+unpack | D2H pipeline, 3 compute streams"},
             "e2e_rl": e2e_rl,
             "gpu_launches": int(red["counters"]["launches"]),
             "clocks": sampler.summary(),

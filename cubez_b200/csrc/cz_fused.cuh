@@ -129,9 +129,10 @@ static inline bool plan(FusedPlan &fp, int B, int P, int Cc, int nchk, int sched
     fp.smemBytes = smem;
     fp.keepContacts = env_int("CUBEZ_FUSED_KEEP_CONTACTS", 1);
     fp.bodyMasks = env_int("CUBEZ_FUSED_BODY_MASKS", 1);
-    // Large batches run one launch per phase of the frame (every warp of the GPU is then in the same
-    // code region: +15 % on 65 536 worlds); small batches keep the single persistent launch.
-    fp.split = env_int("CUBEZ_FUSED_SPLIT", W >= 8192 ? 1 : 0);
+    // Large batches run one launch per phase of the frame (every warp of the GPU is then in the same code region and
+    // each phase stages a short record: 3 CTAs per SM); small batches keep the single persistent launch.  Measured
+    // crossover on B200 (tools/split_threshold_probe.py): 16 384 worlds 887 vs 916 us per frame, 24 576 worlds 1 228 vs 1 070.
+    fp.split = env_int("CUBEZ_FUSED_SPLIT", W >= 20480 ? 1 : 0);
     fp.splitMinb = env_int("CUBEZ_FUSED_SPLIT_MINB", 3);
     if (fp.splitMinb < 2 || fp.splitMinb > 4 || G != 8) fp.splitMinb = 2;   // instantiated for G = 8 only
     fp.phaseAMinb = env_int("CUBEZ_FUSED_PHASE_A_MINB", 3);

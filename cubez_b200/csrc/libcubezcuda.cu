@@ -992,7 +992,7 @@ static int host_pipe_init(cz_world *w) {
     auto &pp = w->pipe;
     if (pp.ready) return CZ_OK;
     const long long NB = w->b.n;
-    int chunks = czf::env_int("CUBEZ_HOST_CHUNKS", 8);
+    int chunks = czf::env_int("CUBEZ_HOST_CHUNKS", 6);
     if (!w->useFused) chunks = 1;
     if (chunks > w->d.n_worlds) chunks = w->d.n_worlds;
     if (chunks < 1) chunks = 1;

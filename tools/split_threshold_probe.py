@@ -5,7 +5,7 @@ sys.path.insert(0, ROOT)
 import numpy as np
 from cubez_b200 import scenes
 from cubez_b200.api import BatchedWorld
-for W in (512, 1024, 2048, 4096, 8192):
+for W in [int(a) for a in sys.argv[1:]] or (512, 1024, 2048, 4096, 8192):
     sc = scenes.batched_cubedrop(n_worlds=W)
     ph = (np.arange(W) % 600).astype(np.int32)
     res = []
