@@ -260,3 +260,44 @@ def test_cost_ordered_scheduling_is_result_neutral(monkeypatch):
     assert res[0][0] == res[1][0] and res[0][1] == res[1][1]
     for a, b in zip(res[0][2], res[1][2]):
         assert np.array_equal(a, b)
+
+
+def test_contact_capacity_exact_fit_and_one_short():
+    """Edge of the capacity contract: a capacity equal to the largest contact count of the run works (and gives the
+    golden trajectory); one slot less is CZ_ERR_CAPACITY, never a silent truncation (it would change 8*len)."""
+    from cubez_b200._abi import CubezError
+    gold = load_golden("cubedrop_f64")
+    peak = int(gold["counts"].max())
+    scene = scenes.cubedrop()
+    for path in ("multi", "fused8"):
+        w = make_world(scene, path, contacts_per_world=peak)
+        check_against_golden(w, scene, gold, CASES["cubedrop_f64"][1], he.pair_hash)
+        w.close()
+        w = make_world(scene, path, contacts_per_world=peak - 1)
+        with pytest.raises(CubezError) as e:
+            w.step(scene.dt, CASES["cubedrop_f64"][1])
+        assert e.value.code == _abi.CZ_ERR_CAPACITY
+        w.close()
+
+
+def test_full_size_batch_equals_the_sum_of_its_parts():
+    """BASELINE cfg4 at full size (65 536 worlds, split-phase launches) against the same worlds stepped as four
+    batches of 16 384 (persistent kernel): worlds are independent, so checksums (sum mod 2^64) and counters add up."""
+    from cubez_b200.api import BatchedWorld
+    W, parts, frames = 65536, 4, 130
+    def run(first, n):
+        sc = scenes.batched_cubedrop(n_worlds=n, first_world=first)
+        w = BatchedWorld.from_scene(sc, contacts_per_world=64)
+        w.set_episodes(600, ((first + np.arange(n)) % 600).astype(np.int32))
+        st = w.step(sc.dt, frames)
+        out = (w.checksum_energy()[0], st["contacts"], st["pos_iterations"], st["vel_iterations"])
+        w.close()
+        return out
+    whole = run(0, W)
+    acc = [0, 0, 0, 0]
+    for k in range(parts):
+        r = run(k * (W // parts), W // parts)
+        acc = [a + b for a, b in zip(acc, r)]
+    acc[0] &= (1 << 64) - 1
+    assert whole[1] > 0 and whole[3] > 0
+    assert tuple(acc) == whole
