@@ -104,6 +104,15 @@ static inline bool plan(FusedPlan &fp, int B, int P, int Cc, int nchk, int sched
     int G = B <= 8 ? 8 : (B <= 16 ? 16 : 32);
     int g = env_int("CUBEZ_FUSED_G", 0);
     if (g == 8 || g == 16 || g == 32) G = g;
+    else {
+        // Small batches do not fill the GPU with 8 lanes per world: a frame is then one world's serial chain (~0.4 ms),
+        // and wider groups shorten its parallel parts.  Measured on B200, 8-body worlds, us per frame at G = 8 / 16 / 32:
+        // 1 024 worlds 389 / 278 / 272, 2 048: 402 / 318 / 314, 4 096: 455 / 376 / 511, 6 144: 478 / 527 / 707
+        // (tools/split_threshold_probe.py) -> the widest group while the batch is within about two waves of it.
+        const long long r32 = (long long)smCount * 2 * 4, r16 = (long long)smCount * 2 * 8;   // resident worlds at 2 CTAs of 128 threads per SM
+        if ((long long)W * 4 <= r32 * 7) G = 32;
+        else if (G < 16 && (long long)W * 5 <= r16 * 11) G = 16;
+    }
     int threads = env_int("CUBEZ_FUSED_THREADS", 128);
     if (threads != 32 && threads != 64 && threads != 128) threads = 128;
     int gpb = threads / G;
