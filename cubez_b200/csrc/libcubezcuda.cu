@@ -16,6 +16,104 @@
 #include <cstring>
 #include <string>
 #include <vector>
+#include <map>
+#include <mutex>
+#include <unordered_map>
+#include <cuda_runtime.h>
+
+// ------------------------------------------------------------------------------------------
+// Small-block device memory cache.  The object-API shims (cz_integrate, cz_narrowphase,
+// cz_resolve_contacts: one call per RigidBody.Integrate / CheckForCollisions / ResolveContacts of a
+// drop-in caller) build a scratch batch or a one-world handle per call: ~30 cudaMalloc/cudaFree pairs
+// of a few KB each, which dominated the call.  Blocks of up to 1 MiB are kept per (device, size class)
+// after their release and handed out again; larger blocks go straight to the runtime.  A release keeps
+// cudaFree's contract (the device is idle when the block becomes reusable).
+// ------------------------------------------------------------------------------------------
+namespace czp {
+static std::mutex g_mu;
+static std::unordered_map<void *, std::pair<int, size_t>> g_live;          // block -> (device, size class)
+static std::map<std::pair<int, size_t>, std::vector<void *>> g_free;
+static size_t g_cached = 0;
+constexpr size_t kSmall = 1u << 20, kMaxCached = 256u << 20;
+static inline cudaError_t pool_malloc(void **p, size_t bytes) {
+    if (bytes > kSmall) return ::cudaMalloc(p, bytes);
+    size_t cls = 256;
+    while (cls < bytes) cls <<= 1;
+    int dev = 0;
+    ::cudaGetDevice(&dev);
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        auto it = g_free.find({dev, cls});
+        if (it != g_free.end() && !it->second.empty()) {
+            *p = it->second.back();
+            it->second.pop_back();
+            g_cached -= cls;
+            g_live[*p] = {dev, cls};
+            return cudaSuccess;
+        }
+    }
+    cudaError_t e = ::cudaMalloc(p, cls);
+    if (e == cudaSuccess) { std::lock_guard<std::mutex> lk(g_mu); g_live[*p] = {dev, cls}; }
+    return e;
+}
+static inline cudaError_t pool_free(void *p) {
+    if (!p) return cudaSuccess;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        auto it = g_live.find(p);
+        if (it != g_live.end() && g_cached + it->second.second <= kMaxCached) {
+            const std::pair<int, size_t> key = it->second;
+            g_live.erase(it);
+            ::cudaDeviceSynchronize();   // as cudaFree: nothing in flight may still use the block
+            g_free[key].push_back(p);
+            g_cached += key.second;
+            return cudaSuccess;
+        }
+        if (it != g_live.end()) g_live.erase(it);
+    }
+    return ::cudaFree(p);
+}
+template <class T> static inline cudaError_t pool_malloc_t(T **p, size_t bytes) { return pool_malloc((void **)p, bytes); }
+// page-locked host blocks of up to 64 KiB (the per-world status mirror): cudaHostAlloc / cudaFreeHost cost ~0.5 ms each
+static std::unordered_map<void *, size_t> g_hostLive;
+static std::map<size_t, std::vector<void *>> g_hostFree;
+static inline cudaError_t pool_host_alloc(void **p, size_t bytes, unsigned flags) {
+    if (bytes > (64u << 10) || flags != cudaHostAllocDefault) return ::cudaHostAlloc(p, bytes, flags);
+    size_t cls = 256;
+    while (cls < bytes) cls <<= 1;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        auto it = g_hostFree.find(cls);
+        if (it != g_hostFree.end() && !it->second.empty()) {
+            *p = it->second.back();
+            it->second.pop_back();
+            g_hostLive[*p] = cls;
+            return cudaSuccess;
+        }
+    }
+    cudaError_t e = ::cudaHostAlloc(p, cls, flags);
+    if (e == cudaSuccess) { std::lock_guard<std::mutex> lk(g_mu); g_hostLive[*p] = cls; }
+    return e;
+}
+static inline cudaError_t pool_host_free(void *p) {
+    if (!p) return cudaSuccess;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        auto it = g_hostLive.find(p);
+        if (it != g_hostLive.end()) {
+            const size_t cls = it->second;
+            g_hostLive.erase(it);
+            if (g_hostFree[cls].size() < 64) { ::cudaDeviceSynchronize(); g_hostFree[cls].push_back(p); return cudaSuccess; }
+        }
+    }
+    return ::cudaFreeHost(p);
+}
+template <class T> static inline cudaError_t pool_host_alloc_t(T **p, size_t bytes, unsigned flags) { return pool_host_alloc((void **)p, bytes, flags); }
+}  // namespace czp
+#define cudaMalloc(p, n) czp::pool_malloc_t((p), (size_t)(n))
+#define cudaFree(p) czp::pool_free((void *)(p))
+#define cudaHostAlloc(p, n, f) czp::pool_host_alloc_t((p), (size_t)(n), (f))
+#define cudaFreeHost(p) czp::pool_host_free((void *)(p))
 
 #include "cz_kernels.cuh"
 #include "cz_fused.cuh"
