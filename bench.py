@@ -249,11 +249,11 @@ def main():
     roofline = {"bound": "hbm", "kernel": "k_world_fused, split mode: phases A | B | C, one launch each per frame",
                 "achieved": fused_bytes / (frame_ms * 1e-3) / 1e9, "peak": peak,
                 "unit": "GB/s", "frac": fused_bytes / (frame_ms * 1e-3) / 1e9 / peak,
-                "traffic": 1.979e9,   # dram__bytes_read+write of the three launches of one frame, ncu --set full (profiles/r01_fused_split_phases_v4.txt)
+                "traffic": 1.979e9,   # dram__bytes_read+write of the three launches of one frame, ncu --set full (profiles/r01_fused_split_phases_v5.txt)
                 "algorithmic_bytes_per_frame": fused_bytes, "peak_kind": peak_kind,
                 "note": "not HBM-bound by design: a frame's working state is shared-memory resident inside each launch; the kernels are bound by FP64 dependency latency and L2 latency of the cold contact records at 12 warps per SM (see profiles/)",
-                # what does bound it, from ncu --set full of one frame at 65 536 worlds (profiles/r01_fused_split_phases_v4.txt):
-                "ncu": {"phases_ms": {"A integrate+narrowphase+prepare": 0.641, "B position loop": 0.383, "C velocity loop": 1.034},
+                # what does bound it, from ncu --set full of one frame at 65 536 worlds (profiles/r01_fused_split_phases_v5.txt):
+                "ncu": {"phases_ms": {"A integrate+narrowphase+prepare": 0.642, "B position loop": 0.382, "C velocity loop": 1.014},
                         "fp64_pipe_active_pct": {"A": 21.6, "B": 14.8, "C": 31.6}, "issue_active_pct": {"A": 34.4, "B": 28.4, "C": 39.0},
                         "active_lanes_of_32": {"A": 16.3, "B": 18.4, "C": 20.0}, "warps_per_sm": 12, "registers_per_thread": 168,
                         "top_stalls": ["long_scoreboard (cold contact records and staged state in L2)", "wait (fixed-latency FP64 dependency at 3 warps per scheduler)"]}}
