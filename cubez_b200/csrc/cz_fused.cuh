@@ -75,11 +75,14 @@ static inline size_t world_bytes(int B, int Cc, int nchk) {
     return (bytes + 15) / 16 * 16;
 }
 
-// world record of the loop phases: body work record, hot contact fields, body masks, contact ids, flags, match list
-static inline size_t world_bytes_loops(int B, int Cc) {
-    size_t reals = (size_t)czr::BW_NF * B + 2 * (size_t)Cc + (size_t)B;
-    size_t ints = 2 * (size_t)Cc + 2 * (size_t)B;
-    size_t bytes = reals * sizeof(real) + ints * sizeof(int) + (size_t)Cc;
+// world record of a loop-phase launch: body work record, the phase's ONE hot contact field (penetration for the
+// position loop, desired delta-v for the velocity loop), body masks, contact body ids; the match list only when
+// the masks are off.  2.8 KB for an 8-body world with 64 contacts: three CTAs need 138 KB of shared memory, which
+// leaves the SM a 92 KB L1 for the cold contact records (164 KB carve-out instead of 196 KB).
+static inline size_t world_bytes_loops(int B, int Cc, bool masks) {
+    size_t reals = (size_t)czr::BW_NF * B + (((size_t)Cc + 1) & ~(size_t)1) + (size_t)B;   // hot field padded to an even count: the 64-bit masks follow it
+    size_t ints = 2 * (size_t)Cc;
+    size_t bytes = reals * sizeof(real) + sizeof(real) + ints * sizeof(int) + (masks ? 0 : (size_t)Cc);
     return (bytes + 15) / 16 * 16;
 }
 
@@ -146,7 +149,7 @@ static inline bool plan(FusedPlan &fp, int B, int P, int Cc, int nchk, int sched
     if (fp.splitMinb < 2 || fp.splitMinb > 4 || G != 8) fp.splitMinb = 2;   // instantiated for G = 8 only
     fp.phaseAMinb = env_int("CUBEZ_FUSED_PHASE_A_MINB", 3);
     if (fp.phaseAMinb < 2 || fp.phaseAMinb > 4 || G != 8) fp.phaseAMinb = 2;
-    fp.loopWorldBytes = world_bytes_loops(B, Cc);
+    fp.loopWorldBytes = world_bytes_loops(B, Cc, Cc <= 64 && fp.bodyMasks);
     fp.loopSmemBytes = fp.loopWorldBytes * gpb;
     {
         int lb = (int)(perSM / (fp.loopSmemBytes + 1024));
@@ -282,8 +285,10 @@ __device__ __forceinline__ void stage_world(const Staged &s, const BodyStore &st
         }
         s.fb[BW_INVM * B + b] = st.ld(czb::C_MD, gi).x;
         s.fb[BW_AWAKE * B + b] = st.awake[gi] ? R_(1) : R_(0);
-        s.flags[b] = (int)st.shape[gi] | (st.can_sleep[gi] ? FF_CANSLEEP : 0) | (st.integ[gi] ? FF_INTEG : 0) | (st.ident[gi] ? FF_IDENT : 0);
-        s.active[b] = st.active_from[gi];
+        if (FULL) {
+            s.flags[b] = (int)st.shape[gi] | (st.can_sleep[gi] ? FF_CANSLEEP : 0) | (st.integ[gi] ? FF_INTEG : 0) | (st.ident[gi] ? FF_IDENT : 0);
+            s.active[b] = st.active_from[gi];
+        }
     }
 }
 
@@ -315,14 +320,14 @@ __global__ void __launch_bounds__(128, MINB) k_world_fused(WorldParams p, FusedP
     s.fb = (real *)base; s.bs = B;
     const int ch = A_ONLY ? 0 : Cc;   // hot contact fields held in shared memory
     s.pen = s.fb + (size_t)(FULL ? (int)FB_NF : (int)BW_NF) * B;
-    s.ddv = s.pen + ch;
-    unsigned long long *const bmask = (unsigned long long *)(s.ddv + ch);   // [B]
+    s.ddv = FULL ? s.pen + ch : s.pen;   // a loop-phase launch holds one hot field: B scans pen, C scans ddv
+    unsigned long long *const bmask = (unsigned long long *)(s.ddv + (FULL ? ch : ((ch + 1) & ~1)));   // [B]
     s.cb0 = (int *)(bmask + (A_ONLY ? 0 : B));
     s.cb1 = s.cb0 + ch;
-    s.flags = s.cb1 + ch;
-    s.active = s.flags + B;
+    s.flags = s.cb1 + ch;                // flags, activation and the check queues exist only where phase A runs
+    s.active = s.flags + (FULL ? B : 0);
     const int nq = FULL ? p.nchk : 0;
-    s.info = (unsigned short *)(s.active + B);
+    s.info = (unsigned short *)(s.active + (FULL ? B : 0));
     s.queue = s.info + nq;
     s.pbase = s.queue + nq;
     s.cnt = (unsigned char *)(s.pbase + nq);
@@ -338,7 +343,7 @@ __global__ void __launch_bounds__(128, MINB) k_world_fused(WorldParams p, FusedP
     x.cold = s.cold; x.cfs = 1; x.ccs = CW_NCOLD;       // AoS
     x.pen = s.pen; x.ddv = s.ddv; x.fric = nullptr; x.rest = nullptr;
     x.cb0 = s.cb0; x.cb1 = s.cb1; x.nC = 0; x.dt = dt;
-    x.mlist = (Cc <= 256 && !A_ONLY) ? mlist : nullptr;                      // the loops' scratch: absent from the phase-A record
+    x.mlist = (Cc <= 256 && !A_ONLY && (FULL || !(Cc <= 64 && fp.bodyMasks))) ? mlist : nullptr;   // the loops' scratch: absent from the phase-A record, and from a loop record that has masks
     x.bmask = (Cc <= 64 && fp.bodyMasks && !A_ONLY) ? bmask : nullptr;
     x.xb = nullptr; x.xbs = 0; x.store = st;
     GenView gv;
