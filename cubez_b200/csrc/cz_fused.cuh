@@ -67,11 +67,14 @@ struct FusedPlan {
     int *hotCb0, *hotCb1;    // [W][Cc]
 };
 
+// Every size below is in BYTES and mirrors the carve at the top of k_world_fused field by field.  The per-body contact
+// masks are 64-bit whatever `real` is (the float32 build once sized them as one real per body and overran the record).
 static inline size_t world_bytes(int B, int Cc, int nchk) {
-    size_t reals = (size_t)FB_NF * B + 2 * (size_t)Cc + (size_t)B;   // + one 64-bit contact mask per body
-    size_t ints = 2 * (size_t)Cc + 2 * (size_t)B;
-    size_t shorts = 3 * (size_t)nchk;          // per-check info + the queues of checks that need a full test + plane-check base slots
-    size_t bytes = reals * sizeof(real) + ints * sizeof(int) + shorts * sizeof(unsigned short) + 2 * (size_t)nchk + (size_t)Cc;
+    size_t bytes = ((size_t)FB_NF * B + 2 * (size_t)Cc) * sizeof(real);   // body + collider record, penetration, desired delta-v
+    bytes += (size_t)B * sizeof(unsigned long long);                          // one 64-bit contact mask per body
+    bytes += (2 * (size_t)Cc + 2 * (size_t)B) * sizeof(int);                  // contact body ids, flags, activation
+    bytes += 3 * (size_t)nchk * sizeof(unsigned short);                       // per-check info + the queues of checks that need a full test + plane-check base slots
+    bytes += 2 * (size_t)nchk + (size_t)Cc;                                   // per-check counts, vertex masks, the match list
     return (bytes + 15) / 16 * 16;
 }
 
@@ -80,9 +83,9 @@ static inline size_t world_bytes(int B, int Cc, int nchk) {
 // the masks are off.  2.8 KB for an 8-body world with 64 contacts: three CTAs need 138 KB of shared memory, which
 // leaves the SM a 92 KB L1 for the cold contact records (164 KB carve-out instead of 196 KB).
 static inline size_t world_bytes_loops(int B, int Cc, bool masks) {
-    size_t reals = (size_t)czr::BW_NF * B + (((size_t)Cc + 1) & ~(size_t)1) + (size_t)B;   // hot field padded to an even count: the 64-bit masks follow it
-    size_t ints = 2 * (size_t)Cc;
-    size_t bytes = reals * sizeof(real) + sizeof(real) + ints * sizeof(int) + (masks ? 0 : (size_t)Cc);
+    size_t bytes = ((size_t)czr::BW_NF * B + (((size_t)Cc + 1) & ~(size_t)1)) * sizeof(real);   // hot field padded to an even count: the 64-bit masks follow it
+    bytes += (size_t)B * sizeof(unsigned long long);
+    bytes += 2 * (size_t)Cc * sizeof(int) + (masks ? 0 : (size_t)Cc);
     return (bytes + 15) / 16 * 16;
 }
 
@@ -90,6 +93,23 @@ static inline size_t world_bytes_loops(int B, int Cc, bool masks) {
 static inline size_t world_bytes_phase_a(int B, int nchk) {
     size_t bytes = (size_t)FB_NF * B * sizeof(real) + 2 * (size_t)B * sizeof(int) + 3 * (size_t)nchk * sizeof(unsigned short) + 2 * (size_t)nchk;
     return (bytes + 15) / 16 * 16;
+}
+
+// End offset (bytes) of the shared-memory carve k_world_fused performs for one world, computed with the kernel's own
+// pointer arithmetic: mode 0 = full record (PH_ALL), 1 = phase A only, 2 = a loop phase.  plan() refuses a shape whose
+// carve would run past the record the helpers above size (a host-side guard for the two to stay in step).
+static inline size_t carve_end(int B, int Cc, int nchk, int mode, bool masks) {
+    const bool full = mode != 2, aOnly = mode == 1;
+    const size_t ch = aOnly ? 0 : (size_t)Cc;
+    size_t off = (size_t)(full ? (int)FB_NF : (int)czr::BW_NF) * B * sizeof(real);   // s.pen
+    off += (full ? 2 * ch : ((ch + 1) & ~(size_t)1)) * sizeof(real);                   // bmask
+    off += (aOnly ? 0 : (size_t)B) * sizeof(unsigned long long);                       // s.cb0
+    off += 2 * ch * sizeof(int);                                                       // s.flags
+    off += (full ? 2 * (size_t)B : 0) * sizeof(int);                                   // s.info
+    const size_t nq = full ? (size_t)nchk : 0;
+    off += 3 * nq * sizeof(unsigned short) + 2 * nq;                                   // mlist
+    const bool hasMlist = Cc <= 256 && !aOnly && (full || !masks);
+    return off + (hasMlist ? (size_t)Cc : 0);
 }
 
 static inline int env_int(const char *name, int dflt) {
@@ -174,6 +194,12 @@ static inline bool plan(FusedPlan &fp, int B, int P, int Cc, int nchk, int sched
     fp.lockstep = env_int("CUBEZ_FUSED_LOCKSTEP", 3);   // 0 none, 1 frame start, 2 + before narrowphase/resolve, 3 + between the two loops
     fp.coldReals = (size_t)Cc * czr::CW_NCOLD + (size_t)nchk * 8;   // + staging of pair-test contacts
     fp.cold = nullptr;
+    const bool lm = Cc <= 64 && fp.bodyMasks;
+    if (carve_end(B, Cc, nchk, 0, lm) > fp.worldBytes || carve_end(B, Cc, nchk, 1, lm) > fp.phaseAWorldBytes ||
+        carve_end(B, Cc, nchk, 2, lm) > fp.loopWorldBytes) {
+        fprintf(stderr, "libcubezcuda: fused shared-memory carve exceeds its record (B %d Cc %d nchk %d) — not using the fused kernel\n", B, Cc, nchk);
+        return false;
+    }
     return true;
 }
 

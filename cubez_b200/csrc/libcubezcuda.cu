@@ -58,20 +58,41 @@ static inline cudaError_t pool_malloc(void **p, size_t bytes) {
 }
 static inline cudaError_t pool_free(void *p) {
     if (!p) return cudaSuccess;
+    std::pair<int, size_t> key{0, 0};
+    bool cache = false;
     {
         std::lock_guard<std::mutex> lk(g_mu);
         auto it = g_live.find(p);
-        if (it != g_live.end() && g_cached + it->second.second <= kMaxCached) {
-            const std::pair<int, size_t> key = it->second;
+        if (it != g_live.end()) {
+            key = it->second;
+            cache = g_cached + key.second <= kMaxCached;
             g_live.erase(it);
-            ::cudaDeviceSynchronize();   // as cudaFree: nothing in flight may still use the block
-            g_free[key].push_back(p);
-            g_cached += key.second;
-            return cudaSuccess;
+            if (cache) g_cached += key.second;   // reserved now, published below
         }
-        if (it != g_live.end()) g_live.erase(it);
     }
-    return ::cudaFree(p);
+    if (!cache) return ::cudaFree(p);
+    // as cudaFree: nothing in flight on the block's OWN device may still use it.  The wait happens outside the lock.
+    int cur = 0;
+    ::cudaGetDevice(&cur);
+    if (cur != key.first) ::cudaSetDevice(key.first);
+    ::cudaDeviceSynchronize();
+    if (cur != key.first) ::cudaSetDevice(cur);
+    std::lock_guard<std::mutex> lk(g_mu);
+    g_free[key].push_back(p);
+    return cudaSuccess;
+}
+// release every cached block of one device (cz_shutdown)
+static inline void pool_trim(int device) {
+    std::vector<void *> blocks;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        for (auto &kv : g_free) {
+            if (kv.first.first != device) continue;
+            for (void *q : kv.second) { blocks.push_back(q); g_cached -= kv.first.second; }
+            kv.second.clear();
+        }
+    }
+    for (void *q : blocks) ::cudaFree(q);
 }
 template <class T> static inline cudaError_t pool_malloc_t(T **p, size_t bytes) { return pool_malloc((void **)p, bytes); }
 // page-locked host blocks of up to 64 KiB (the per-world status mirror): cudaHostAlloc / cudaFreeHost cost ~0.5 ms each
@@ -421,9 +442,31 @@ static inline const int *phase_order(cz_world *w, int ph) {
     return w->order3 + (size_t)(ph == czf::PH_A ? 0 : (ph == czf::PH_B ? 1 : 2)) * w->d.n_worlds;
 }
 
+template <class T> static inline void free_and_null(T *&p) { if (p) { cudaFree(p); p = nullptr; } }
+
+// The chunk pipeline of cz_world_step_host / cz_world_step_rl is sized from the fused plan (cold scratch per compute
+// stream, chunk count, compute streams).  A re-plan (planes or schedule uploaded later) invalidates it: it is torn
+// down here and rebuilt from the current plan by the next host step.
+static void host_pipe_destroy(cz_world *w) {
+    auto &pp = w->pipe;
+    if (!pp.ready) return;
+    cudaStreamSynchronize(w->ctx->stream);
+    cudaStreamSynchronize(pp.sUp); cudaStreamSynchronize(pp.sDown);
+    for (int k = 0; k < pp.nComp; k++) if (pp.sComp[k]) cudaStreamSynchronize(pp.sComp[k]);
+    cudaStreamDestroy(pp.sUp); cudaStreamDestroy(pp.sDown);
+    for (int k = 0; k < pp.nComp; k++) if (pp.sComp[k] && pp.sComp[k] != w->ctx->stream) cudaStreamDestroy(pp.sComp[k]);
+    for (auto e : pp.evUp) cudaEventDestroy(e);
+    for (auto e : pp.evComp) cudaEventDestroy(e);
+    cudaEventDestroy(pp.evBegin); cudaEventDestroy(pp.evDownDone);
+    cudaFree(pp.dIn); cudaFree(pp.dOut); cudaFree(pp.dFlags); cudaFree(pp.dNext);
+    for (int k = 1; k < 16; k++) if (pp.coldX[k]) cudaFree(pp.coldX[k]);
+    pp = cz_world::HostPipe();
+}
+
 // (Re)derive everything that depends on the schedule size / capacities.
 static int world_plan(cz_world *w) {
     cz_ctx *ctx = w->ctx;
+    host_pipe_destroy(w);
     const int B = w->d.bodies_per_world, Cc = w->d.contacts_per_world, W = w->d.n_worlds;
     if (w->d.schedule == CZ_SCHED_ALL_PAIRS_ORDERED) w->nchk = B * (w->P + B);
     // narrowphase tiling
@@ -469,9 +512,9 @@ static int world_plan(cz_world *w) {
     // fused small-world kernel
     w->useFused = false;
     if (!(w->d.flags & CZ_WORLD_NO_FUSED)) {
-        if (w->fused.cold) { cudaFree(w->fused.cold); w->fused.cold = nullptr; }
-        { void *sp[] = {w->fused.coldW, w->fused.hotPen, w->fused.hotDdv, w->fused.hotCb0, w->fused.hotCb1};
-          for (void *q : sp) if (q) cudaFree(q); }
+        free_and_null(w->fused.cold);
+        free_and_null(w->fused.coldW); free_and_null(w->fused.hotPen); free_and_null(w->fused.hotDdv);
+        free_and_null(w->fused.hotCb0); free_and_null(w->fused.hotCb1);
         w->useFused = !w->useBP && czf::plan(w->fused, B, w->P, Cc, w->nchk, w->d.schedule, ctx->smem_optin, ctx->sm_count, W);
         if (w->useFused) {
             CK(ctx, cudaMalloc(&w->fused.cold, sizeof(real) * w->fused.coldReals * (size_t)w->fused.maxGrid * w->fused.groupsPerBlock));
@@ -490,6 +533,8 @@ static int world_plan(cz_world *w) {
     }
     return CZ_OK;
 }
+
+static int take_status(cz_world *w);
 
 extern "C" {
 
@@ -526,6 +571,7 @@ int cz_shutdown(cz_ctx *ctx) {
     cudaEventDestroy(ctx->ev0);
     cudaEventDestroy(ctx->ev1);
     cudaStreamDestroy(ctx->stream);
+    czp::pool_trim(ctx->device);
     delete ctx;
     return CZ_OK;
 }
@@ -560,19 +606,23 @@ int cz_world_create(cz_ctx *ctx, const cz_world_desc *desc, cz_world **out) {
     const long long NB = (long long)desc->n_worlds * desc->bodies_per_world;
     const size_t NC = (size_t)desc->n_worlds * desc->contacts_per_world;
     int rc = batch_alloc(ctx, w->b, NB);
-    if (rc) { delete w; return rc; }
-    CK(ctx, cudaMalloc(&w->gen, sizeof(real) * czr::G_NF * NC));
-    CK(ctx, cudaMalloc(&w->gb0, sizeof(int) * NC));
-    CK(ctx, cudaMalloc(&w->gb1, sizeof(int) * NC));
-    CK(ctx, cudaMalloc(&w->nContacts, sizeof(int) * desc->n_worlds));
-    CK(ctx, cudaMalloc(&w->posIters, sizeof(int) * desc->n_worlds));
-    CK(ctx, cudaMalloc(&w->velIters, sizeof(int) * desc->n_worlds));
-    CK(ctx, cudaMemsetAsync(w->nContacts, 0, sizeof(int) * desc->n_worlds, ctx->stream));
-    CK(ctx, cudaMemsetAsync(w->posIters, 0, sizeof(int) * desc->n_worlds, ctx->stream));
-    CK(ctx, cudaMemsetAsync(w->velIters, 0, sizeof(int) * desc->n_worlds, ctx->stream));
-    CK(ctx, cudaMalloc(&w->stats, sizeof(unsigned long long) * ST_N));
-    CK(ctx, cudaMemsetAsync(w->stats, 0, sizeof(unsigned long long) * ST_N, ctx->stream));
-    CK(ctx, cudaHostAlloc(&w->h_stats, sizeof(unsigned long long) * ST_N, cudaHostAllocDefault));
+    if (rc) { cz_world_destroy(w); return rc; }
+    auto alloc_all = [&]() -> int {
+        CK(ctx, cudaMalloc(&w->gen, sizeof(real) * czr::G_NF * NC));
+        CK(ctx, cudaMalloc(&w->gb0, sizeof(int) * NC));
+        CK(ctx, cudaMalloc(&w->gb1, sizeof(int) * NC));
+        CK(ctx, cudaMalloc(&w->nContacts, sizeof(int) * desc->n_worlds));
+        CK(ctx, cudaMalloc(&w->posIters, sizeof(int) * desc->n_worlds));
+        CK(ctx, cudaMalloc(&w->velIters, sizeof(int) * desc->n_worlds));
+        CK(ctx, cudaMemsetAsync(w->nContacts, 0, sizeof(int) * desc->n_worlds, ctx->stream));
+        CK(ctx, cudaMemsetAsync(w->posIters, 0, sizeof(int) * desc->n_worlds, ctx->stream));
+        CK(ctx, cudaMemsetAsync(w->velIters, 0, sizeof(int) * desc->n_worlds, ctx->stream));
+        CK(ctx, cudaMalloc(&w->stats, sizeof(unsigned long long) * ST_N));
+        CK(ctx, cudaMemsetAsync(w->stats, 0, sizeof(unsigned long long) * ST_N, ctx->stream));
+        CK(ctx, cudaHostAlloc(&w->h_stats, sizeof(unsigned long long) * ST_N, cudaHostAllocDefault));
+        return CZ_OK;
+    };
+    if ((rc = alloc_all())) { cz_world_destroy(w); return rc; }   // no leak on a failed allocation
     for (int i = 0; i < CZ_MAX_PLANES; i++) { w->planes[i].n = czm::mk3(0, 1, 0); w->planes[i].offset = 0; }
     rc = world_plan(w);
     if (rc) { cz_world_destroy(w); return rc; }
@@ -593,13 +643,7 @@ int cz_world_destroy(cz_world *w) {
     for (void *p : ptrs) if (p) cudaFree(p);
     if (w->h_stats) cudaFreeHost(w->h_stats);
     if (w->h_pin) cudaFreeHost(w->h_pin);
-    if (w->pipe.ready) {
-        cudaStreamDestroy(w->pipe.sUp); cudaStreamDestroy(w->pipe.sDown); for (int k = 0; k < w->pipe.nComp; k++) if (w->pipe.sComp[k] != w->ctx->stream) cudaStreamDestroy(w->pipe.sComp[k]);
-        for (auto e : w->pipe.evUp) cudaEventDestroy(e);
-        for (auto e : w->pipe.evComp) cudaEventDestroy(e);
-        cudaEventDestroy(w->pipe.evBegin); cudaEventDestroy(w->pipe.evDownDone);
-        cudaFree(w->pipe.dIn); cudaFree(w->pipe.dOut); cudaFree(w->pipe.dFlags); cudaFree(w->pipe.dNext); for (int k = 1; k < 16; k++) if (w->pipe.coldX[k]) cudaFree(w->pipe.coldX[k]);
-    }
+    host_pipe_destroy(w);
     delete w;
     return CZ_OK;
 }
@@ -649,9 +693,11 @@ int cz_world_upload_schedule(cz_world *w, int32_t n_checks, const int32_t *one, 
     cz_ctx *ctx = w->ctx;
     CK(ctx, cudaSetDevice(ctx->device));
     if (w->d.schedule != CZ_SCHED_EXPLICIT) return fail(ctx, CZ_ERR_INVALID, "world was not created with CZ_SCHED_EXPLICIT");
+    if (n_checks > 0 && (!one || !two)) return fail(ctx, CZ_ERR_INVALID, "cz_world_upload_schedule: NULL check list");
     for (int i = 0; i < n_checks; i++) {
-        if (one[i] >= w->d.bodies_per_world || two[i] >= w->d.bodies_per_world || one[i] < -CZ_MAX_PLANES || two[i] < -CZ_MAX_PLANES)
-            return fail(ctx, CZ_ERR_INVALID, "schedule entry out of range");
+        // planes are named -(p+1) and must exist: upload the planes before the schedule
+        if (one[i] >= w->d.bodies_per_world || two[i] >= w->d.bodies_per_world || one[i] < -w->P || two[i] < -w->P)
+            return fail(ctx, CZ_ERR_INVALID, "schedule entry out of range (body id >= bodies_per_world, or a plane that was not uploaded)");
     }
     if (w->d_one) cudaFree(w->d_one);
     if (w->d_two) cudaFree(w->d_two);
@@ -760,7 +806,7 @@ int cz_world_synchronize(cz_world *w) {
     if (!w) return CZ_ERR_INVALID;
     CK(w->ctx, cudaSetDevice(w->ctx->device));
     CK(w->ctx, cudaStreamSynchronize(w->ctx->stream));
-    return CZ_OK;
+    return take_status(w);
 }
 
 }  // extern "C"
@@ -868,6 +914,25 @@ static int world_prepare_step(cz_world *w, real dt) {
     return CZ_OK;
 }
 
+static int status_error(cz_ctx *ctx, int status) {
+    if (status == CZ_ERR_CAPACITY) return fail(ctx, status, "contact capacity exceeded (contacts_per_world too small)");
+    if (status == CZ_ERR_NIL_BODY) return fail(ctx, status, "frictionless one-body contact: the reference dereferences a nil body (contact.go:512-523)");
+    if (status) return fail(ctx, status, "device-side error");
+    return CZ_OK;
+}
+// The device-side status (first error raised by any kernel since it was last observed) is STICKY: a step never clears
+// it, so errors raised by asynchronous steps (stats == NULL) are not lost.  Whoever observes it — a step with stats,
+// cz_world_synchronize, a download, the counters, the checksum — returns it and clears it.
+static int take_status(cz_world *w) {
+    cz_ctx *ctx = w->ctx;
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    CK(ctx, cudaMemcpy(&w->h_stats[ST_STATUS], w->stats + ST_STATUS, sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    const int status = -(int)w->h_stats[ST_STATUS];
+    if (!status) return CZ_OK;
+    CK(ctx, cudaMemset(w->stats + ST_STATUS, 0, sizeof(unsigned long long)));
+    return status_error(ctx, status);
+}
+
 static int read_stats(cz_world *w, cz_step_stats *stats, long long launches, int n_steps, float ms) {
     cz_ctx *ctx = w->ctx;
     CK(ctx, cudaMemcpyAsync(w->h_stats, w->stats, sizeof(unsigned long long) * ST_N, cudaMemcpyDeviceToHost, ctx->stream));
@@ -885,10 +950,8 @@ static int read_stats(cz_world *w, cz_step_stats *stats, long long launches, int
         stats->status = status;
         stats->device_ms = ms;
     }
-    if (status == CZ_ERR_CAPACITY) return fail(ctx, status, "contact capacity exceeded (contacts_per_world too small)");
-    if (status == CZ_ERR_NIL_BODY) return fail(ctx, status, "frictionless one-body contact: the reference dereferences a nil body (contact.go:512-523)");
-    if (status) return fail(ctx, status, "device-side error");
-    return CZ_OK;
+    if (status) CK(ctx, cudaMemsetAsync(w->stats + ST_STATUS, 0, sizeof(unsigned long long), ctx->stream));   // observed: cleared
+    return status_error(ctx, status);
 }
 
 extern "C" {
@@ -903,7 +966,7 @@ int cz_world_step(cz_world *w, cz_real dt, int32_t n_steps, cz_step_stats *stats
     if (rc) return rc;
     long long launches = 0;
     if (stats) {
-        CK(ctx, cudaMemsetAsync(w->stats, 0, sizeof(unsigned long long) * ST_N, ctx->stream));
+        CK(ctx, cudaMemsetAsync(w->stats, 0, sizeof(unsigned long long) * ST_STATUS, ctx->stream));
         CK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
     }
     if (w->useFused) {
@@ -948,6 +1011,7 @@ int cz_world_download_bodies(cz_world *w, int32_t first, int32_t n, cz_bodies *o
     if (rc) return rc;
     CK(w->ctx, cudaSetDevice(w->ctx->device));
     const long long B = w->d.bodies_per_world;
+    if ((rc = take_status(w))) return rc;   // an error raised by an asynchronous step surfaces here
     return download_bodies(w->b, first * B, n * B, out);
 }
 int cz_world_download_colliders(cz_world *w, int32_t first, int32_t n, cz_colliders *out) {
@@ -974,7 +1038,8 @@ int cz_world_download_contacts(cz_world *w, int32_t world, cz_contacts *out) {
     int nC = 0;
     CK(ctx, cudaStreamSynchronize(ctx->stream));
     CK(ctx, cudaMemcpy(&nC, w->nContacts + world, sizeof(int), cudaMemcpyDeviceToHost));
-    out->n = nC;
+    out->n = nC;   // reported even on CZ_ERR_CAPACITY: the caller learns the count it must make room for
+    if ((rc = take_status(w))) return rc;
     if (nC > out->capacity || nC > w->d.contacts_per_world) return fail(ctx, CZ_ERR_CAPACITY, "cz_world_download_contacts: capacity too small");
     if (nC == 0) return CZ_OK;
     const size_t Cc = w->d.contacts_per_world, gs = (size_t)w->d.n_worlds * Cc, off = (size_t)world * Cc;
@@ -1033,7 +1098,7 @@ int cz_world_last_step_counts(cz_world *w, int32_t *n_contacts, int32_t *pos_it,
     if (!w) return CZ_ERR_INVALID;
     cz_ctx *ctx = w->ctx;
     CK(ctx, cudaSetDevice(ctx->device));
-    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    { int rc = take_status(w); if (rc) return rc; }
     const size_t bytes = sizeof(int) * w->d.n_worlds;
     if (n_contacts) CK(ctx, cudaMemcpy(n_contacts, w->nContacts, bytes, cudaMemcpyDeviceToHost));
     if (pos_it) CK(ctx, cudaMemcpy(pos_it, w->posIters, bytes, cudaMemcpyDeviceToHost));
@@ -1044,6 +1109,7 @@ int cz_world_checksum_energy(cz_world *w, uint64_t *checksum, double *energy) {
     if (!w) return CZ_ERR_INVALID;
     cz_ctx *ctx = w->ctx;
     CK(ctx, cudaSetDevice(ctx->device));
+    { int rc = take_status(w); if (rc) return rc; }
     const int W = w->d.n_worlds;
     unsigned long long *dh = nullptr;
     double *de = nullptr;
@@ -1154,7 +1220,7 @@ int cz_world_step_host(cz_world *w, cz_bodies *io, cz_real dt, int32_t n_steps, 
     HostOut hout{oPos, oOri, oVel, oRot, oMot, oLacc, oTr, oIitw, fAwakeOut};
     static const bool hostTrace = getenv("CUBEZ_HOST_TRACE") != nullptr;
     const auto tc0 = std::chrono::steady_clock::now();
-    CK(ctx, cudaMemsetAsync(w->stats, 0, sizeof(unsigned long long) * ST_N, ctx->stream));
+    CK(ctx, cudaMemsetAsync(w->stats, 0, sizeof(unsigned long long) * ST_STATUS, ctx->stream));
     CK(ctx, cudaMemsetAsync(pp.dNext, 0, sizeof(unsigned int) * 4 * pp.chunks, ctx->stream));
     CK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
     CK(ctx, cudaEventRecord(pp.evBegin, ctx->stream));
@@ -1306,7 +1372,7 @@ int cz_world_step_rl(cz_world *w, const cz_real *add_velocity, const cz_real *ad
     }
     const bool anyOut = hout.pos || hout.ori || hout.vel || hout.rot || hout.motion || hout.lacc || hout.tr || hout.iitw || hout.awake;
     const bool anyIn = add_velocity || add_rotation;
-    CK(ctx, cudaMemsetAsync(w->stats, 0, sizeof(unsigned long long) * ST_N, ctx->stream));
+    CK(ctx, cudaMemsetAsync(w->stats, 0, sizeof(unsigned long long) * ST_STATUS, ctx->stream));
     CK(ctx, cudaMemsetAsync(pp.dNext, 0, sizeof(unsigned int) * 4 * pp.chunks, ctx->stream));
     CK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
     CK(ctx, cudaEventRecord(pp.evBegin, ctx->stream));
@@ -1502,6 +1568,13 @@ int cz_resolve_contacts(cz_ctx *ctx, int32_t max_iterations, cz_contacts *io, cz
     if (!ctx || !io || !bodies || bodies->n <= 0) return fail(ctx, CZ_ERR_INVALID, "cz_resolve_contacts: bad argument");
     if (iters) iters[0] = iters[1] = 0;
     if (!(dt > 0) || io->n <= 0) return CZ_OK;   // contact.go:210-212
+    if (!io->body0 || !io->body1 || !io->point || !io->normal || !io->penetration)
+        return fail(ctx, CZ_ERR_INVALID, "cz_resolve_contacts: body0, body1, point, normal and penetration must be given");
+    for (int i = 0; i < io->n; i++) {
+        const int a = io->body0[i], b = io->body1[i];
+        if (a >= bodies->n || b >= bodies->n || a < -1 || b < -1) return fail(ctx, CZ_ERR_INVALID, "cz_resolve_contacts: contact body index out of range");
+        if (a < 0 && b < 0) return fail(ctx, CZ_ERR_NIL_BODY, "cz_resolve_contacts: contact with two nil bodies (the reference dereferences nil, contact.go:66-70)");
+    }
     cz_world_desc d{1, bodies->n, io->n, CZ_SCHED_EXPLICIT, CZ_WORLD_NO_FUSED};
     cz_world *w = nullptr;
     int rc = cz_world_create(ctx, &d, &w);

@@ -221,6 +221,8 @@ int cz_world_upload_bodies(cz_world *w, int32_t first_world, int32_t n_worlds, c
 int cz_world_upload_colliders(cz_world *w, int32_t first_world, int32_t n_worlds, const cz_colliders *c,
                               int32_t derive);
 int cz_world_upload_planes(cz_world *w, const cz_planes *p);                      /* shared by all worlds */
+/* Explicit ordered check list: one[k]/two[k] >= 0 body (collider) index, < 0 plane -(p+1).  Planes must be uploaded
+ * first: an entry naming a plane that does not exist is CZ_ERR_INVALID. */
 int cz_world_upload_schedule(cz_world *w, int32_t n_checks, const int32_t *one, const int32_t *two);
 /* active_from[i]: body i takes part from this step index on; integrate[i] == 0: body is never
  * integrated (ballistic backboard, examples/ballistic.go:27-44).  NULL = all 0 / all 1. */
@@ -245,9 +247,14 @@ int cz_world_set_materials(cz_world *w, int32_t n_materials, const cz_real *fric
  * is at frame phase0[k] (0 <= phase0[k] < length) of its episode now and is restored to the
  * snapshot at the start of every frame on which its phase wraps to 0.  length <= 0 disables. */
 int cz_world_set_episodes(cz_world *w, int32_t length, const int32_t *phase0);
-/* n_steps frames of updateCallback (examples/cubedrop.go:69-75). Asynchronous unless stats != NULL. */
+/* n_steps frames of updateCallback (examples/cubedrop.go:69-75). Asynchronous unless stats != NULL.
+ * Device-side errors (CZ_ERR_CAPACITY, CZ_ERR_NIL_BODY) are STICKY: an asynchronous step cannot return them, so the
+ * first one raised stays recorded until a call observes it — a step with stats != NULL, cz_world_synchronize, any
+ * cz_world_download_*, cz_world_last_step_counts or cz_world_checksum_energy — which returns it and clears it.
+ * A world that overflowed its contact capacity skipped ResolveContacts for that frame: treat the error as fatal for
+ * the run and re-create the world with a larger contacts_per_world. */
 int cz_world_step(cz_world *w, cz_real dt, int32_t n_steps, cz_step_stats *stats);
-int cz_world_synchronize(cz_world *w);
+int cz_world_synchronize(cz_world *w); /* waits for the world's stream; returns (and clears) a pending device-side error */
 int cz_world_download_bodies(cz_world *w, int32_t first_world, int32_t n_worlds, cz_bodies *out);
 int cz_world_download_colliders(cz_world *w, int32_t first_world, int32_t n_worlds, cz_colliders *out);
 /* contacts of the last step of one world, as generated (before ResolveContacts), canonical order */

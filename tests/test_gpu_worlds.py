@@ -301,3 +301,70 @@ def test_full_size_batch_equals_the_sum_of_its_parts():
     acc[0] &= (1 << 64) - 1
     assert whole[1] > 0 and whole[3] > 0
     assert tuple(acc) == whole
+
+
+@pytest.mark.parametrize("split", ["0", "1"])
+def test_f32_fused_records_at_exact_capacity(split, monkeypatch):
+    """float32 build, persistent and split-phase launches, contact capacity EQUAL to the peak count: the per-body
+    contact masks are 64-bit whatever Real is, so the shared-memory record must be sized in bytes (an f32 record sized
+    in reals let a world within 4 contacts of capacity overwrite its neighbour in the CTA)."""
+    scene = scenes.batched_cubedrop(_abi.F32, n_worlds=80)
+    cpu = OracleWorld.from_scene(scene)
+    ref = [cpu.step(scene.dt, 20, n_threads=8) for _ in range(10)]
+    peak = max(r["max_contacts"] for r in ref)
+    monkeypatch.setenv("CUBEZ_FUSED_SPLIT", split)
+    gpu = make_world(scene, "fused8", contacts_per_world=peak)
+    for r in ref:
+        gs = gpu.step(scene.dt, 20)
+        for k in ("contacts", "pos_iterations", "vel_iterations", "max_contacts"):
+            assert gs[k] == r[k], (k, gs[k], r[k])
+    g, c = gpu.download(), cpu.download()
+    for f in STATE_FIELDS:
+        assert np.array_equal(getattr(g, f), getattr(c, f)), f
+    gpu.close()
+
+
+def test_f32_wide_group_record_ballistic():
+    """float32, 18 bodies per world (32 lanes per world, persistent kernel): the always-written per-check tails of
+    the record follow the 64-bit masks."""
+    scene = scenes.ballistic(_abi.F32, n_bullets=16)
+    gpu, cpu = make_world(scene, "fused32"), OracleWorld.from_scene(scene)
+    for s in range(0, 300, 10):
+        gs, cs = gpu.step(scene.dt, 10), cpu.step(scene.dt, 10)
+        for k in ("contacts", "pos_iterations", "vel_iterations"):
+            assert gs[k] == cs[k], (s, k, gs[k], cs[k])
+    g, c = gpu.download(), cpu.download()
+    for f in STATE_FIELDS:
+        assert np.array_equal(getattr(g, f), getattr(c, f)), f
+    gpu.close()
+
+
+def test_replan_after_host_step_rebuilds_the_pipeline():
+    """cz_world_upload_planes after a host-buffer step re-plans the world; the chunk pipeline (sized from the old
+    plan) must be rebuilt, not reused."""
+    scene = scenes.batched_cubedrop(n_worlds=48)
+    a, b = make_world(scene, "fused8"), make_world(scene, "fused8")
+    host = a.download()
+    a.step_host(host, scene.dt, 1); b.step(scene.dt, 1, stats=False)
+    two = _abi.Planes([[0, 1, 0], [0.6, 0.8, 0.0]], [0.0, -3.0], scene.prec)
+    a.upload_planes(two); b.upload_planes(two)          # more checks per world -> larger records, new scratch sizes
+    for _ in range(60):
+        a.step_host(host, scene.dt, 1); b.step(scene.dt, 1, stats=False)
+    ref = b.download()
+    for f in STATE_FIELDS:
+        assert np.array_equal(getattr(host, f), getattr(ref, f)), f
+    a.close(); b.close()
+
+
+def test_device_status_is_sticky_across_async_steps():
+    """An asynchronous step (stats=NULL) cannot return a device-side error; it must surface at the next observing
+    call instead of being wiped by it."""
+    from cubez_b200._abi import CubezError
+    scene = scenes.cubedrop()
+    w = make_world(scene, "fused8", contacts_per_world=16)
+    w.step(scene.dt, 200, stats=False)                 # overflows around frame 90; nothing can be reported here
+    with pytest.raises(CubezError) as e:
+        w.synchronize()
+    assert e.value.code == _abi.CZ_ERR_CAPACITY
+    w.synchronize()                                    # observed once: cleared
+    w.close()
