@@ -1,14 +1,11 @@
-// cubedrop_headless: the UNMODIFIED reference (github.com/tbogdala/cubez) on BASELINE config 1 (cubedrop: fire()
-// twice, ground plane, dt = 1/60; examples/cubedrop.go:29-75, :146-177) and config 4 (W independent, perturbed
-// copies of it), without GL.  One line per frame — contact count, FNV hash of the (body, body) sequence, hash of the
-// as-generated contact geometry, hash of every body's state — then the final state in raw IEEE bits.
+// pile_headless: the UNMODIFIED reference (github.com/tbogdala/cubez) on BASELINE config 3 — a side^3 jittered lattice of
+// alternating cubes and spheres falling into a pile on the ground plane, stepped by the all-pairs-ordered loop of
+// examples/cubedrop.go:29-75 (16.8 M ordered checks per frame at side = 16: this is the reference's O(n^2) stress).
+// Same dump as cubedrop_headless.go.
 //
-//	go run cubedrop_headless.go <steps> [worlds [firstWorld [secondFireStep]]] > dump.txt
-//	python tools/compare_go_dump.py dump.txt            (compares with the oracle, bit for bit)
+//	go run pile_headless.go <steps> [side] > dump.txt ; python tools/compare_go_dump.py dump.txt
 //
-// Straight-line calls of the reference's public API only.  This file is also what oracle/go2cpp.py translates
-// (together with the reference's own sources) into oracle/_ref/cubedrop_headless, so keep it inside the Go subset that
-// tool documents: no closures, no goroutines, no generics.
+// Also translated by oracle/go2cpp.py into oracle/_ref/pile_headless: keep it inside that tool's Go subset.
 package main
 
 import (
@@ -147,42 +144,42 @@ func (w *world) step(ground *cubez.CollisionPlane, step int, dt m.Real, pairs *u
 	return len(contacts)
 }
 
-// fire(), examples/cubedrop.go:146-177, without the GL node
-func fire(w *world, from int) {
-	var offset float32 = 0.0
-	if len(w.colliders) > 0 && (len(w.colliders)/4)%2 >= 1 {
-		offset = 0.75
-	}
-	for i := 0; i < 4; i++ {
-		c := cubez.NewCollisionCube(nil, m.Vector3{0.5, 0.5, 0.5})
-		c.Body.Position = m.Vector3{m.Real(i*2-2) - 0.5 + m.Real(offset), 10.0, 0.0}
-		c.Body.SetMass(8.0)
-		c.Body.CanSleep = true
+// SURVEY section 8d, cfg3: body b = ix + side*(iz + side*iy) at (1.25*(ix-h)+jx, 0.75+1.25*iy+jy, 1.25*(iz-h)+jz),
+// jitter U(-0.05, 0.05) from splitmix64(0xC0BE2 + b); (ix+iy+iz) even: cube half 0.5 mass 8, odd: sphere r 0.5 mass 4
+func build(w *world, side int) {
+	h := float64(side-1) / 2.0
+	for b := 0; b < side*side*side; b++ {
+		ix := b % side
+		iz := (b / side) % side
+		iy := b / (side * side)
+		state := uint64(0xC0BE2) + uint64(b)
+		jx := uniform(draw(&state), -0.05, 0.05)
+		jy := uniform(draw(&state), -0.05, 0.05)
+		jz := uniform(draw(&state), -0.05, 0.05)
+		pos := m.Vector3{m.Real(1.25*(float64(ix)-h) + jx), m.Real(0.75 + 1.25*float64(iy) + jy), m.Real(1.25*(float64(iz)-h) + jz)}
 		var inertia m.Matrix3
-		inertia.SetBlockInertiaTensor(&c.HalfSize, 8.0)
-		c.Body.SetInertiaTensor(&inertia)
-		c.Body.CalculateDerivedData()
-		c.CalculateDerivedData()
-		w.add(c, from)
-	}
-}
-
-// cfg4 perturbation of world number id (SURVEY section 8d): per cube six draws of splitmix64(1234 + id)
-func perturb(w *world, id uint64) {
-	state := 1234 + id
-	for _, c := range w.colliders {
-		b := c.GetBody()
-		dx := uniform(draw(&state), -0.1, 0.1)
-		dz := uniform(draw(&state), -0.1, 0.1)
-		dy := uniform(draw(&state), -1.0, 1.0)
-		b.Position[0] = m.Real(float64(b.Position[0]) + dx)
-		b.Position[1] = m.Real(float64(b.Position[1]) + dy)
-		b.Position[2] = m.Real(float64(b.Position[2]) + dz)
-		q := m.Quat{1.0, m.Real(uniform(draw(&state), -0.1, 0.1)), m.Real(uniform(draw(&state), -0.1, 0.1)), m.Real(uniform(draw(&state), -0.1, 0.1))}
-		ln := m.RealSqrt(q[0]*q[0] + q[1]*q[1] + q[2]*q[2] + q[3]*q[3])
-		b.Orientation = m.Quat{q[0] / ln, q[1] / ln, q[2] / ln, q[3] / ln}
-		b.CalculateDerivedData()
-		c.CalculateDerivedData()
+		if (ix+iy+iz)%2 == 0 {
+			c := cubez.NewCollisionCube(nil, m.Vector3{0.5, 0.5, 0.5})
+			c.Body.Position = pos
+			c.Body.SetMass(8.0)
+			inertia.SetBlockInertiaTensor(&c.HalfSize, 8.0)
+			c.Body.SetInertiaTensor(&inertia)
+			c.Body.CalculateDerivedData()
+			c.CalculateDerivedData()
+			w.add(c, 0)
+		} else {
+			var mass m.Real = 4.0
+			var radius m.Real = 0.5
+			s := cubez.NewCollisionSphere(nil, radius)
+			s.Body.Position = pos
+			s.Body.SetMass(mass)
+			var coeff m.Real = 0.4 * mass * radius * radius
+			inertia.SetInertiaTensorCoeffs(coeff, coeff, coeff, 0.0, 0.0, 0.0)
+			s.Body.SetInertiaTensor(&inertia)
+			s.Body.CalculateDerivedData()
+			s.CalculateDerivedData()
+			w.add(s, 0)
+		}
 	}
 }
 
@@ -197,53 +194,31 @@ func argInt(k int, dflt int) int {
 }
 
 func main() {
-	steps := argInt(1, 600)
-	nWorlds := argInt(2, 0)
-	firstWorld := argInt(3, 0)
-	secondFire := argInt(4, 0)
-	ground := cubez.NewCollisionPlane(m.Vector3{0.0, 1.0, 0.0}, 0.0) // cubedrop.go:127
-	var worlds []*world
-	count := nWorlds
-	if count == 0 {
-		count = 1
-	}
-	for k := 0; k < count; k++ {
-		w := new(world)
-		w.index = make(map[*cubez.RigidBody]int)
-		fire(w, 0)
-		fire(w, secondFire)
-		if nWorlds > 0 {
-			perturb(w, uint64(firstWorld+k))
-		}
-		worlds = append(worlds, w)
-	}
+	steps := argInt(1, 60)
+	side := argInt(2, 16)
+	ground := cubez.NewCollisionPlane(m.Vector3{0.0, 1.0, 0.0}, 0.0)
+	w := new(world)
+	w.index = make(map[*cubez.RigidBody]int)
+	build(w, side)
 	dt := m.Real(1.0 / 60.0)
-	fmt.Printf("cubez-dump v2 scene=cubedrop worlds=%d bodies=%d steps=%d\n", count, 8*count, steps)
+	fmt.Printf("cubez-dump v2 scene=pile worlds=1 bodies=%d steps=%d\n", len(w.colliders), steps)
 	start := time.Now()
 	for s := 0; s < steps; s++ {
 		var pairs uint64
 		var gen hasher
 		var state hasher
-		total := 0
-		for _, w := range worlds {
-			total += w.step(ground, s, dt, &pairs, &gen)
-		}
-		for _, w := range worlds {
-			for _, c := range w.colliders {
-				state.body(c.GetBody())
-			}
+		total := w.step(ground, s, dt, &pairs, &gen)
+		for _, c := range w.colliders {
+			state.body(c.GetBody())
 		}
 		fmt.Printf("step %d contacts %d pairhash %016x genhash %016x statehash %016x\n", s, total, pairs, gen.h, state.h)
+		fmt.Fprintf(os.Stderr, "frame %d: %d contacts, %.3f s so far\n", s, total, time.Since(start).Seconds())
 	}
 	wall := time.Since(start).Seconds()
-	n := 0
-	for _, w := range worlds {
-		for _, c := range w.colliders {
-			if n < 64 {
-				printBody(n, c.GetBody())
-			}
-			n++
+	for i, c := range w.colliders {
+		if i < 64 {
+			printBody(i, c.GetBody())
 		}
 	}
-	fmt.Fprintf(os.Stderr, "wall %.6f s for %d steps of %d worlds\n", wall, steps, count)
+	fmt.Fprintf(os.Stderr, "wall %.6f s for %d steps of %d bodies\n", wall, steps, len(w.colliders))
 }

@@ -1,0 +1,41 @@
+#!/usr/bin/env python
+"""Generates tests/golden/ref/*.txt — dumps printed by the REFERENCE ITSELF (tbogdala/cubez's Go sources, translated
+mechanically by oracle/go2cpp.py and driven by the harness mains of go/harness/, see oracle/Makefile target `ref`).
+The vectors travel to the GPU box (where /root/reference does not exist); tests compare the CPU oracle and the CUDA
+path with them bit for bit.  Re-run after changing a harness:   python oracle/make_ref_golden.py [name ...]
+(pile4096_80 takes ~10 minutes: the reference's all-pairs loop and O(contacts^2) resolver)."""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+OUT = os.path.join(os.path.dirname(HERE), "tests", "golden", "ref")
+CASES = {   # name -> (binary, args)          scene builder of the same case: tests/ref_cases.py
+    "cubedrop_600": ("cubedrop_headless", ["600"]),
+    "cubedrop_staggered_260": ("cubedrop_headless", ["260", "0", "0", "120"]),
+    "ballistic_600": ("ballistic_headless", ["600"]),
+    "ballistic16_300": ("ballistic_headless", ["300", "16"]),
+    "batched256_600": ("cubedrop_headless", ["600", "256", "0"]),
+    "batched64_from1000_300": ("cubedrop_headless", ["300", "64", "1000"]),
+    "pile27_150": ("pile_headless", ["150", "3"]),
+    "pile216_120": ("pile_headless", ["120", "6"]),
+    "pile4096_80": ("pile_headless", ["80", "16"]),
+    "free65536_16": ("integrate_bench_headless", ["16", "65536"]),
+}
+
+if __name__ == "__main__":
+    subprocess.run(["make", "-s", "ref"], cwd=HERE, check=True)
+    os.makedirs(OUT, exist_ok=True)
+    only = sys.argv[1:]
+    for name, (binary, args) in CASES.items():
+        if only and name not in only:
+            continue
+        r = subprocess.run([os.path.join(HERE, "_ref", binary)] + args, capture_output=True, text=True, check=True)
+        with open(os.path.join(OUT, name + ".txt"), "w") as f:
+            f.write(r.stdout)
+        print(name, len(r.stdout.splitlines()), "lines;", r.stderr.strip().splitlines()[-1])
+    if not only or "math_tests" in only:
+        r = subprocess.run([os.path.join(HERE, "_ref", "math_tests")], capture_output=True, text=True)
+        with open(os.path.join(OUT, "math_tests.txt"), "w") as f:
+            f.write(r.stdout)
+        print("math_tests:", r.stdout.strip().splitlines()[-1])

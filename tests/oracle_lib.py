@@ -213,7 +213,11 @@ class OracleWorld:
         return out
 
     def contacts(self, world: int = 0) -> Contacts:
-        out = Contacts(max(self.Cc, 1 << 16), self.prec)
+        # the oracle never truncates (contacts_per_world is only a hint for it): size the arrays from the count
+        probe = Contacts(1, self.prec)
+        pst = probe.struct()
+        self.lib.czo_world_download_contacts(self.h, world, C.byref(pst))
+        out = Contacts(max(int(pst.n), 1), self.prec)
         st = out.struct()
         rc = self.lib.czo_world_download_contacts(self.h, world, C.byref(st))
         assert rc == 0, rc

@@ -1,0 +1,24 @@
+"""Scene builders of the reference dumps under tests/golden/ref/ (written by oracle/make_ref_golden.py from the
+reference's own Go sources, mechanically translated — see oracle/go2cpp.py).  name -> (scene factory, frames)."""
+import os
+
+from cubez_b200 import scenes
+
+REF_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref")
+REF_CASES = {
+    "cubedrop_600": (lambda: scenes.cubedrop(), 600),
+    "cubedrop_staggered_260": (lambda: scenes.cubedrop(second_fire_step=120), 260),
+    "ballistic_600": (lambda: scenes.ballistic(), 600),
+    "ballistic16_300": (lambda: scenes.ballistic(n_bullets=16), 300),
+    "batched256_600": (lambda: scenes.batched_cubedrop(n_worlds=256), 600),
+    "batched64_from1000_300": (lambda: scenes.batched_cubedrop(n_worlds=64, first_world=1000), 300),
+    "pile27_150": (lambda: scenes.pile(side=3), 150),
+    "pile216_120": (lambda: scenes.pile(side=6), 120),
+    "pile4096_80": (lambda: scenes.pile(side=16), 80),
+    "free65536_16": (lambda: scenes.free_bodies(n=65536), 16),
+}
+
+
+def ref_text(name: str) -> str:
+    with open(os.path.join(REF_DIR, name + ".txt")) as f:
+        return f.read()
