@@ -582,6 +582,14 @@ __global__ void __launch_bounds__(NT) k_resolve(WorldParams p, ResolveScratch rs
         pi = resolve_loop<32, false>(x, true, maxIter, tid, &status);
         __syncthreads();
         vi = resolve_loop<32, true>(x, true, maxIter, tid, &status);
+    } else if (useSmem == 3 && nC <= hotCap) {   // one large world: adjacency lists + shared arg-max caches + prefetched propagation
+        __shared__ BigBroadcast bb;
+        __shared__ int scanScratch[NT / 32 + 1];
+        const BigShared sh = big_carve(smem_raw, (NT > 32 ? NT : 64), hotCap, p.B);
+        big_build_adjacency<(NT > 32 ? NT : 64)>(x, p.B, tid, sh, scanScratch);
+        pi = resolve_loop_big<(NT > 32 ? NT : 64), false>(x, maxIter, &gs, &bb, tid, &status, sh);
+        __syncthreads();
+        vi = resolve_loop_big<(NT > 32 ? NT : 64), true>(x, maxIter, &gs, &bb, tid, &status, sh);
     } else if (useSmem == 2 && nC <= hotCap) {   // one large world: hot value + 16-bit body ids in shared memory, cached arg-max
         real *sHot = (real *)smem_raw;
         unsigned short *sB0 = (unsigned short *)(sHot + hotCap), *sB1 = sB0 + hotCap;

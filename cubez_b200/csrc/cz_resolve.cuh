@@ -746,4 +746,306 @@ __device__ __forceinline__ int resolve_loop_cta_cached(const Ctx &x0, int maxIte
     return used;
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// ONE LARGE world per CTA, third design (cfg3: 14 k contacts, both loops at their 8*len cap = 120 k strictly
+// sequential iterations per frame).  ncu of the loop above at 14 k contacts (profiles/r02_resolve_large_world_before.txt):
+// 14.9 k warp-instructions per iteration, 55 % of them the body-id scan of every contact, 11 % the re-scan of the
+// owners' hot values, 25 % of the stall samples the barrier at which 7 warps wait for warp 0's scalar resolve.
+// Here an iteration touches only what the winner touches:
+//   * adjacency lists body -> contacts (CSR, 16-bit ids, shared memory), built once per frame: the contacts the
+//     winner's change reaches are the two lists of its bodies — O(degree), no scan;
+//   * the per-owner arg-max cache (owner o = contacts o, o+NT, ...) lives in shared memory; an owner is re-scanned
+//     only when its cached best was touched or overtaken, by its whole warp (2 loads per lane);
+//   * while warp 0 computes the winner's resolve (one L2 round trip + the FP64 chain), the other warps already hold
+//     the cold records of the touched contacts in registers (same L2 round trip): the propagation is arithmetic only.
+// Same worst-first order as the reference (contact.go:240-245 / :396-402): ties to the lowest index in every reduce,
+// NaN never wins.  The order in which touched contacts are updated is free: each is updated exactly once per
+// iteration with the reference's (b, d) order inside (contact.go:259-279, :416-442).
+// ------------------------------------------------------------------------------------------------
+struct BigShared {
+    real *hot;                  // [cap] staged hot value of the running phase (penetration | desired delta-v)
+    unsigned short *adjList;    // [2*cap] contact ids grouped by body
+    unsigned short *adjOff;     // [B+1] first entry of every body's list
+    real *cacheV;               // [NT] best hot value among the owner's contacts (> epsilon) ...
+    int *cacheI;                // [NT] ... and its contact (0x7fffffff: none)
+    unsigned char *dirty;       // [NT] owner must be re-scanned
+};
+// shared-memory bytes of the plan for `cap` contacts (cap <= 32767) and B bodies (B < 65535)
+static inline size_t big_shared_bytes(int NT, long long cap, long long B) {
+    size_t hotBytes = (size_t)cap * sizeof(real);
+    if (hotBytes < (size_t)B * sizeof(int)) hotBytes = (size_t)B * sizeof(int);   // the CSR build borrows the region for its counters
+    size_t bytes = (hotBytes + 15) / 16 * 16;
+    bytes += ((size_t)2 * cap * sizeof(unsigned short) + 15) / 16 * 16;
+    bytes += ((size_t)(B + 1) * sizeof(unsigned short) + 15) / 16 * 16;
+    bytes += (size_t)NT * (sizeof(real) + sizeof(int) + 1) + 16;
+    return (bytes + 15) / 16 * 16;
+}
+__device__ __forceinline__ BigShared big_carve(unsigned char *base, int NT, int cap, int B) {
+    BigShared s;
+    size_t hotBytes = (size_t)cap * sizeof(real);
+    if (hotBytes < (size_t)B * sizeof(int)) hotBytes = (size_t)B * sizeof(int);
+    size_t off = 0;
+    s.hot = (real *)base; off += (hotBytes + 15) / 16 * 16;
+    s.adjList = (unsigned short *)(base + off); off += ((size_t)2 * cap * sizeof(unsigned short) + 15) / 16 * 16;
+    s.adjOff = (unsigned short *)(base + off); off += ((size_t)(B + 1) * sizeof(unsigned short) + 15) / 16 * 16;
+    s.cacheV = (real *)(base + off); off += (size_t)NT * sizeof(real);
+    s.cacheI = (int *)(base + off); off += (size_t)NT * sizeof(int);
+    s.dirty = base + off;
+    return s;
+}
+
+// CSR adjacency of the contact graph: counting sort of (body, contact) incidences in shared memory.
+template <int NT>
+__device__ __forceinline__ void big_build_adjacency(const Ctx &x, int nBodies, int tid, const BigShared &sh, int *scanScratch /* shared int[NT/32 + 1] */) {
+    int *deg = (int *)sh.hot;    // counters, then fill cursors
+    for (int b = tid; b < nBodies; b += NT) deg[b] = 0;
+    __syncthreads();
+    for (int c = tid; c < x.nC; c += NT) {
+        const int b0 = x.cb0[c], b1 = x.cb1[c];
+        atomicAdd(&deg[b0], 1);
+        if (b1 >= 0 && b1 != b0) atomicAdd(&deg[b1], 1);
+    }
+    __syncthreads();
+    const int per = (nBodies + NT - 1) / NT, lo = min(tid * per, nBodies), hi = min(lo + per, nBodies);
+    int sum = 0;
+    for (int b = lo; b < hi; b++) sum += deg[b];
+    const int lane = tid & 31, warp = tid >> 5;
+    int incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) scanScratch[warp] = incl;
+    __syncthreads();
+    int base = 0;
+    for (int w2 = 0; w2 < warp; w2++) base += scanScratch[w2];
+    int run = base + incl - sum;
+    for (int b = lo; b < hi; b++) {
+        const int d = deg[b];
+        sh.adjOff[b] = (unsigned short)run;
+        deg[b] = run;
+        run += d;
+    }
+    if (hi == nBodies && lo < nBodies) sh.adjOff[nBodies] = (unsigned short)run;
+    if (nBodies == 0 && tid == 0) sh.adjOff[0] = 0;
+    __syncthreads();
+    for (int c = tid; c < x.nC; c += NT) {
+        const int b0 = x.cb0[c], b1 = x.cb1[c];
+        sh.adjList[atomicAdd(&deg[b0], 1)] = (unsigned short)c;
+        if (b1 >= 0 && b1 != b0) sh.adjList[atomicAdd(&deg[b1], 1)] = (unsigned short)c;
+    }
+    __syncthreads();
+}
+
+// a touched contact held in registers while warp 0 resolves the winner
+struct Touched {
+    int c, b0, b1;
+    V3 n, ty, tz, rp0, rp1, cv, la0, la1;
+    real restitution;
+    bool aw0, aw1;
+};
+
+template <bool VELOCITY>
+__device__ __forceinline__ void big_prefetch(const Ctx &x, int c, Touched &t) {
+    t.c = c;
+    t.b0 = x.cb0[c]; t.b1 = x.cb1[c];
+    t.n = cw3(x, CW_N, c);
+    t.rp0 = cw3(x, CW_RP0, c);
+    t.rp1 = cw3(x, CW_RP1, c);
+    if (VELOCITY) {
+        t.ty = cw3(x, CW_TY, c); t.tz = cw3(x, CW_TZ, c); t.cv = cw3(x, CW_CV, c);
+        t.restitution = ctx_restitution(x, c);
+        t.aw0 = bw_awake(x, t.b0);
+        t.la0 = bw3(x, BW_LACC, t.b0);
+        t.aw1 = false; t.la1 = zero3();
+        if (t.b1 >= 0) { t.aw1 = bw_awake(x, t.b1); t.la1 = bw3(x, BW_LACC, t.b1); }
+    }
+}
+
+// contact.go:259-279 on a prefetched contact; returns the new penetration
+__device__ __forceinline__ real big_propagate_position(const Touched &t, real pen, const Change &ch) {
+    const int cb[2] = {t.b0, t.b1};
+#pragma unroll
+    for (int b = 0; b < 2; b++) {
+        if (cb[b] < 0) continue;
+        const V3 rp = b == 0 ? t.rp0 : t.rp1;
+#pragma unroll
+        for (int d = 0; d < 2; d++) {
+            if (cb[b] == ch.b[d]) {
+                V3 dp = v_cross(ch.ang[d], rp);
+                v_add(dp, ch.lin[d]);
+                const real sign = b == 0 ? R_(-1.0) : R_(1.0);
+                pen += v_dot(dp, t.n) * sign;
+            }
+        }
+    }
+    return pen;
+}
+// contact.go:416-442 on a prefetched contact (flags already fixed up for a body woken by the winner); returns the new
+// desiredDeltaVelocity, `cv` receives the new contactVelocity
+__device__ __forceinline__ real big_propagate_velocity(const Touched &t, const Change &ch, real dt, V3 &cv) {
+    const int cb[2] = {t.b0, t.b1};
+    cv = t.cv;
+#pragma unroll
+    for (int b = 0; b < 2; b++) {
+        if (cb[b] < 0) continue;
+        const V3 rp = b == 0 ? t.rp0 : t.rp1;
+#pragma unroll
+        for (int d = 0; d < 2; d++) {
+            if (cb[b] == ch.b[d]) {
+                V3 dv = v_cross(ch.ang[d], rp);
+                v_add(dv, ch.lin[d]);
+                const real sign = b == 1 ? R_(-1.0) : R_(1.0);
+                V3 tt = mk3(v_dot(dv, t.n), v_dot(dv, t.ty), v_dot(dv, t.tz));
+                v_mul(tt, sign);
+                v_add(cv, tt);
+            }
+        }
+    }
+    // calculateDesiredDeltaVelocity (contact.go:87-112) from the prefetched flags and last-frame accelerations
+    real vfa = R_(0);
+    if (t.aw0) { V3 a = t.la0; v_mul(a, dt); vfa += v_dot(a, t.n); }
+    if (t.b1 >= 0 && t.aw1) { V3 a = t.la1; v_mul(a, dt); vfa -= v_dot(a, t.n); }
+    real rest = t.restitution;
+    if (rabs(cv.c[0]) < R_(0.25)) rest = R_(0);
+    return -cv.c[0] - rest * (cv.c[0] - vfa);
+}
+
+// warp-cooperative re-scan of owner `o`: lanes stride the owner's contacts, arg-max with ties to the lowest index
+template <int NT>
+__device__ __forceinline__ void big_rescan_owner(const BigShared &sh, int nC, int o, int lane) {
+    real v = R_(0.01);    // positionEpsilon / velocityEpsilon (contact.go:12-13)
+    int i = 0x7fffffff;
+    for (int c = o + lane * NT; c < nC; c += 32 * NT) {
+        const real hv = sh.hot[c];
+        if (hv > v) { v = hv; i = c; }
+    }
+    warp_argmax<32>(v, i, 0xffffffffu);
+    if (lane == 0) { sh.cacheV[o] = v; sh.cacheI[o] = i; sh.dirty[o] = 0; }
+}
+
+struct BigBroadcast {   // warp 0 -> everyone, once per iteration
+    real chg[12];
+    int chb[2];
+    int wake;           // body woken by matchAwakeState, or -1
+};
+
+template <int NT, bool VELOCITY>
+__device__ __forceinline__ int resolve_loop_big(const Ctx &x0, int maxIterations, GroupScratch *gs, BigBroadcast *bb, int tid, int *status, const BigShared &sh) {
+    static_assert(NT >= 64 && (NT & (NT - 1)) == 0, "owner = contact mod NT");
+    const int lane = tid & 31, warp = tid >> 5;
+    const unsigned full = 0xffffffffu;
+    Ctx x = x0;
+    real *gHot = VELOCITY ? x0.ddv : x0.pen;
+    for (int c = tid; c < x.nC; c += NT) sh.hot[c] = gHot[c];
+    if (VELOCITY) x.ddv = sh.hot; else x.pen = sh.hot;
+    sh.dirty[tid] = 0;
+    __syncthreads();
+    {   // every thread is an owner: initial cache
+        real v = R_(0.01);
+        int i = 0x7fffffff;
+        for (int c = tid; c < x.nC; c += NT) {
+            const real hv = sh.hot[c];
+            if (hv > v) { v = hv; i = c; }
+        }
+        sh.cacheV[tid] = v; sh.cacheI[tid] = i;
+    }
+    __syncthreads();
+    int used = 0;
+    while (used < maxIterations) {
+        // ---- worst contact: block arg-max of the owners' caches ------------------------------------------------
+        real best = sh.cacheV[tid];
+        int idx = sh.cacheI[tid];
+        warp_argmax<32>(best, idx, full);
+        if (lane == 0) { gs->redv[warp] = best; gs->redi[warp] = idx; }
+        __syncthreads();
+        best = lane < NT / 32 ? gs->redv[lane] : R_(0.01);
+        idx = lane < NT / 32 ? gs->redi[lane] : 0x7fffffff;
+        warp_argmax<32>(best, idx, full);
+        if (idx == 0x7fffffff) break;
+        // ---- the contacts the winner's change will reach: the adjacency lists of its bodies --------------------
+        const int wb0 = x.cb0[idx], wb1 = x.cb1[idx];
+        const int s0 = sh.adjOff[wb0], n0 = (int)sh.adjOff[wb0 + 1] - s0;
+        const int s1 = wb1 >= 0 && wb1 != wb0 ? (int)sh.adjOff[wb1] : 0, n1 = wb1 >= 0 && wb1 != wb0 ? (int)sh.adjOff[wb1 + 1] - s1 : 0;
+        const int nT = n0 + n1;
+        // warps 1.. take one touched contact per thread and fetch its record now, under warp 0's resolve
+        Touched t;
+        const int item = tid - 32;
+        bool mine = false;
+        if (item >= 0 && item < nT) {
+            const int c = item < n0 ? sh.adjList[s0 + item] : sh.adjList[s1 + item - n0];
+            big_prefetch<VELOCITY>(x, c, t);
+            // a contact between the winner's two bodies is in both lists: it is updated once, from the first
+            mine = item < n0 || (t.b0 != wb0 && t.b1 != wb0);
+        }
+        Change ch;
+        if (warp == 0) {
+            PosCommit pc;
+            VelCommit vc;
+            if (VELOCITY) resolve_velocity(x, idx, ch, vc);
+            else resolve_position(x, idx, best, ch, pc);
+            __syncwarp();
+            if (lane == 0) {
+                if (VELOCITY) { commit_velocity(x, vc); if (vc.status) *status = vc.status; }
+                else commit_position(x, pc);
+#pragma unroll
+                for (int k = 0; k < 3; k++) { bb->chg[k] = ch.lin[0].c[k]; bb->chg[3 + k] = ch.lin[1].c[k]; bb->chg[6 + k] = ch.ang[0].c[k]; bb->chg[9 + k] = ch.ang[1].c[k]; }
+                bb->chb[0] = ch.b[0]; bb->chb[1] = ch.b[1];
+                const int wk = VELOCITY ? vc.wake : pc.wake;
+                bb->wake = wk >= 0 ? ch.b[wk] : -1;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 3; k++) { ch.lin[0].c[k] = bb->chg[k]; ch.lin[1].c[k] = bb->chg[3 + k]; ch.ang[0].c[k] = bb->chg[6 + k]; ch.ang[1].c[k] = bb->chg[9 + k]; }
+        ch.b[0] = bb->chb[0]; ch.b[1] = bb->chb[1];
+        const int woken = bb->wake;
+        // ---- propagation: arithmetic on the prefetched records ------------------------------------------------------
+        auto publish = [&](int c, real v) {
+            sh.hot[c] = v;
+            const int o = c & (NT - 1);
+            const real cv0 = sh.cacheV[o];
+            const int ci = sh.cacheI[o];
+            if (c == ci || v > cv0 || (v == cv0 && c < ci)) sh.dirty[o] = 1;
+        };
+        if (mine) {
+            if (VELOCITY) {
+                if (woken >= 0) { if (t.b0 == woken) t.aw0 = true; if (t.b1 == woken) t.aw1 = true; }
+                V3 cv;
+                const real ddv = big_propagate_velocity(t, ch, x.dt, cv);
+                cw3_set(x, CW_CV, t.c, cv);
+                publish(t.c, ddv);
+            } else {
+                publish(t.c, big_propagate_position(t, sh.hot[t.c], ch));
+            }
+        }
+        // more touched contacts than prefetching threads (a body with hundreds of contacts): the rest in place
+        for (int it2 = NT - 32 + tid; it2 < nT; it2 += NT) {
+            const int c = it2 < n0 ? sh.adjList[s0 + it2] : sh.adjList[s1 + it2 - n0];
+            if (it2 >= n0 && (x.cb0[c] == wb0 || x.cb1[c] == wb0)) continue;
+            if (VELOCITY) propagate_velocity(x, c, ch);
+            else propagate_position(x, c, ch);
+            publish(c, sh.hot[c]);
+        }
+        __syncthreads();
+        // ---- owners whose cached best was touched or overtaken are re-scanned by their warp ----------------------
+        unsigned dm = __ballot_sync(full, sh.dirty[tid] != 0);
+        while (dm) {
+            const int l2 = __ffs(dm) - 1;
+            dm &= dm - 1;
+            big_rescan_owner<NT>(sh, x.nC, warp * 32 + l2, lane);
+        }
+        __syncwarp();
+        used++;
+        // the next iteration's first barrier (inside the reduce) orders this iteration's shared-memory writes of other
+        // warps before warp 0 reads the winner's hot value
+    }
+    __syncthreads();
+    for (int c = tid; c < x.nC; c += NT) gHot[c] = sh.hot[c];
+    __syncthreads();
+    return used;
+}
+
 }  // namespace czr

@@ -815,14 +815,18 @@ template <int NT>
 static void launch_resolve(cz_world *w, const WorldParams &p, int maxIterOverride, real dt, bool forceGlobal, long long contactsHint = -1) {
     int smem = forceGlobal ? 0 : w->resolveSmem;
     int mode = smem > 0 ? 1 : 0, hotCap = 0;
-    if (NT > 32 && mode == 0 && p.B < 0xffff && !czf::env_int("CUBEZ_RESOLVE_NO_CACHE", 0)) {
-        // one large world: stage the hot value (8 B) and 16-bit body ids (4 B) of every contact in shared memory.
-        // The host knows the contact count on the broadphase path; otherwise size for the capacity.
+    // CUBEZ_RESOLVE_MODE: 0 plain CTA loop, 2 staged hot values + cached arg-max (round 1), 3 adjacency lists (default)
+    const int want_mode = czf::env_int("CUBEZ_RESOLVE_NO_CACHE", 0) ? 0 : czf::env_int("CUBEZ_RESOLVE_MODE", 3);
+    if (NT > 32 && mode == 0 && p.B < 0xffff && want_mode != 0) {
+        // one large world: the loop's working set in shared memory.  The host knows the contact count on the
+        // broadphase path; otherwise size for the capacity.
         long long want = contactsHint >= 0 ? std::min<long long>(contactsHint, p.Cc) : p.Cc;
         want = (want + 255) / 256 * 256;
-        const size_t bytes = (size_t)want * (sizeof(real) + 4);
         const size_t limit = w->ctx->smem_optin > 4096 ? w->ctx->smem_optin - 4096 : 0;
-        if (want > 0 && bytes <= limit) { mode = 2; hotCap = (int)want; smem = (int)bytes; }
+        const size_t big = czr::big_shared_bytes(NT, want, p.B);
+        const size_t bytes = (size_t)want * (sizeof(real) + 4);
+        if (want_mode == 3 && want > 0 && want <= 32767 && big <= limit) { mode = 3; hotCap = (int)want; smem = (int)big; }
+        else if (want > 0 && bytes <= limit) { mode = 2; hotCap = (int)want; smem = (int)bytes; }
     }
     cudaError_t ea = cudaSuccess;
     if (smem + 2048 > 48 * 1024) ea = cudaFuncSetAttribute(k_resolve<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
