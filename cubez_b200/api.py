@@ -351,6 +351,62 @@ class BatchedWorld:
             pass
 
 
+class Run:
+    """Multi-GPU run of batched worlds inside ONE process (cz_run_*): the worlds of a scene are sharded contiguously
+    over `devices`, stepped with no traffic between devices, and cz_run_finish reduces checksum / energy / counters
+    with one grouped ncclAllReduce (host reduce when shards share a device)."""
+
+    def __init__(self, scene, devices, contacts_per_world: Optional[int] = None, flags: int = 0):
+        from ._abi import CzRunTotals, load
+        self._Totals = CzRunTotals
+        self.prec = scene.prec
+        self.lib = load(scene.prec.name)
+        self.scene = scene
+        devs = np.ascontiguousarray(devices, dtype=np.int32)
+        self.desc = CzWorldDesc(scene.n_worlds, scene.bodies_per_world, contacts_per_world or scene.contacts_per_world, scene.schedule, flags)
+        self.h = C.c_void_p()
+        self._check(self.lib.cz_run_create(devs.shape[0], devs.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(self.desc), C.byref(self.h)), created=False)
+        pst = scene.planes.struct()
+        self._check(self.lib.cz_run_upload_planes(self.h, C.byref(pst)))
+        bst = scene.bodies.struct()
+        self._check(self.lib.cz_run_upload_bodies(self.h, C.byref(bst), 1))
+        cst = scene.colliders.struct()
+        self._check(self.lib.cz_run_upload_colliders(self.h, C.byref(cst), 1))
+
+    def _check(self, rc, created=True):
+        if rc != 0:
+            msg = self.lib.cz_run_last_error(self.h if created else None)
+            raise CubezError(rc, (msg or b"").decode())
+
+    def shard(self, k: int):
+        w, first, n = C.c_void_p(), C.c_int32(), C.c_int32()
+        self._check(self.lib.cz_run_shard(self.h, k, C.byref(w), C.byref(first), C.byref(n)))
+        return w, int(first.value), int(n.value)
+
+    def set_episodes(self, length: int, phase0=None):
+        ph = None if phase0 is None else np.ascontiguousarray(phase0, dtype=np.int32)
+        self._check(self.lib.cz_run_set_episodes(self.h, length, None if ph is None else ph.ctypes.data_as(C.POINTER(C.c_int32))))
+
+    def step(self, dt, n_steps: int = 1):
+        self._check(self.lib.cz_run_step(self.h, self.prec.ctype(dt), n_steps))
+
+    def finish(self) -> dict:
+        t = self._Totals()
+        self._check(self.lib.cz_run_finish(self.h, C.byref(t)))
+        return t.as_dict()
+
+    def close(self):
+        if self.h:
+            self.lib.cz_run_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 # ==========================================================================================
 # The reference's object API (rigidbody.go / colliders.go / contact.go), same identifiers.
 # ==========================================================================================

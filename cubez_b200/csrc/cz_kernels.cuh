@@ -508,6 +508,7 @@ struct ResolveScratch {
     real *bw;   // [W][BW_NF*B]
     real *cw;   // [W][CW_NREAL*Cc]
     int *cb;    // [W][2*Cc]
+    real *pre;  // [W][VP_NF*Cc] per-contact velocity response of the large-world loop, or NULL
 };
 
 CZD void load_body_work(const czr::Ctx &x, const BodyStore &s, long long gi, int b) {
@@ -587,9 +588,10 @@ __global__ void __launch_bounds__(NT) k_resolve(WorldParams p, ResolveScratch rs
         __shared__ int scanScratch[NT / 32 + 1];
         const BigShared sh = big_carve(smem_raw, (NT > 32 ? NT : 64), hotCap, p.B);
         big_build_adjacency<(NT > 32 ? NT : 64)>(x, p.B, tid, sh, scanScratch);
-        pi = resolve_loop_big<(NT > 32 ? NT : 64), false>(x, maxIter, &gs, &bb, tid, &status, sh);
+        real *velPre = rs.pre ? rs.pre + (size_t)w * czr::VP_NF * p.Cc : nullptr;
+        pi = resolve_loop_big<(NT > 32 ? NT : 64), false>(x, maxIter, &gs, &bb, tid, &status, sh, nullptr);
         __syncthreads();
-        vi = resolve_loop_big<(NT > 32 ? NT : 64), true>(x, maxIter, &gs, &bb, tid, &status, sh);
+        vi = resolve_loop_big<(NT > 32 ? NT : 64), true>(x, maxIter, &gs, &bb, tid, &status, sh, velPre);
     } else if (useSmem == 2 && nC <= hotCap) {   // one large world: hot value + 16-bit body ids in shared memory, cached arg-max
         real *sHot = (real *)smem_raw;
         unsigned short *sB0 = (unsigned short *)(sHot + hotCap), *sB1 = sB0 + hotCap;

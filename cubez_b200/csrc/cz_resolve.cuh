@@ -191,7 +191,8 @@ CZD void resolve_position(const Ctx &x, int c, real penetration, Change &ch, Pos
     V3 rp[2] = {cw3(x, CW_RP0, c), cw3(x, CW_RP1, c)};
     bool awake[2] = {bw_awake(x, b[0]), b[1] >= 0 ? bw_awake(x, b[1]) : false};
     int wake = match_awake(awake[0], awake[1], b[1]);   // :252
-    if (wake >= 0) awake[wake] = true;
+    if (wake == 0) awake[0] = true;
+    if (wake == 1) awake[1] = true;
     pc.wake = wake;
     real angularInertia[2] = {R_(0), R_(0)}, linearInertia[2] = {R_(0), R_(0)}, angularMove[2], linearMove[2];
     real totalInertia = R_(0);
@@ -278,8 +279,9 @@ CZD void commit_position(const Ctx &x, PosCommit &pc) {
         for (int k = 0; k < 4; k++) x.bw[(BW_Q + k) * x.bs + b] = pc.q[i].c[k];
     }
     if (pc.wake >= 0) {   // SetAwake(true) rigidbody.go:183-186
-        x.bw[BW_AWAKE * x.bs + pc.b[pc.wake]] = R_(1);
-        x.bw[BW_MOTION * x.bs + pc.b[pc.wake]] = R_(0.6);
+        const int wb = pc.wake == 0 ? pc.b[0] : pc.b[1];
+        x.bw[BW_AWAKE * x.bs + wb] = R_(1);
+        x.bw[BW_MOTION * x.bs + wb] = R_(0.6);
     }
 }
 
@@ -314,7 +316,64 @@ struct VelCommit {
     int status;
 };
 
-CZD void resolve_velocity(const Ctx &x, int c, Change &ch, VelCommit &vc) {
+// calculateFrictionImpulse, contact.go:535-577: the velocity change per unit impulse in contact coordinates (dv) and its
+// inverse (im).  Functions of the relative contact positions, the bodies' world inverse inertia, their inverse masses
+// and the contact basis only — none of which changes during adjustVelocities (contact.go:390-445 moves velocities, not
+// positions), so a caller may evaluate this once per contact and frame (VEL_PRE record below) instead of once per pick:
+// same expressions, same operands, same bits.
+enum VelPre : int { VP_IM = 0, VP_DV0 = 9, VP_DV3 = 10, VP_DV6 = 11, VP_NF = 12 };
+CZD void friction_response(const V3 rp[2], const M3 iit[2], const real invMass[2], bool two, const M3 &c2w, M3 &dv, M3 &im) {
+    real inverseMass = invMass[0];
+    M3 itt;
+    set_skew(itt, rp[0]);
+    M3 dvw = m3_mul_m(itt, iit[0]);
+    dvw = m3_mul_m(dvw, itt);
+#pragma unroll
+    for (int k = 0; k < 9; k++) dvw.c[k] *= R_(-1.0);
+    if (two) {
+        set_skew(itt, rp[1]);
+        M3 dvw2 = m3_mul_m(itt, iit[1]);
+        dvw2 = m3_mul_m(dvw2, itt);
+#pragma unroll
+        for (int k = 0; k < 9; k++) dvw2.c[k] *= R_(-1.0);
+#pragma unroll
+        for (int k = 0; k < 9; k++) dvw.c[k] += dvw2.c[k];
+        inverseMass += invMass[1];
+    }
+    dv = m3_transpose(c2w);
+    dv = m3_mul_m(dv, dvw);
+    dv = m3_mul_m(dv, c2w);
+    dv.c[0] += inverseMass; dv.c[4] += inverseMass; dv.c[8] += inverseMass;
+    im = m3_invert(dv);
+}
+CZD M3 contact_to_world(const V3 &n, const V3 &ty, const V3 &tz) {   // columns (n, ty, tz)  (SetComponents math/matrix.go:52)
+    M3 c2w;
+    c2w.c[0] = n.c[0]; c2w.c[1] = n.c[1]; c2w.c[2] = n.c[2];
+    c2w.c[3] = ty.c[0]; c2w.c[4] = ty.c[1]; c2w.c[5] = ty.c[2];
+    c2w.c[6] = tz.c[0]; c2w.c[7] = tz.c[1]; c2w.c[8] = tz.c[2];
+    return c2w;
+}
+// the VEL_PRE record of contact c (12 reals): friction_response evaluated ahead of the loop
+CZD void precompute_velocity_response(const Ctx &x, int c, real *pre) {
+    const int b0 = x.cb0[c], b1 = x.cb1[c];
+    const V3 rp[2] = {cw3(x, CW_RP0, c), cw3(x, CW_RP1, c)};
+    M3 iit[2];
+    real invMass[2] = {R_(0), R_(0)};
+    iit[0] = bw_iitw(x, b0);
+    invMass[0] = x.bw[BW_INVM * x.bs + b0];
+#pragma unroll
+    for (int k = 0; k < 9; k++) iit[1].c[k] = R_(0);
+    if (b1 >= 0) { iit[1] = bw_iitw(x, b1); invMass[1] = x.bw[BW_INVM * x.bs + b1]; }
+    const M3 c2w = contact_to_world(cw3(x, CW_N, c), cw3(x, CW_TY, c), cw3(x, CW_TZ, c));
+    M3 dv, im;
+    friction_response(rp, iit, invMass, b1 >= 0, c2w, dv, im);
+#pragma unroll
+    for (int k = 0; k < 9; k++) pre[VP_IM + k] = im.c[k];
+    pre[VP_DV0] = dv.c[0]; pre[VP_DV3] = dv.c[3]; pre[VP_DV6] = dv.c[6];
+}
+
+// pre: the contact's VEL_PRE record or NULL (evaluate the response here)
+CZD void resolve_velocity(const Ctx &x, int c, Change &ch, VelCommit &vc, const real *pre = nullptr) {
     int b[2] = {x.cb0[c], x.cb1[c]};
     V3 n = cw3(x, CW_N, c), ty = cw3(x, CW_TY, c), tz = cw3(x, CW_TZ, c);
     V3 rp[2] = {cw3(x, CW_RP0, c), cw3(x, CW_RP1, c)};
@@ -337,10 +396,7 @@ CZD void resolve_velocity(const Ctx &x, int c, Change &ch, VelCommit &vc) {
         vc.vel[i] = bw3(x, BW_VEL, b[i]);
         vc.rot[i] = bw3(x, BW_ROT, b[i]);
     }
-    M3 c2w;   // contactToWorld, columns (n, ty, tz)  (SetComponents math/matrix.go:52)
-    c2w.c[0] = n.c[0]; c2w.c[1] = n.c[1]; c2w.c[2] = n.c[2];
-    c2w.c[3] = ty.c[0]; c2w.c[4] = ty.c[1]; c2w.c[5] = ty.c[2];
-    c2w.c[6] = tz.c[0]; c2w.c[7] = tz.c[1]; c2w.c[8] = tz.c[2];
+    const M3 c2w = contact_to_world(n, ty, tz);
     V3 ic;
     if (friction == R_(0.0)) {
         // calculateFrictionlessImpulse :498-531 (second-body block is guarded by Bodies[1]==nil
@@ -354,35 +410,24 @@ CZD void resolve_velocity(const Ctx &x, int c, Change &ch, VelCommit &vc) {
         ic = mk3(rdiv(ddv, dv), R_(0), R_(0));
     } else {
         // calculateFrictionImpulse :535-606
-        real inverseMass = invMass[0];
-        M3 itt;
-        set_skew(itt, rp[0]);
-        M3 dvw = m3_mul_m(itt, iit[0]);
-        dvw = m3_mul_m(dvw, itt);
+        M3 im;
+        real dv0, dv3, dv6;
+        if (pre) {
 #pragma unroll
-        for (int k = 0; k < 9; k++) dvw.c[k] *= R_(-1.0);
-        if (b[1] >= 0) {
-            set_skew(itt, rp[1]);
-            M3 dvw2 = m3_mul_m(itt, iit[1]);
-            dvw2 = m3_mul_m(dvw2, itt);
-#pragma unroll
-            for (int k = 0; k < 9; k++) dvw2.c[k] *= R_(-1.0);
-#pragma unroll
-            for (int k = 0; k < 9; k++) dvw.c[k] += dvw2.c[k];
-            inverseMass += invMass[1];
+            for (int k = 0; k < 9; k++) im.c[k] = pre[VP_IM + k];
+            dv0 = pre[VP_DV0]; dv3 = pre[VP_DV3]; dv6 = pre[VP_DV6];
+        } else {
+            M3 dv;
+            friction_response(rp, iit, invMass, b[1] >= 0, c2w, dv, im);
+            dv0 = dv.c[0]; dv3 = dv.c[3]; dv6 = dv.c[6];
         }
-        M3 dv = m3_transpose(c2w);
-        dv = m3_mul_m(dv, dvw);
-        dv = m3_mul_m(dv, c2w);
-        dv.c[0] += inverseMass; dv.c[4] += inverseMass; dv.c[8] += inverseMass;
-        M3 im = m3_invert(dv);
         V3 velKill = mk3(ddv, -cv.c[1], -cv.c[2]);
         ic = m3_mul_v(im, velKill);
         real planar = rsqrt_(ic.c[1] * ic.c[1] + ic.c[2] * ic.c[2]);
         if (planar > ic.c[0] * friction) {
             ic.c[1] = rdiv(ic.c[1], planar);
             ic.c[2] = rdiv(ic.c[2], planar);
-            ic.c[0] = dv.c[0] + dv.c[3] * friction * ic.c[1] + dv.c[6] * friction * ic.c[2];
+            ic.c[0] = dv0 + dv3 * friction * ic.c[1] + dv6 * friction * ic.c[2];
             ic.c[0] = rdiv(ddv, ic.c[0]);
             ic.c[1] *= friction * ic.c[0];
             ic.c[2] *= friction * ic.c[0];
@@ -414,8 +459,9 @@ CZD void commit_velocity(const Ctx &x, const VelCommit &vc) {
         bw3_set(x, BW_ROT, vc.b[1], vc.rot[1]);
     }
     if (vc.wake >= 0) {
-        x.bw[BW_AWAKE * x.bs + vc.b[vc.wake]] = R_(1);
-        x.bw[BW_MOTION * x.bs + vc.b[vc.wake]] = R_(0.6);
+        const int wb = vc.wake == 0 ? vc.b[0] : vc.b[1];
+        x.bw[BW_AWAKE * x.bs + wb] = R_(1);
+        x.bw[BW_MOTION * x.bs + wb] = R_(0.6);
     }
 }
 
@@ -463,6 +509,25 @@ __device__ __forceinline__ void warp_argmax(real &v, int &i, unsigned mask) {
         int oi = __shfl_xor_sync(mask, i, o);
         argmax_combine(v, i, ov, oi);
     }
+}
+// The same arg-max over a full warp for values that are positive and not NaN (the owners' caches of the large-world
+// loop: a cached value is > epsilon, or the epsilon sentinel itself): IEEE order equals the order of the raw bits, so
+// three (float: two) redux.sync replace five rounds of 64-bit shuffles and compares.
+__device__ __forceinline__ void warp_argmax_positive(real &v, int &i) {
+    const unsigned full = 0xffffffffu;
+#ifdef CUBEZ_REAL_FLOAT
+    const unsigned key = __float_as_uint(v);
+    const unsigned mk = __reduce_max_sync(full, key);
+    i = __reduce_min_sync(full, key == mk ? i : 0x7fffffff);
+    v = __uint_as_float(mk);
+#else
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
+    const unsigned hi = (unsigned)(bits >> 32), lo = (unsigned)bits;
+    const unsigned mh = __reduce_max_sync(full, hi);
+    const unsigned ml = __reduce_max_sync(full, hi == mh ? lo : 0u);
+    i = __reduce_min_sync(full, (hi == mh && lo == ml) ? i : 0x7fffffff);
+    v = __longlong_as_double((long long)(((unsigned long long)mh << 32) | ml));
+#endif
 }
 // Per-body contact bitmasks for worlds with at most 64 contacts: mask[b] has bit c set when contact c
 // touches body b.  Called by the NT lanes that own the world, after the contact body ids are final
@@ -922,7 +987,7 @@ __device__ __forceinline__ void big_rescan_owner(const BigShared &sh, int nC, in
         const real hv = sh.hot[c];
         if (hv > v) { v = hv; i = c; }
     }
-    warp_argmax<32>(v, i, 0xffffffffu);
+    warp_argmax_positive(v, i);
     if (lane == 0) { sh.cacheV[o] = v; sh.cacheI[o] = i; sh.dirty[o] = 0; }
 }
 
@@ -933,7 +998,8 @@ struct BigBroadcast {   // warp 0 -> everyone, once per iteration
 };
 
 template <int NT, bool VELOCITY>
-__device__ __forceinline__ int resolve_loop_big(const Ctx &x0, int maxIterations, GroupScratch *gs, BigBroadcast *bb, int tid, int *status, const BigShared &sh) {
+__device__ __forceinline__ int resolve_loop_big(const Ctx &x0, int maxIterations, GroupScratch *gs, BigBroadcast *bb, int tid, int *status, const BigShared &sh,
+                                                real *velPre /* [nC][VP_NF] scratch or NULL */) {
     static_assert(NT >= 64 && (NT & (NT - 1)) == 0, "owner = contact mod NT");
     const int lane = tid & 31, warp = tid >> 5;
     const unsigned full = 0xffffffffu;
@@ -942,6 +1008,13 @@ __device__ __forceinline__ int resolve_loop_big(const Ctx &x0, int maxIterations
     for (int c = tid; c < x.nC; c += NT) sh.hot[c] = gHot[c];
     if (VELOCITY) x.ddv = sh.hot; else x.pen = sh.hot;
     sh.dirty[tid] = 0;
+    if (VELOCITY && velPre) {
+        // the 3x3 response matrix of every contact and its inverse are constants of this loop (see friction_response):
+        // evaluated here by all threads, once per contact, instead of by warp 0 once per pick (4 matrix products, a
+        // determinant, a division — the longest dependent chain of the serial resolve)
+        for (int c = tid; c < x.nC; c += NT)
+            if (ctx_friction(x, c) != R_(0.0)) precompute_velocity_response(x, c, velPre + (size_t)c * VP_NF);
+    }
     __syncthreads();
     {   // every thread is an owner: initial cache
         real v = R_(0.01);
@@ -958,12 +1031,12 @@ __device__ __forceinline__ int resolve_loop_big(const Ctx &x0, int maxIterations
         // ---- worst contact: block arg-max of the owners' caches ------------------------------------------------
         real best = sh.cacheV[tid];
         int idx = sh.cacheI[tid];
-        warp_argmax<32>(best, idx, full);
+        warp_argmax_positive(best, idx);
         if (lane == 0) { gs->redv[warp] = best; gs->redi[warp] = idx; }
         __syncthreads();
         best = lane < NT / 32 ? gs->redv[lane] : R_(0.01);
         idx = lane < NT / 32 ? gs->redi[lane] : 0x7fffffff;
-        warp_argmax<32>(best, idx, full);
+        warp_argmax_positive(best, idx);
         if (idx == 0x7fffffff) break;
         // ---- the contacts the winner's change will reach: the adjacency lists of its bodies --------------------
         const int wb0 = x.cb0[idx], wb1 = x.cb1[idx];
@@ -984,7 +1057,7 @@ __device__ __forceinline__ int resolve_loop_big(const Ctx &x0, int maxIterations
         if (warp == 0) {
             PosCommit pc;
             VelCommit vc;
-            if (VELOCITY) resolve_velocity(x, idx, ch, vc);
+            if (VELOCITY) resolve_velocity(x, idx, ch, vc, velPre ? velPre + (size_t)idx * VP_NF : nullptr);
             else resolve_position(x, idx, best, ch, pc);
             __syncwarp();
             if (lane == 0) {
@@ -994,7 +1067,7 @@ __device__ __forceinline__ int resolve_loop_big(const Ctx &x0, int maxIterations
                 for (int k = 0; k < 3; k++) { bb->chg[k] = ch.lin[0].c[k]; bb->chg[3 + k] = ch.lin[1].c[k]; bb->chg[6 + k] = ch.ang[0].c[k]; bb->chg[9 + k] = ch.ang[1].c[k]; }
                 bb->chb[0] = ch.b[0]; bb->chb[1] = ch.b[1];
                 const int wk = VELOCITY ? vc.wake : pc.wake;
-                bb->wake = wk >= 0 ? ch.b[wk] : -1;
+                bb->wake = wk == 0 ? ch.b[0] : (wk == 1 ? ch.b[1] : -1);
             }
         }
         __syncthreads();

@@ -495,6 +495,7 @@ static int world_plan(cz_world *w) {
             CK(ctx, cudaMalloc(&w->rs.bw, sizeof(real) * (size_t)W * czr::BW_NF * B));
             CK(ctx, cudaMalloc(&w->rs.cw, sizeof(real) * (size_t)W * CW_NREAL * Cc));
             CK(ctx, cudaMalloc(&w->rs.cb, sizeof(int) * (size_t)W * 2 * Cc));
+            if (!czf::env_int("CUBEZ_RESOLVE_NO_PRE", 0)) CK(ctx, cudaMalloc(&w->rs.pre, sizeof(real) * (size_t)W * czr::VP_NF * Cc));
         }
     }
     // sort-based broadphase for one large world
@@ -638,7 +639,7 @@ int cz_world_destroy(cz_world *w) {
     if (w->snap.st.base) batch_free(w->snap);
     if (w->d_phase0) cudaFree(w->d_phase0);
     void *ptrs[] = {w->d_one, w->d_two, w->gen, w->gb0, w->gb1, w->nContacts, w->posIters, w->velIters, w->stats,
-                    w->tileCount, w->tileBase, w->hitCount, w->rs.bw, w->rs.cw, w->rs.cb, w->fused.cold, w->d_next, w->order3,
+                    w->tileCount, w->tileBase, w->hitCount, w->rs.bw, w->rs.cw, w->rs.cb, w->rs.pre, w->fused.cold, w->d_next, w->order3,
                     w->fused.coldW, w->fused.hotPen, w->fused.hotDdv, w->fused.hotCb0, w->fused.hotCb1, w->d_matFric, w->d_matRest, w->d_bodyMat, w->d_export};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (w->h_stats) cudaFreeHost(w->h_stats);
@@ -1630,6 +1631,278 @@ int cz_resolve_contacts(cz_ctx *ctx, int32_t max_iterations, cz_contacts *io, cz
     cz_world_destroy(w);
     return rc;
 }
+
+// ---- multi-GPU runs: worlds sharded over devices, one grouped ncclAllReduce at the end ---------------------------
+}  // extern "C"
+
+#include <dlfcn.h>
+namespace cznccl {   // the five NCCL entry points the run needs, resolved from libnccl.so.2 at run time (values of nccl.h 2.x)
+typedef struct ncclComm *comm_t;
+enum { Int64 = 4, Uint64 = 5, Float32 = 7, Float64 = 8, Sum = 0, Max = 2 };
+typedef int (*CommInitAll_t)(comm_t *, int, const int *);
+typedef int (*CommDestroy_t)(comm_t);
+typedef int (*AllReduce_t)(const void *, void *, size_t, int, int, comm_t, cudaStream_t);
+typedef int (*Group_t)(void);
+typedef const char *(*ErrStr_t)(int);
+struct Api {
+    void *lib = nullptr;
+    CommInitAll_t CommInitAll = nullptr;
+    CommDestroy_t CommDestroy = nullptr;
+    AllReduce_t AllReduce = nullptr;
+    Group_t GroupStart = nullptr, GroupEnd = nullptr;
+    ErrStr_t GetErrorString = nullptr;
+    bool ok() const { return CommInitAll && CommDestroy && AllReduce && GroupStart && GroupEnd; }
+};
+static Api &api() {
+    static Api a;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        for (const char *name : {"libnccl.so.2", "libnccl.so"}) {
+            a.lib = dlopen(name, RTLD_NOW | RTLD_LOCAL);
+            if (a.lib) break;
+        }
+        if (!a.lib) return;
+        a.CommInitAll = (CommInitAll_t)dlsym(a.lib, "ncclCommInitAll");
+        a.CommDestroy = (CommDestroy_t)dlsym(a.lib, "ncclCommDestroy");
+        a.AllReduce = (AllReduce_t)dlsym(a.lib, "ncclAllReduce");
+        a.GroupStart = (Group_t)dlsym(a.lib, "ncclGroupStart");
+        a.GroupEnd = (Group_t)dlsym(a.lib, "ncclGroupEnd");
+        a.GetErrorString = (ErrStr_t)dlsym(a.lib, "ncclGetErrorString");
+    });
+    return a;
+}
+}  // namespace cznccl
+
+struct cz_run {
+    struct Shard {
+        int device = 0;
+        cz_ctx *ctx = nullptr;
+        cz_world *world = nullptr;
+        int first = 0, count = 0;
+        cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+        bool timing = false;
+        long long steps = 0;
+        // reduce buffers on the shard's device: [0] u64 checksum | [1] f64 energy | [2..5] i64 world-steps, contacts, pos, vel | [6] f32 ms
+        unsigned long long *dRed = nullptr;
+    };
+    std::vector<Shard> shards;
+    cz_world_desc desc{};
+    bool distinct = true;                 // every shard on its own device -> NCCL
+    std::vector<cznccl::comm_t> comms;
+    std::string err;
+};
+static int run_fail(cz_run *r, int code, const std::string &msg) {
+    g_err = msg;
+    if (r) r->err = msg;
+    return code;
+}
+// the slice of a whole-batch cz_bodies / cz_colliders that belongs to a shard
+template <class T> static inline T *adv(T *p, long long n) { return p ? p + n : nullptr; }
+static cz_bodies slice_bodies(const cz_bodies &a, long long first, long long n) {
+    cz_bodies s = a;
+    s.n = (int32_t)n;
+    s.position = adv(a.position, first * 3); s.orientation = adv(a.orientation, first * 4); s.velocity = adv(a.velocity, first * 3);
+    s.rotation = adv(a.rotation, first * 3); s.acceleration = adv(a.acceleration, first * 3); s.linear_damping = adv(a.linear_damping, first);
+    s.angular_damping = adv(a.angular_damping, first); s.inverse_inertia_tensor = adv(a.inverse_inertia_tensor, first * 9);
+    s.inverse_mass = adv(a.inverse_mass, first); s.motion = adv(a.motion, first); s.is_awake = adv(a.is_awake, first); s.can_sleep = adv(a.can_sleep, first);
+    s.transform = adv(a.transform, first * 12); s.inverse_inertia_tensor_world = adv(a.inverse_inertia_tensor_world, first * 9);
+    s.last_frame_acceleration = adv(a.last_frame_acceleration, first * 3);
+    return s;
+}
+static cz_colliders slice_colliders(const cz_colliders &a, long long first, long long n) {
+    cz_colliders s = a;
+    s.n = (int32_t)n;
+    s.shape = adv(a.shape, first); s.body = adv(a.body, first); s.offset = adv(a.offset, first * 12); s.transform = adv(a.transform, first * 12);
+    s.half_size = adv(a.half_size, first * 3); s.radius = adv(a.radius, first);
+    return s;
+}
+
+extern "C" {
+
+const char *cz_run_last_error(cz_run *r) { return r ? r->err.c_str() : g_err.c_str(); }
+
+int cz_run_destroy(cz_run *r) {
+    if (!r) return CZ_ERR_INVALID;
+    for (auto &c : r->comms) if (c) { cznccl::api().CommDestroy(c); }
+    for (auto &s : r->shards) {
+        if (s.ctx) cudaSetDevice(s.device);
+        if (s.world) cz_world_destroy(s.world);
+        if (s.ev0) cudaEventDestroy(s.ev0);
+        if (s.ev1) cudaEventDestroy(s.ev1);
+        if (s.dRed) cudaFree(s.dRed);
+        if (s.ctx) cz_shutdown(s.ctx);
+    }
+    delete r;
+    return CZ_OK;
+}
+
+int cz_run_create(int32_t n_shards, const int32_t *devices, const cz_world_desc *desc, cz_run **out) {
+    if (!out || !desc || n_shards <= 0 || n_shards > 64 || desc->n_worlds < n_shards) return run_fail(nullptr, CZ_ERR_INVALID, "cz_run_create: bad argument (1..64 shards, at least one world per shard)");
+    *out = nullptr;
+    cz_run *r = new cz_run;
+    r->desc = *desc;
+    r->shards.resize(n_shards);
+    const long long W = desc->n_worlds;
+    for (int k = 0; k < n_shards; k++) {
+        auto &s = r->shards[k];
+        s.device = devices ? devices[k] : k;
+        for (int j = 0; j < k; j++) if (r->shards[j].device == s.device) r->distinct = false;
+        s.first = (int)(W * k / n_shards);
+        s.count = (int)(W * (k + 1) / n_shards) - s.first;
+        int rc = cz_init(s.device, &s.ctx);
+        if (rc) { std::string e = g_err; cz_run_destroy(r); return run_fail(nullptr, rc, "cz_run_create: shard " + std::to_string(k) + ": " + e); }
+        cz_world_desc d = *desc;
+        d.n_worlds = s.count;
+        rc = cz_world_create(s.ctx, &d, &s.world);
+        if (rc) { std::string e = s.ctx->err; cz_run_destroy(r); return run_fail(nullptr, rc, "cz_run_create: shard " + std::to_string(k) + ": " + e); }
+        if (cudaEventCreate(&s.ev0) != cudaSuccess || cudaEventCreate(&s.ev1) != cudaSuccess || cudaMalloc(&s.dRed, sizeof(unsigned long long) * 8) != cudaSuccess) {
+            cz_run_destroy(r);
+            return run_fail(nullptr, CZ_ERR_CUDA, "cz_run_create: event / buffer allocation failed");
+        }
+    }
+    if (n_shards > 1 && r->distinct) {
+        cznccl::Api &nc = cznccl::api();
+        if (!nc.ok()) { cz_run_destroy(r); return run_fail(nullptr, CZ_ERR_CUDA, "cz_run_create: libnccl.so.2 could not be loaded (needed to reduce over more than one device)"); }
+        std::vector<int> devs;
+        for (auto &s : r->shards) devs.push_back(s.device);
+        r->comms.assign(n_shards, nullptr);
+        const int e = nc.CommInitAll(r->comms.data(), n_shards, devs.data());
+        if (e != 0) {
+            std::string msg = std::string("ncclCommInitAll: ") + (nc.GetErrorString ? nc.GetErrorString(e) : "error");
+            r->comms.clear();
+            cz_run_destroy(r);
+            return run_fail(nullptr, CZ_ERR_CUDA, msg);
+        }
+    }
+    *out = r;
+    return CZ_OK;
+}
+
+int cz_run_shard(cz_run *r, int32_t k, cz_world **world, int32_t *first_world, int32_t *n_worlds) {
+    if (!r || k < 0 || k >= (int)r->shards.size()) return run_fail(r, CZ_ERR_INVALID, "cz_run_shard: no such shard");
+    if (world) *world = r->shards[k].world;
+    if (first_world) *first_world = r->shards[k].first;
+    if (n_worlds) *n_worlds = r->shards[k].count;
+    return CZ_OK;
+}
+#define RUN_EACH(call)                                                                                                      \
+    for (auto &s : r->shards) {                                                                                             \
+        const int rc__ = (call);                                                                                            \
+        if (rc__) return run_fail(r, rc__, s.ctx->err);                                                                     \
+    }
+int cz_run_upload_bodies(cz_run *r, const cz_bodies *all, int32_t derive) {
+    if (!r || !all) return CZ_ERR_INVALID;
+    const long long B = r->desc.bodies_per_world;
+    if (all->n != (long long)r->desc.n_worlds * B) return run_fail(r, CZ_ERR_INVALID, "cz_run_upload_bodies: all->n must cover every world of the run");
+    RUN_EACH(([&] { cz_bodies b = slice_bodies(*all, s.first * B, s.count * B); return cz_world_upload_bodies(s.world, 0, s.count, &b, derive); })());
+    return CZ_OK;
+}
+int cz_run_upload_colliders(cz_run *r, const cz_colliders *all, int32_t derive) {
+    if (!r || !all) return CZ_ERR_INVALID;
+    const long long B = r->desc.bodies_per_world;
+    if (all->n != (long long)r->desc.n_worlds * B) return run_fail(r, CZ_ERR_INVALID, "cz_run_upload_colliders: all->n must cover every world of the run");
+    RUN_EACH(([&] { cz_colliders c = slice_colliders(*all, s.first * B, s.count * B); return cz_world_upload_colliders(s.world, 0, s.count, &c, derive); })());
+    return CZ_OK;
+}
+int cz_run_upload_planes(cz_run *r, const cz_planes *p) {
+    if (!r || !p) return CZ_ERR_INVALID;
+    RUN_EACH(cz_world_upload_planes(s.world, p));
+    return CZ_OK;
+}
+int cz_run_set_episodes(cz_run *r, int32_t length, const int32_t *phase0) {
+    if (!r) return CZ_ERR_INVALID;
+    RUN_EACH(cz_world_set_episodes(s.world, length, phase0 ? phase0 + s.first : nullptr));
+    return CZ_OK;
+}
+int cz_run_step(cz_run *r, cz_real dt, int32_t n_steps) {
+    if (!r || n_steps < 0) return CZ_ERR_INVALID;
+    for (auto &s : r->shards) {
+        if (s.timing) continue;
+        if (cudaSetDevice(s.device) != cudaSuccess || cudaEventRecord(s.ev0, s.ctx->stream) != cudaSuccess) return run_fail(r, CZ_ERR_CUDA, "cz_run_step: event record failed");
+        s.timing = true;
+    }
+    // a few frames per shard and round: every device has work queued before the host goes on enqueueing for the first
+    const int chunk = 8;
+    for (int done = 0; done < n_steps; done += chunk) {
+        const int n = std::min(chunk, n_steps - done);
+        RUN_EACH(cz_world_step(s.world, dt, n, nullptr));
+    }
+    for (auto &s : r->shards) {
+        s.steps += n_steps;
+        if (cudaSetDevice(s.device) != cudaSuccess || cudaEventRecord(s.ev1, s.ctx->stream) != cudaSuccess) return run_fail(r, CZ_ERR_CUDA, "cz_run_step: event record failed");
+    }
+    return CZ_OK;
+}
+int cz_run_finish(cz_run *r, cz_run_totals *out) {
+    if (!r || !out) return CZ_ERR_INVALID;
+    std::memset(out, 0, sizeof(*out));
+    const int n = (int)r->shards.size();
+    struct Part { unsigned long long checksum; double energy; long long c[4]; float ms; };
+    std::vector<Part> part(n);
+    for (int k = 0; k < n; k++) {
+        auto &s = r->shards[k];
+        cz_ctx *ctx = s.ctx;
+        if (cudaSetDevice(s.device) != cudaSuccess) return run_fail(r, CZ_ERR_CUDA, "cudaSetDevice failed");
+        int rc = cz_world_synchronize(s.world);                       // also surfaces a sticky device-side error of the asynchronous steps
+        if (rc) return run_fail(r, rc, "shard " + std::to_string(k) + ": " + ctx->err);
+        uint64_t cks = 0;
+        double en = 0;
+        if ((rc = cz_world_checksum_energy(s.world, &cks, &en))) return run_fail(r, rc, ctx->err);
+        unsigned long long h[ST_N];
+        if (cudaMemcpy(h, s.world->stats, sizeof(h), cudaMemcpyDeviceToHost) != cudaSuccess ||
+            cudaMemset(s.world->stats, 0, sizeof(unsigned long long) * ST_STATUS) != cudaSuccess) return run_fail(r, CZ_ERR_CUDA, "reading the shard counters failed");
+        float ms = 0;
+        if (s.timing) cudaEventElapsedTime(&ms, s.ev0, s.ev1);
+        part[k] = Part{cks, en, {(long long)s.count * s.steps, (long long)h[ST_CONTACTS], (long long)h[ST_POS], (long long)h[ST_VEL]}, ms};
+        s.timing = false;
+        s.steps = 0;
+    }
+    out->n_shards = n;
+    if (!r->comms.empty()) {
+        // ONE grouped all-reduce over the single-process communicator: every shard contributes its partial sums from a
+        // buffer on its own device and receives the totals
+        cznccl::Api &nc = cznccl::api();
+        for (int k = 0; k < n; k++) {
+            auto &s = r->shards[k];
+            unsigned long long buf[8] = {0};
+            buf[0] = part[k].checksum;
+            std::memcpy(&buf[1], &part[k].energy, 8);
+            for (int j = 0; j < 4; j++) buf[2 + j] = (unsigned long long)part[k].c[j];
+            std::memcpy(&buf[6], &part[k].ms, 4);
+            if (cudaSetDevice(s.device) != cudaSuccess || cudaMemcpyAsync(s.dRed, buf, sizeof(buf), cudaMemcpyHostToDevice, s.ctx->stream) != cudaSuccess)
+                return run_fail(r, CZ_ERR_CUDA, "staging the reduce buffers failed");
+        }
+        int e = nc.GroupStart();
+        for (int k = 0; k < n && e == 0; k++) {
+            auto &s = r->shards[k];
+            e = nc.AllReduce(s.dRed + 0, s.dRed + 0, 1, cznccl::Uint64, cznccl::Sum, r->comms[k], s.ctx->stream);
+            if (!e) e = nc.AllReduce(s.dRed + 1, s.dRed + 1, 1, cznccl::Float64, cznccl::Sum, r->comms[k], s.ctx->stream);
+            if (!e) e = nc.AllReduce(s.dRed + 2, s.dRed + 2, 4, cznccl::Int64, cznccl::Sum, r->comms[k], s.ctx->stream);
+            if (!e) e = nc.AllReduce(s.dRed + 6, s.dRed + 6, 1, cznccl::Float32, cznccl::Max, r->comms[k], s.ctx->stream);
+        }
+        const int e2 = nc.GroupEnd();
+        if (e || e2) return run_fail(r, CZ_ERR_CUDA, std::string("ncclAllReduce: ") + (nc.GetErrorString ? nc.GetErrorString(e ? e : e2) : "error"));
+        unsigned long long buf[8];
+        auto &s0 = r->shards[0];
+        if (cudaSetDevice(s0.device) != cudaSuccess || cudaMemcpyAsync(buf, s0.dRed, sizeof(buf), cudaMemcpyDeviceToHost, s0.ctx->stream) != cudaSuccess ||
+            cudaStreamSynchronize(s0.ctx->stream) != cudaSuccess) return run_fail(r, CZ_ERR_CUDA, "reading the reduced totals failed");
+        for (int k = 1; k < n; k++) { cudaSetDevice(r->shards[k].device); cudaStreamSynchronize(r->shards[k].ctx->stream); }
+        out->checksum = buf[0];
+        std::memcpy(&out->energy, &buf[1], 8);
+        out->world_steps = (int64_t)buf[2]; out->contacts = (int64_t)buf[3]; out->pos_iterations = (int64_t)buf[4]; out->vel_iterations = (int64_t)buf[5];
+        std::memcpy(&out->max_device_ms, &buf[6], 4);
+        out->used_nccl = 1;
+    } else {
+        for (int k = 0; k < n; k++) {
+            out->checksum += part[k].checksum;
+            out->energy += part[k].energy;
+            out->world_steps += part[k].c[0]; out->contacts += part[k].c[1]; out->pos_iterations += part[k].c[2]; out->vel_iterations += part[k].c[3];
+            out->max_device_ms = std::max(out->max_device_ms, part[k].ms);
+        }
+    }
+    return CZ_OK;
+}
+#undef RUN_EACH
 
 // ---- microbench / diagnostics --------------------------------------------------------------
 int cz_bench_integrate(cz_ctx *ctx, int64_t n, uint64_t seed, int32_t warmup, int32_t steps, cz_real dt, float *avg_ms, uint64_t *checksum) {

@@ -1,17 +1,26 @@
-// Package cubez is a drop-in for github.com/tbogdala/cubez whose per-step pipeline runs on
-// libcubezcuda (B200, sm_100a) through cgo.  Exported identifiers, field names and call
-// semantics are the reference's (rigidbody.go, colliders.go, contact.go); the math value types
-// are the reference's own pure-Go package.  A batched-world handle (World) is added.
+// Package cubez is a drop-in for github.com/tbogdala/cubez whose per-step pipeline runs on libcubezcuda (B200,
+// sm_100a) through cgo.  Exported identifiers, field names and call semantics are the reference's (rigidbody.go,
+// colliders.go, contact.go); the math value types are the reference's own pure-Go package.  Added: the batched-world
+// handle (World, world.go) and multi-GPU runs (Run, run.go).
 //
-// SOURCE ONLY: no Go toolchain exists in the build image, so this file has never been compiled.
-// It is the binding a maintainer would add; INTEGRATION.md walks through it.
+// There is NO CPU fallback: Init panics without a CUDA device, and every call goes to the library.
 //
-// Build: CGO_CFLAGS=-I<repo>/include CGO_LDFLAGS="-L<repo>/cubez_b200/lib -lcubezcuda -lcudart"
-//        (float32: -tags cubez_f32, links -lcubezcuda_f32 and needs math.Real = float32).
+// Files: cubez.go (context, RigidBody, marshalling) · colliders.go (colliders, CheckForCollisions) · contact.go
+// (Contact, ResolveContacts) · world.go (cz_world_*) · run.go (cz_run_*) · real_f64.go / real_f32.go (precision).
+//
+// Cost model — read before porting a loop: every object-API call (body.Integrate, CheckForCollisions,
+// ResolveContacts) is one upload + kernel + download, about 0.7 ms; the reference's body.Integrate is ~100 ns.
+// The object API exists for drop-in correctness; throughput comes from the batch entry points (IntegrateBodies,
+// CheckCollisionList) and above all from World, which keeps the state on the device.
+//
+// Compiled by nobody here: the build image has no Go toolchain (tests/test_go_binding.py checks every C.cz_* call
+// against include/cubezcuda.h by name and arity instead).
+//
+//	CGO_CFLAGS=-I<repo>/include CGO_LDFLAGS="-L<repo>/cubez_b200/lib" go build            (float64)
+//	... go build -tags cubez_f32    (float32: links libcubezcuda_f32 and needs math.Real = float32, see real_f32.go)
 package cubez
 
 /*
-#cgo LDFLAGS: -lcubezcuda -lcudart
 #include <stdlib.h>
 #include "cubezcuda.h"
 */
@@ -29,14 +38,60 @@ var ctx *C.cz_ctx
 
 // Init binds the package to a CUDA device.  There is no CPU fallback: it panics without one.
 func Init(device int) {
+	if int(C.cz_real_size()) != int(unsafe.Sizeof(m.Real(0))) {
+		panic("cubez: math.Real and the linked libcubezcuda disagree on the precision (build tag cubez_f32?)")
+	}
 	if rc := C.cz_init(C.int(device), &ctx); rc != 0 {
 		panic("cubez: " + C.GoString(C.cz_last_error(nil)))
 	}
 }
 
+// Shutdown releases the device context.
+func Shutdown() {
+	if ctx != nil {
+		C.cz_shutdown(ctx)
+		ctx = nil
+	}
+}
+
+// Synchronize waits for everything queued on the context's stream.
+func Synchronize() { check(C.cz_ctx_synchronize(ctx)) }
+
+// Stream is the cudaStream_t the context launches on (for interop with other CUDA code).
+func Stream() unsafe.Pointer { return C.cz_ctx_stream(ctx) }
+
 func check(rc C.int) {
 	if rc != 0 { // the reference has no error returns; failures are panics (contact.go:512-523)
 		panic("cubez: " + C.GoString(C.cz_last_error(ctx)))
+	}
+}
+
+// PinnedReals returns a []m.Real backed by page-locked host memory (cz_host_alloc): buffers of World.StepHost /
+// StepRL that the DMA engines read and write directly.  Release with FreePinned.
+func PinnedReals(count int) []m.Real {
+	var p unsafe.Pointer
+	check(C.cz_host_alloc(ctx, C.uint64_t(count)*C.uint64_t(unsafe.Sizeof(C.cz_real(0))), &p))
+	return unsafe.Slice((*m.Real)(p), count)
+}
+
+// PinnedBytes is PinnedReals for flag arrays (IsAwake, CanSleep).
+func PinnedBytes(count int) []uint8 {
+	var p unsafe.Pointer
+	check(C.cz_host_alloc(ctx, C.uint64_t(count), &p))
+	return unsafe.Slice((*uint8)(p), count)
+}
+
+// FreePinned releases a PinnedReals buffer.
+func FreePinned(buf []m.Real) {
+	if len(buf) > 0 {
+		check(C.cz_host_free(ctx, unsafe.Pointer(&buf[0])))
+	}
+}
+
+// FreePinnedBytes releases a PinnedBytes buffer.
+func FreePinnedBytes(buf []uint8) {
+	if len(buf) > 0 {
+		check(C.cz_host_free(ctx, unsafe.Pointer(&buf[0])))
 	}
 }
 
@@ -62,7 +117,7 @@ type RigidBody struct {
 func NewRigidBody() *RigidBody { // rigidbody.go:104-114
 	b := new(RigidBody)
 	b.Orientation.SetIdentity()
-	b.LinearDamping, b.AngularDamping = 0.95, 0.95
+	b.LinearDamping, b.AngularDamping = 0.95, 0.95 // :107-108 assigns defaultLinearDamping to both
 	b.Acceleration = m.Vector3{0.0, -9.78, 0.0}
 	b.inverseInertiaTensorWorld.SetIdentity()
 	b.CanSleep = true
@@ -80,7 +135,7 @@ func (b *RigidBody) GetInverseInertiaTensorWorld() m.Matrix3 { return b.inverseI
 func (b *RigidBody) SetInertiaTensor(t *m.Matrix3)           { b.InverseInertiaTensor = t.Invert() }
 func (b *RigidBody) AddVelocity(v *m.Vector3)                { b.Velocity.Add(v) }
 func (b *RigidBody) AddRotation(v *m.Vector3)                { b.Rotation.Add(v) }
-func (b *RigidBody) ClearAccumulators()                      {}
+func (b *RigidBody) ClearAccumulators()                      {} // the accumulators have no writer in the reference (rigidbody.go:86-92)
 func (b *RigidBody) GetMass() m.Real {
 	if b.inverseMass == 0 {
 		return m.MaxValue
@@ -97,15 +152,15 @@ func (b *RigidBody) SetAwake(awake bool) { // rigidbody.go:182-192
 	}
 }
 
-// flat is the cz_bodies SoA of a batch of bodies in C memory (no Go pointer crosses the boundary).
+// flat is the cz_bodies SoA of a batch of bodies in C memory (cgo: no Go pointer crosses the boundary).
 type flat struct {
-	n  int
-	c  C.cz_bodies
+	n   int
+	c   C.cz_bodies
 	mem []unsafe.Pointer
 }
 
 func (f *flat) alloc(n, comps int) *C.cz_real {
-	p := C.malloc(C.size_t(n * comps * C.sizeof_cz_real))
+	p := C.malloc(C.size_t(n*comps) * C.size_t(unsafe.Sizeof(C.cz_real(0))))
 	f.mem = append(f.mem, p)
 	return (*C.cz_real)(p)
 }
@@ -115,6 +170,12 @@ func (f *flat) free() {
 	}
 }
 func reals(p *C.cz_real, n int) []m.Real { return unsafe.Slice((*m.Real)(unsafe.Pointer(p)), n) }
+func b2u(v bool) uint8 {
+	if v {
+		return 1
+	}
+	return 0
+}
 
 func gather(bodies []*RigidBody) *flat {
 	n := len(bodies)
@@ -145,6 +206,8 @@ func gather(bodies []*RigidBody) *flat {
 	}
 	return f
 }
+
+// scatter mirrors what Integrate / ResolveContacts write back into the Go structs (SURVEY §8b).
 func (f *flat) scatter(bodies []*RigidBody) {
 	n := f.n
 	awake := unsafe.Slice((*uint8)(unsafe.Pointer(f.c.is_awake)), n)
@@ -159,19 +222,16 @@ func (f *flat) scatter(bodies []*RigidBody) {
 		b.motion, b.IsAwake = reals(f.c.motion, n)[i], awake[i] != 0
 	}
 }
-func b2u(v bool) uint8 {
-	if v {
-		return 1
-	}
-	return 0
-}
 
-// Integrate — rigidbody.go:213-259.  The three math.Pow results are evaluated HERE, in Go, and
+// Integrate — rigidbody.go:213-259.  The three math.Pow results (:233, :234, :250) are evaluated HERE, in Go, and
 // handed to the library, so they are bit-identical to what the reference computes.
 func (b *RigidBody) Integrate(duration m.Real) { IntegrateBodies([]*RigidBody{b}, duration) }
 
 // IntegrateBodies is the batch form (one upload, one kernel, one download).
 func IntegrateBodies(bodies []*RigidBody, duration m.Real) {
+	if len(bodies) == 0 {
+		return
+	}
 	runtime.LockOSThread()
 	defer runtime.UnlockOSThread()
 	f := gather(bodies)
@@ -193,245 +253,20 @@ func (b *RigidBody) CalculateDerivedData() {
 	defer f.free()
 	check(C.cz_calculate_derived_data(ctx, &f.c))
 	f.scatter([]*RigidBody{b})
-	copy(b.Orientation[:], reals(f.c.orientation, 4)) // Normalize() result
 }
 
-// ---------------------------------------------------------------------------------------------
-// Colliders — colliders.go:15-71.  CheckAgainst* forward to CheckForCollisions (cz_narrowphase).
-// ---------------------------------------------------------------------------------------------
-type Collider interface {
-	Clone() Collider
-	CalculateDerivedData()
-	GetBody() *RigidBody
-	GetTransform() m.Matrix3x4
-	CheckAgainstHalfSpace(plane *CollisionPlane, existingContacts []*Contact) (bool, []*Contact)
-	CheckAgainstSphere(sphere *CollisionSphere, existingContacts []*Contact) (bool, []*Contact)
-	CheckAgainstCube(secondCube *CollisionCube, existingContacts []*Contact) (bool, []*Contact)
+// MathOp runs one operation of the math layer on the device (cz_math_op; CZ_OP_* codes of cubezcuda.h) — the hook
+// the reference's math/*_test.go known answers are checked through.  in holds up to 24 reals, out receives up to 12.
+func MathOp(op int, in []m.Real) [12]m.Real {
+	var buf [24]m.Real
+	var out [12]m.Real
+	copy(buf[:], in)
+	cin := (*C.cz_real)(C.malloc(C.size_t(24) * C.size_t(unsafe.Sizeof(C.cz_real(0)))))
+	cout := (*C.cz_real)(C.malloc(C.size_t(12) * C.size_t(unsafe.Sizeof(C.cz_real(0)))))
+	defer C.free(unsafe.Pointer(cin))
+	defer C.free(unsafe.Pointer(cout))
+	copy(reals(cin, 24), buf[:])
+	check(C.cz_math_op(ctx, C.int32_t(op), cin, cout))
+	copy(out[:], reals(cout, 12))
+	return out
 }
-type CollisionPlane struct {
-	Normal m.Vector3
-	Offset m.Real
-}
-type CollisionCube struct {
-	Body      *RigidBody
-	Offset    m.Matrix3x4
-	transform m.Matrix3x4
-	HalfSize  m.Vector3
-}
-type CollisionSphere struct {
-	Body      *RigidBody
-	Offset    m.Matrix3x4
-	transform m.Matrix3x4
-	Radius    m.Real
-}
-
-func NewCollisionPlane(n m.Vector3, o m.Real) *CollisionPlane { return &CollisionPlane{n, o} }
-func NewCollisionCube(optBody *RigidBody, halfSize m.Vector3) *CollisionCube {
-	c := &CollisionCube{Body: optBody, HalfSize: halfSize}
-	c.Offset.SetIdentity()
-	if c.Body == nil {
-		c.Body = NewRigidBody()
-	}
-	return c
-}
-func NewCollisionSphere(optBody *RigidBody, radius m.Real) *CollisionSphere {
-	s := &CollisionSphere{Body: optBody, Radius: radius}
-	s.Offset.SetIdentity()
-	if s.Body == nil {
-		s.Body = NewRigidBody()
-	}
-	return s
-}
-func (p *CollisionPlane) Clone() Collider           { return NewCollisionPlane(p.Normal, p.Offset) }
-func (p *CollisionPlane) CalculateDerivedData()     {}
-func (p *CollisionPlane) GetBody() *RigidBody       { return nil }
-func (p *CollisionPlane) GetTransform() m.Matrix3x4 { var t m.Matrix3x4; t.SetIdentity(); return t }
-func (c *CollisionCube) GetBody() *RigidBody        { return c.Body }
-func (c *CollisionCube) GetTransform() m.Matrix3x4  { return c.transform }
-func (s *CollisionSphere) GetBody() *RigidBody      { return s.Body }
-func (s *CollisionSphere) GetTransform() m.Matrix3x4 { return s.transform }
-func (c *CollisionCube) Clone() Collider {
-	n := NewCollisionCube(c.Body.Clone(), c.HalfSize)
-	n.Offset, n.transform = c.Offset, c.transform
-	return n
-}
-func (s *CollisionSphere) Clone() Collider {
-	n := NewCollisionSphere(s.Body.Clone(), s.Radius)
-	n.Offset, n.transform = s.Offset, s.transform
-	return n
-}
-func derive(body *RigidBody, offset *m.Matrix3x4) (out m.Matrix3x4) { // colliders.go:173-176 / 302-304
-	check(C.cz_collider_derive(ctx, 1, (*C.cz_real)(unsafe.Pointer(&body.transform[0])), (*C.cz_real)(unsafe.Pointer(&offset[0])),
-		(*C.cz_real)(unsafe.Pointer(&out[0]))))
-	return
-}
-func (c *CollisionCube) CalculateDerivedData()   { c.transform = derive(c.Body, &c.Offset) }
-func (s *CollisionSphere) CalculateDerivedData() { s.transform = derive(s.Body, &s.Offset) }
-
-func (p *CollisionPlane) CheckAgainstHalfSpace(_ *CollisionPlane, e []*Contact) (bool, []*Contact) { return false, e }
-func (p *CollisionPlane) CheckAgainstSphere(s *CollisionSphere, e []*Contact) (bool, []*Contact)   { return CheckForCollisions(p, s, e) }
-func (p *CollisionPlane) CheckAgainstCube(c *CollisionCube, e []*Contact) (bool, []*Contact)       { return CheckForCollisions(p, c, e) }
-func (c *CollisionCube) CheckAgainstHalfSpace(p *CollisionPlane, e []*Contact) (bool, []*Contact)  { return CheckForCollisions(c, p, e) }
-func (c *CollisionCube) CheckAgainstSphere(s *CollisionSphere, e []*Contact) (bool, []*Contact)    { return CheckForCollisions(c, s, e) }
-func (c *CollisionCube) CheckAgainstCube(o *CollisionCube, e []*Contact) (bool, []*Contact)        { return CheckForCollisions(c, o, e) }
-func (s *CollisionSphere) CheckAgainstHalfSpace(p *CollisionPlane, e []*Contact) (bool, []*Contact) { return CheckForCollisions(s, p, e) }
-func (s *CollisionSphere) CheckAgainstSphere(o *CollisionSphere, e []*Contact) (bool, []*Contact)  { return CheckForCollisions(s, o, e) }
-func (s *CollisionSphere) CheckAgainstCube(c *CollisionCube, e []*Contact) (bool, []*Contact)      { return CheckForCollisions(s, c, e) }
-
-// Contact — contact.go:17-51 (public fields).
-type Contact struct {
-	Bodies                      [2]*RigidBody
-	Friction, Restitution       m.Real
-	ContactPoint, ContactNormal m.Vector3
-	Penetration                 m.Real
-}
-
-func NewContact() *Contact { return new(Contact) }
-
-// Check is one ordered (one, two) entry of a pair schedule.
-type Check struct{ One, Two Collider }
-
-// CheckForCollisions — colliders.go:720-747.
-func CheckForCollisions(one Collider, two Collider, existingContacts []*Contact) (bool, []*Contact) {
-	found, contacts := CheckCollisionList([]Check{{one, two}}, existingContacts)
-	return found[0], contacts
-}
-
-// CheckCollisionList evaluates an ordered list of checks in ONE library call; contacts are
-// appended in the order the reference's append calls would produce.
-func CheckCollisionList(checks []Check, existing []*Contact) ([]bool, []*Contact) {
-	// Flatten the pointer graph to indices (cgo: no Go pointers in C memory): colliders, planes,
-	// bodies are numbered in first-use order; see cubez_b200/api.py:check_collision_list for the
-	// same marshalling spelled out in Python.  cz_narrowphase fills body indices, point, normal,
-	// penetration, friction, restitution; they are mapped back to *RigidBody here.
-	panic("marshalling elided in this source-only sketch: see INTEGRATION.md §3")
-}
-
-// ResolveContacts — contact.go:208-222.
-func ResolveContacts(maxIterations int, contacts []*Contact, duration m.Real) {
-	if duration <= 0.0 || len(contacts) == 0 {
-		return
-	}
-	// bodies := unique non-nil bodies of contacts in first-use order -> gather()
-	// cz_contacts SoA <- contacts (body0/body1 indices, -1 for nil)
-	// C.cz_resolve_contacts(ctx, maxIterations, &cs, &f.c, duration, nil)
-	// scatter(): Position, Orientation, Velocity, Rotation, IsAwake, motion (+ transform and world
-	// inertia for bodies that were asleep, contact.go:380-382); contacts: Penetration, and Bodies /
-	// ContactNormal where Bodies[0] was nil (contact.go:61-65).
-	panic("marshalling elided in this source-only sketch: see INTEGRATION.md §3")
-}
-
-// ---------------------------------------------------------------------------------------------
-// World — the batched-world handle (new API).
-// ---------------------------------------------------------------------------------------------
-type World struct{ h *C.cz_world }
-
-func NewWorld(nWorlds, bodiesPerWorld, contactsPerWorld int, explicitSchedule bool) *World {
-	d := C.cz_world_desc{n_worlds: C.int32_t(nWorlds), bodies_per_world: C.int32_t(bodiesPerWorld), contacts_per_world: C.int32_t(contactsPerWorld)}
-	if explicitSchedule {
-		d.schedule = C.CZ_SCHED_EXPLICIT
-	}
-	w := new(World)
-	check(C.cz_world_create(ctx, &d, &w.h))
-	return w
-}
-
-// Step advances every world by n frames of updateCallback (examples/cubedrop.go:69-75).  One cgo
-// crossing per call amortises the ~100 ns cgo cost and the kernel launch over n frames.
-func (w *World) Step(dt m.Real, n int) C.cz_step_stats {
-	var st C.cz_step_stats
-	check(C.cz_world_step(w.h, C.cz_real(dt), C.int32_t(n), &st))
-	return st
-}
-func (w *World) ChecksumEnergy() (uint64, float64) {
-	var c C.uint64_t
-	var e C.double
-	check(C.cz_world_checksum_energy(w.h, &c, &e))
-	return uint64(c), float64(e)
-}
-// Observation is the part of the body state StepRL copies back each call; the slices view pinned
-// C memory (cz_host_alloc), so neither side copies.
-type Observation struct {
-	c                                          C.cz_bodies
-	Position, Orientation, Velocity, Rotation []m.Real
-}
-
-// NewObservation allocates pinned arrays for n bodies (position 3, orientation 4, velocity 3, rotation 3).
-func NewObservation(n int) *Observation {
-	o := new(Observation)
-	o.c.n = C.int32_t(n)
-	pin := func(count int) *C.cz_real {
-		var p unsafe.Pointer
-		check(C.cz_host_alloc(ctx, C.uint64_t(count)*C.uint64_t(unsafe.Sizeof(C.cz_real(0))), &p))
-		return (*C.cz_real)(p)
-	}
-	o.c.position, o.c.orientation, o.c.velocity, o.c.rotation = pin(3*n), pin(4*n), pin(3*n), pin(3*n)
-	o.Position, o.Orientation = reals(o.c.position, 3*n), reals(o.c.orientation, 4*n)
-	o.Velocity, o.Rotation = reals(o.c.velocity, 3*n), reals(o.c.rotation, 3*n)
-	return o
-}
-
-// PinnedReals returns a pinned []m.Real (action buffers of StepRL).
-func PinnedReals(count int) []m.Real {
-	var p unsafe.Pointer
-	check(C.cz_host_alloc(ctx, C.uint64_t(count)*C.uint64_t(unsafe.Sizeof(C.cz_real(0))), &p))
-	return reals((*C.cz_real)(p), count)
-}
-
-// StepRL is the RL loop's frame: AddVelocity(addVelocity[3i:]) and AddRotation(addRotation[3i:]) on every
-// body (rigidbody.go:195-202; either slice may be nil), n frames on the device, then obs filled.
-func (w *World) StepRL(addVelocity, addRotation []m.Real, obs *Observation, dt m.Real, n int) C.cz_step_stats {
-	var st C.cz_step_stats
-	var av, ar *C.cz_real
-	if addVelocity != nil {
-		av = (*C.cz_real)(unsafe.Pointer(&addVelocity[0]))
-	}
-	if addRotation != nil {
-		ar = (*C.cz_real)(unsafe.Pointer(&addRotation[0]))
-	}
-	var o *C.cz_bodies
-	if obs != nil {
-		o = &obs.c
-	}
-	check(C.cz_world_step_rl(w.h, av, ar, o, C.cz_real(dt), C.int32_t(n), &st))
-	return st
-}
-
-// SetMaterials replaces the hard-wired `c.Friction = 0.9` / `c.Restitution = 0.1` test constants
-// (colliders.go:199-202 and five more FIXME sites) by a table lookup: friction and restitution are
-// nMaterials x nMaterials tables, row = material of CheckForCollisions' `one`, column = `two`;
-// bodyMaterial holds one id per body of every world, planeMaterial one id per plane.
-// nMaterials = 0 restores the constants.
-func (w *World) SetMaterials(nMaterials int, friction, restitution []m.Real, nWorlds int, bodyMaterial, planeMaterial []int32) {
-	var f, r *C.cz_real
-	var bm, pm *C.int32_t
-	if nMaterials > 0 {
-		f, r = (*C.cz_real)(unsafe.Pointer(&friction[0])), (*C.cz_real)(unsafe.Pointer(&restitution[0]))
-	}
-	if bodyMaterial != nil {
-		bm = (*C.int32_t)(unsafe.Pointer(&bodyMaterial[0]))
-	}
-	if planeMaterial != nil {
-		pm = (*C.int32_t)(unsafe.Pointer(&planeMaterial[0]))
-	}
-	check(C.cz_world_set_materials(w.h, C.int32_t(nMaterials), f, r, 0, C.int32_t(nWorlds), bm, pm))
-}
-
-// ExportGL fills float32 Location (3 per body) and LocalRotation (4 per body: W, V[0], V[1], V[2]) of every body —
-// the per-frame SetGlVector3 / SetGlQuat copy of examples/cubedrop.go:35-37 and examples/exampleapp.go:146-159,
-// converted on the device.  model may be nil; otherwise it receives the body transform as a column-major 4x4.
-func (w *World) ExportGL(nWorlds int, location, rotation, model []float32) {
-	var l, q, md *C.float
-	if location != nil {
-		l = (*C.float)(unsafe.Pointer(&location[0]))
-	}
-	if rotation != nil {
-		q = (*C.float)(unsafe.Pointer(&rotation[0]))
-	}
-	if model != nil {
-		md = (*C.float)(unsafe.Pointer(&model[0]))
-	}
-	check(C.cz_world_export_gl(w.h, 0, C.int32_t(nWorlds), l, q, md, 0))
-}
-
-func (w *World) Close() { C.cz_world_destroy(w.h) }

@@ -285,6 +285,40 @@ int cz_world_step_host(cz_world *w, cz_bodies *io, cz_real dt, int32_t n_steps, 
 int cz_world_step_rl(cz_world *w, const cz_real *add_velocity, const cz_real *add_rotation, cz_bodies *obs, cz_real dt,
                      int32_t n_steps, cz_step_stats *stats);
 
+/* ---- multi-GPU runs of batched worlds (new API) -----------------------------------------------
+ * Worlds share no state, so a batch is partitioned by world index into contiguous shards, one per device: shard k
+ * of n owns worlds [k*W/n, (k+1)*W/n).  ONE host process drives every shard (each on its own stream of its own
+ * device); stepping exchanges nothing between devices.  cz_run_finish computes the checksum / energy per shard on
+ * its device and reduces {u64 checksum, f64 energy, i64 counters, f32 device time} over the shards with ONE grouped
+ * ncclAllReduce on a single-process communicator (ncclCommInitAll; libnccl.so.2 is loaded at cz_run_create, the
+ * library does not link against it).  Shards that share a device (n_shards devices not all distinct — useful on a
+ * one-GPU box) are reduced on the host instead and used_nccl reports 0. */
+typedef struct cz_run cz_run;
+typedef struct cz_run_totals {
+    uint64_t checksum;       /* FNV-1a-64 of every world's state, summed mod 2^64: identical for any shard count */
+    double energy;           /* total energy (summation order differs with the shard count: compare to 1e-9 relative) */
+    int64_t world_steps;     /* world-steps executed since the run was created or last finished */
+    int64_t contacts, pos_iterations, vel_iterations;
+    float max_device_ms;     /* slowest shard: CUDA events on its stream, first step enqueued -> last step done */
+    int32_t n_shards;
+    int32_t used_nccl;       /* 1: reduced by ncclAllReduce; 0: one shard, or shards sharing a device (host reduce) */
+} cz_run_totals;
+/* devices: n_shards device indices (NULL: 0 .. n_shards-1); desc->n_worlds is the TOTAL over all shards */
+int cz_run_create(int32_t n_shards, const int32_t *devices, const cz_world_desc *desc, cz_run **out);
+int cz_run_destroy(cz_run *r);
+/* shard k: its world handle (for any cz_world_* call on that shard) and the world range it owns */
+int cz_run_shard(cz_run *r, int32_t k, cz_world **world, int32_t *first_world, int32_t *n_worlds);
+/* whole-batch uploads (arrays hold every world of the run, world-major): sliced per shard */
+int cz_run_upload_bodies(cz_run *r, const cz_bodies *all, int32_t derive);
+int cz_run_upload_colliders(cz_run *r, const cz_colliders *all, int32_t derive);
+int cz_run_upload_planes(cz_run *r, const cz_planes *p);
+int cz_run_set_episodes(cz_run *r, int32_t length, const int32_t *phase0);
+/* n_steps frames on every shard; launches are enqueued on all devices before any is waited for (asynchronous) */
+int cz_run_step(cz_run *r, cz_real dt, int32_t n_steps);
+/* wait for every shard, reduce, report; resets the counters and the timer */
+int cz_run_finish(cz_run *r, cz_run_totals *out);
+const char *cz_run_last_error(cz_run *r);
+
 /* ---- microbench / diagnostics -------------------------------------------------------- */
 /* Integrate + CalculateDerivedData over n device-resident free bodies, `steps` times, timed
  * with CUDA events on the context stream; returns average ms per step. */
