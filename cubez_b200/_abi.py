@@ -317,6 +317,7 @@ def declare(lib: C.CDLL, prec: Precision, prefix: str = "cz_"):
         "run_last_error": ([VP], C.c_char_p),
         "bench_integrate": ([VP, C.c_int64, C.c_uint64, C.c_int32, C.c_int32, R, C.POINTER(C.c_float), C.POINTER(C.c_uint64)], C.c_int),
         "math_op": ([VP, C.c_int32, PR, PR], C.c_int),
+        "bench_fp64_rate": ([VP, C.POINTER(C.c_double)], C.c_int),
         "broadphase_pairs": ([VP, C.c_int64, PR, PR, C.c_int64, P32, C.POINTER(C.c_int64)], C.c_int),
         "bench_broadphase": ([VP, C.c_int64, C.c_uint64, C.c_double, C.c_int32, C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_int64), C.POINTER(C.c_float)], C.c_int),
         "sort_pairs_u32": ([VP, C.c_int64, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)], C.c_int),
@@ -336,7 +337,7 @@ EXPORTED = (
     "world_set_pow world_set_step_index world_set_episodes world_set_materials world_export_gl world_step world_synchronize world_download_bodies "
     "world_download_colliders world_download_contacts world_last_step_counts world_checksum_energy "
     "world_step_host world_step_rl run_create run_destroy run_shard run_upload_bodies run_upload_colliders run_upload_planes "
-    "run_set_episodes run_step run_finish run_last_error bench_integrate math_op broadphase_pairs bench_broadphase sort_pairs_u32 sort_pairs_u64"
+    "run_set_episodes run_step run_finish run_last_error bench_fp64_rate bench_integrate math_op broadphase_pairs bench_broadphase sort_pairs_u32 sort_pairs_u64"
 ).split()
 
 

@@ -1946,6 +1946,38 @@ int cz_bench_integrate(cz_ctx *ctx, int64_t n, uint64_t seed, int32_t warmup, in
     return CZ_OK;
 }
 
+// FP64 pipe rate: the denominator of the fused step's roofline (that kernel is bound by FP64 issue / dependency latency,
+// not by HBM).  Every thread runs 8 independent chains of alternating multiplies and adds (the product is built with
+// -fmad=false, so its arithmetic is separate DMUL / DADD too); full occupancy, no memory traffic.
+__global__ void __launch_bounds__(256) k_fp64_rate(double *out, int iters, double m, double a) {
+    double x0 = threadIdx.x * 1e-9 + 1.0, x1 = x0 + 0.125, x2 = x0 + 0.25, x3 = x0 + 0.375, x4 = x0 + 0.5, x5 = x0 + 0.625, x6 = x0 + 0.75, x7 = x0 + 0.875;
+    for (int i = 0; i < iters; i++) {
+        x0 = x0 * m; x1 = x1 * m; x2 = x2 * m; x3 = x3 * m; x4 = x4 * m; x5 = x5 * m; x6 = x6 * m; x7 = x7 * m;
+        x0 = x0 + a; x1 = x1 + a; x2 = x2 + a; x3 = x3 + a; x4 = x4 + a; x5 = x5 + a; x6 = x6 + a; x7 = x7 + a;
+    }
+    const double r = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+    if (r == 123.456) out[0] = r;   // keeps the chains alive
+}
+int cz_bench_fp64_rate(cz_ctx *ctx, double *ops_per_s) {
+    if (!ctx || !ops_per_s) return fail(ctx, CZ_ERR_INVALID, "cz_bench_fp64_rate: bad argument");
+    CK(ctx, cudaSetDevice(ctx->device));
+    double *d = nullptr;
+    CK(ctx, cudaMalloc(&d, sizeof(double)));
+    const int grid = ctx->sm_count * 8, iters = 1 << 14;
+    k_fp64_rate<<<grid, 256, 0, ctx->stream>>>(d, 256, 0.999999999, 1e-9);   // warm-up
+    cudaEventRecord(ctx->ev0, ctx->stream);
+    k_fp64_rate<<<grid, 256, 0, ctx->stream>>>(d, iters, 0.999999999, 1e-9);
+    cudaEventRecord(ctx->ev1, ctx->stream);
+    cudaError_t e = cudaEventSynchronize(ctx->ev1);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    float ms = 0;
+    cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+    cudaFree(d);
+    if (e != cudaSuccess || !(ms > 0)) return fail(ctx, CZ_ERR_CUDA, cudaGetErrorString(e));
+    *ops_per_s = (double)grid * 256.0 * 16.0 * (double)iters / ((double)ms * 1e-3);   // thread-level FP64 instructions per second
+    return CZ_OK;
+}
+
 // ---- K2 entry points: host-buffer broadphase, microbench, sort test hooks ------------------------
 __global__ void k_bp_load_host(const real *centers, const real *radii, long long n, czbp::Bounds *bounds, long long *box) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;

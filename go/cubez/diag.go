@@ -23,6 +23,13 @@ func BenchIntegrate(n int64, seed uint64, warmup, steps int, dt m.Real) (avgMs f
 	return float32(ms), uint64(cks)
 }
 
+// BenchFP64Rate — cz_bench_fp64_rate: measured thread-level FP64 instructions per second of the device.
+func BenchFP64Rate() float64 {
+	var r C.double
+	check(C.cz_bench_fp64_rate(ctx, &r))
+	return float64(r)
+}
+
 // BenchBroadphase — cz_bench_broadphase: the sort-based broadphase on n unit spheres at `fill` volume fraction.
 func BenchBroadphase(n int64, seed uint64, fill float64, warmup, steps int) (avgMs float32, pairs int64, sortMs float32) {
 	var ms, sms C.float

@@ -324,6 +324,9 @@ const char *cz_run_last_error(cz_run *r);
  * with CUDA events on the context stream; returns average ms per step. */
 int cz_bench_integrate(cz_ctx *ctx, int64_t n, uint64_t seed, int32_t warmup, int32_t steps, cz_real dt,
                        float *avg_ms, uint64_t *checksum);
+/* Measured FP64 pipe rate of the device: thread-level DMUL / DADD instructions per second with every SM busy and no
+ * memory traffic — the denominator of the fused world step's roofline (bench.py), which is FP64-issue bound. */
+int cz_bench_fp64_rate(cz_ctx *ctx, double *ops_per_s);
 /* Sort-based broadphase (K2) on host-supplied bounding spheres: candidate pairs (i, j) whose
  * spheres overlap within the library's 0.5 % inflation.  pairs holds 2*capacity ints; *n_pairs is
  * the number found (may exceed capacity: CZ_ERR_CAPACITY).  Order is unspecified. */
