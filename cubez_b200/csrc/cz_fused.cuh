@@ -48,6 +48,7 @@ struct FusedPlan {
     int keepContacts;
     int bodyMasks;       // per-body contact bitmasks drive the propagation (contact capacity <= 64)
     int lockstep;        // CTA barriers between the phases of a frame (instruction-cache locality)
+    int velPre;          // the velocity loop evaluates every contact's response matrix once per frame (czr::friction_response)
     real *cold;          // [grid*groupsPerBlock][Cc*CW_NCOLD]
     size_t coldReals;    // per group
     // split mode: one launch per phase of the frame (A: integrate + narrowphase + prepare, B: position
@@ -63,6 +64,7 @@ struct FusedPlan {
     int loopBlocksPerSM, loopGrid;
     int phaseAMinb;      // register budget of the phase-A launch
     real *coldW;         // [W][Cc*CW_NCOLD]
+    real *preW;          // [W][Cc*VP_NF] per-contact velocity response of the velocity loop (split mode), or NULL
     real *hotPen, *hotDdv;   // [W][Cc]
     int *hotCb0, *hotCb1;    // [W][Cc]
 };
@@ -190,9 +192,10 @@ static inline bool plan(FusedPlan &fp, int B, int P, int Cc, int nchk, int sched
     }
     fp.maxGrid = fp.grid > fp.phaseAGrid ? fp.grid : fp.phaseAGrid;
     if (fp.loopGrid > fp.maxGrid) fp.maxGrid = fp.loopGrid;
-    fp.coldW = nullptr; fp.hotPen = fp.hotDdv = nullptr; fp.hotCb0 = fp.hotCb1 = nullptr;
+    fp.coldW = nullptr; fp.preW = nullptr; fp.hotPen = fp.hotDdv = nullptr; fp.hotCb0 = fp.hotCb1 = nullptr;
     fp.lockstep = env_int("CUBEZ_FUSED_LOCKSTEP", 3);   // 0 none, 1 frame start, 2 + before narrowphase/resolve, 3 + between the two loops
-    fp.coldReals = (size_t)Cc * czr::CW_NCOLD + (size_t)nchk * 8;   // + staging of pair-test contacts
+    fp.velPre = env_int("CUBEZ_FUSED_VEL_PRE", 1);
+    fp.coldReals = (size_t)Cc * czr::CW_NCOLD + (size_t)nchk * 8 + (fp.velPre ? (size_t)Cc * czr::VP_NF : 0);   // + staging of pair-test contacts + velocity responses
     fp.cold = nullptr;
     const bool lm = Cc <= 64 && fp.bodyMasks;
     if (carve_end(B, Cc, nchk, 0, lm) > fp.worldBytes || carve_end(B, Cc, nchk, 1, lm) > fp.phaseAWorldBytes ||
@@ -372,6 +375,7 @@ __global__ void __launch_bounds__(128, MINB) k_world_fused(WorldParams p, FusedP
     x.mlist = (Cc <= 256 && !A_ONLY && (FULL || !(Cc <= 64 && fp.bodyMasks))) ? mlist : nullptr;   // the loops' scratch: absent from the phase-A record, and from a loop record that has masks
     x.bmask = (Cc <= 64 && fp.bodyMasks && !A_ONLY) ? bmask : nullptr;
     x.xb = nullptr; x.xbs = 0; x.store = st;
+    x.pre = (fp.velPre && PH == PH_ALL) ? groupScratch + (size_t)Cc * CW_NCOLD + (size_t)p.nchk * 8 : nullptr;
     GenView gv;
     gv.pn = s.cold; gv.fs = 1; gv.cs = CW_NCOLD; gv.pen = s.pen; gv.fric = nullptr; gv.rest = nullptr; gv.b0 = s.cb0; gv.b1 = s.cb1;
 
@@ -403,6 +407,7 @@ __global__ void __launch_bounds__(128, MINB) k_world_fused(WorldParams p, FusedP
         if (PH != PH_ALL) {   // split mode: contact state of this world lives in global memory between launches
             s.cold = fp.coldW + (size_t)w * Cc * CW_NCOLD;
             x.cold = s.cold; gv.pn = s.cold;
+            if ((PH & PH_C) && fp.preW) x.pre = fp.preW + (size_t)w * Cc * VP_NF;
             if (DIRECT && (PH & PH_A)) {
                 const long long gsAll = (long long)p.W * Cc, o = (long long)w * Cc;
                 gv.pn = p.gen + o; gv.fs = (int)gsAll; gv.cs = 1;

@@ -46,6 +46,8 @@ struct Ctx {
     real *xb; int xbs;
     czb::BodyStore store;
     int64_t body_base;          // global index of the world's body 0 in `store`
+    real *pre = nullptr;        // optional [capacity][VP_NF] scratch: per-contact velocity response, evaluated once per frame by
+                                // the velocity loop (see friction_response) instead of once per pick
 };
 enum ExtraBody : int { XB_IITB = 0, XB_TR = 9, XB_NF = 21 };
 
@@ -578,6 +580,7 @@ __device__ __forceinline__ int resolve_loop(const Ctx &x, bool enabled, int maxI
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) maxC = max(maxC, __shfl_xor_sync(full, maxC, o));
     int used = 0;
+    bool havePre = false;
     while (true) {
         real best = R_(0.01);   // positionEpsilon / velocityEpsilon (contact.go:12-13)
         int idx = 0x7fffffff;
@@ -590,6 +593,18 @@ __device__ __forceinline__ int resolve_loop(const Ctx &x, bool enabled, int maxI
         warp_argmax<NT>(best, idx, full);
         if (idx == 0x7fffffff) done = true;
         if (__all_sync(full, done)) break;
+        if (VELOCITY && x.pre && !havePre) {
+            // First pick of the frame: the worlds of this warp that have anything to resolve evaluate the 3x3 velocity
+            // response of every contact (4 matrix products, determinant, inverse: two thirds of the serial resolve) ONCE,
+            // one contact per lane, instead of redundantly in all lanes of the group at every pick.  Constants of this loop
+            // (friction_response); worlds at rest never get here.
+            for (int c0 = 0; c0 < maxC; c0 += NT) {
+                const int c = c0 + tid;
+                if (!done && c < x.nC && ctx_friction(x, c) != R_(0.0)) precompute_velocity_response(x, c, x.pre + (size_t)c * VP_NF);
+            }
+            __syncwarp();
+            havePre = true;
+        }
         // The contacts the winner will touch are the set bits of the masks of its two bodies.  (Prefetching their
         // cold records into L1 here, under the winner's FP64 chain, was tried: 1.5 % slower — the L1 left beside
         // the shared-memory carve-out is too small for the lines to survive.)
@@ -607,7 +622,7 @@ __device__ __forceinline__ int resolve_loop(const Ctx &x, bool enabled, int maxI
         PosCommit pc;
         VelCommit vc;
         if (!done) {
-            if (VELOCITY) resolve_velocity(x, idx, ch, vc);
+            if (VELOCITY) resolve_velocity(x, idx, ch, vc, (x.pre && havePre) ? x.pre + (size_t)idx * VP_NF : nullptr);
             else resolve_position(x, idx, best, ch, pc);
         }
         __syncwarp();   // every lane has read the old body state before one lane overwrites it

@@ -514,7 +514,7 @@ static int world_plan(cz_world *w) {
     w->useFused = false;
     if (!(w->d.flags & CZ_WORLD_NO_FUSED)) {
         free_and_null(w->fused.cold);
-        free_and_null(w->fused.coldW); free_and_null(w->fused.hotPen); free_and_null(w->fused.hotDdv);
+        free_and_null(w->fused.coldW); free_and_null(w->fused.preW); free_and_null(w->fused.hotPen); free_and_null(w->fused.hotDdv);
         free_and_null(w->fused.hotCb0); free_and_null(w->fused.hotCb1);
         w->useFused = !w->useBP && czf::plan(w->fused, B, w->P, Cc, w->nchk, w->d.schedule, ctx->smem_optin, ctx->sm_count, W);
         if (w->useFused) {
@@ -525,6 +525,7 @@ static int world_plan(cz_world *w) {
             if (w->fused.split) {
                 const size_t WC = (size_t)W * Cc;
                 CK(ctx, cudaMalloc(&w->fused.coldW, sizeof(real) * WC * czr::CW_NCOLD));
+                if (w->fused.velPre) CK(ctx, cudaMalloc(&w->fused.preW, sizeof(real) * WC * czr::VP_NF));
                 CK(ctx, cudaMalloc(&w->fused.hotPen, sizeof(real) * WC));
                 CK(ctx, cudaMalloc(&w->fused.hotDdv, sizeof(real) * WC));
                 CK(ctx, cudaMalloc(&w->fused.hotCb0, sizeof(int) * WC));
@@ -640,7 +641,7 @@ int cz_world_destroy(cz_world *w) {
     if (w->d_phase0) cudaFree(w->d_phase0);
     void *ptrs[] = {w->d_one, w->d_two, w->gen, w->gb0, w->gb1, w->nContacts, w->posIters, w->velIters, w->stats,
                     w->tileCount, w->tileBase, w->hitCount, w->rs.bw, w->rs.cw, w->rs.cb, w->rs.pre, w->fused.cold, w->d_next, w->order3,
-                    w->fused.coldW, w->fused.hotPen, w->fused.hotDdv, w->fused.hotCb0, w->fused.hotCb1, w->d_matFric, w->d_matRest, w->d_bodyMat, w->d_export};
+                    w->fused.coldW, w->fused.preW, w->fused.hotPen, w->fused.hotDdv, w->fused.hotCb0, w->fused.hotCb1, w->d_matFric, w->d_matRest, w->d_bodyMat, w->d_export};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (w->h_stats) cudaFreeHost(w->h_stats);
     if (w->h_pin) cudaFreeHost(w->h_pin);

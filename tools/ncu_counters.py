@@ -58,7 +58,11 @@ if __name__ == "__main__":
         out["k1_dram_bytes"] = dram(rs[-1:])
     if a.k2:
         rs = rows(a.k2)
-        out["k2_dram_bytes"] = dram(rs)
+        names = [r.get("Kernel Name", "") for r in rs]
+        first = next(i for i, n in enumerate(names) if "k_bp_count" in n or "k_bp_bin" in n)
+        last = next(i for i, n in enumerate(names) if "k_bp_sweep" in n)
+        rs = rs[first:last + 1]      # one frame of the candidate pipeline (without the sphere generator and the radix sort timed beside it)
+        out["k2_dram_bytes"] = dram(rs)   # kernels only: the cudaMemsetAsync of the cell table (4 B per cell) is not a kernel
         out["k2_kernels"] = [r.get("Kernel Name", "")[:40] for r in rs]
     json.dump(out, open(path, "w"), indent=1)
     print(json.dumps(out, indent=1))
