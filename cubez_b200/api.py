@@ -334,6 +334,12 @@ class BatchedWorld:
         self.ctx.check(self.lib.cz_world_last_step_counts(self.h, nc.ctypes.data_as(P32), pi.ctypes.data_as(P32), vi.ctypes.data_as(P32)))
         return nc, pi, vi
 
+    def island_stats(self) -> Tuple[int, int]:
+        """(frames resolved as one CTA per contact island, of which re-run on the single-CTA path because the cap cut the loop)"""
+        a, b = C.c_int64(), C.c_int64()
+        self.ctx.check(self.lib.cz_world_island_stats(self.h, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
+
     def checksum_energy(self) -> Tuple[int, float]:
         cks, en = C.c_uint64(), C.c_double()
         self.ctx.check(self.lib.cz_world_checksum_energy(self.h, C.byref(cks), C.byref(en)))

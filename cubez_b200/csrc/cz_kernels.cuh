@@ -613,6 +613,145 @@ __global__ void __launch_bounds__(NT) k_resolve(WorldParams p, ResolveScratch rs
     }
 }
 
+// --------------------------------------------------------------------------------------
+// Contact islands of ONE large world (north star: "one CTA per world or contact island").
+// Contacts that share no body — directly or through a chain of contacts — never read each other's writes, and the
+// worst-first loop picks, inside an island, exactly the subsequence of the global pick order that belongs to it (the
+// global arg-max restricted to an island is the island's arg-max; ties go to the lowest GLOBAL index either way).
+// So each island may run its own loop, concurrently, and every body / contact ends in the state the reference's single
+// loop leaves — PROVIDED the reference's loop runs to convergence, i.e. the sum of the islands' iterations stays
+// within its cap of 8*len(contacts) per phase (examples/cubedrop.go:73).  When the cap cuts the global loop mid-way,
+// which island had its turn last depends on the interleaving: that case is DETECTED here (sums against the cap) and the
+// host re-runs the frame's resolve on the exact single-CTA path from a snapshot.  Connectivity runs through every
+// non-nil body, static ones included (a zero-mass body still carries the IsAwake flag the velocity loop re-reads,
+// contact.go:438); plane contacts link nothing (hard part 3).
+//   k_island_labels   connected components by min-label propagation with pointer jumping (one CTA, labels in shared memory)
+//   radix sort        contacts by island label, stable: ascending contact index inside an island (cz_sort.cuh)
+//   k_island_ranges   island boundaries in the sorted list
+//   k_resolve_islands one CTA per island on a renumbered, order-preserving slice of the contact arrays
+// --------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_island_labels(WorldParams p, unsigned long long *keys, unsigned *vals) {
+    extern __shared__ int label[];   // [B]
+    const int nC = min(p.nContacts[0], p.Cc);
+    for (int b = threadIdx.x; b < p.B; b += blockDim.x) label[b] = b;
+    __syncthreads();
+    for (int round = 0; round < 4096; round++) {
+        int changed = 0;
+        for (int c = threadIdx.x; c < nC; c += blockDim.x) {
+            const int b0 = p.gb0[c], b1 = p.gb1[c];
+            if (b0 < 0 || b1 < 0) continue;
+            const int l0 = label[b0], l1 = label[b1];
+            if (l0 != l1) {
+                const int m = min(l0, l1);
+                atomicMin(&label[b0], m);
+                atomicMin(&label[b1], m);
+                atomicMin(&label[max(l0, l1)], m);   // hook the larger root too: components merge in O(log) rounds
+                changed = 1;
+            }
+        }
+        __syncthreads();
+        for (int b = threadIdx.x; b < p.B; b += blockDim.x) {   // pointer jumping
+            int l = label[b];
+            while (label[l] != l) l = label[l];
+            label[b] = l;
+        }
+        if (!__syncthreads_or(changed)) break;
+    }
+    for (int c = threadIdx.x; c < nC; c += blockDim.x) {
+        const int b0 = p.gb0[c], b1 = p.gb1[c];
+        keys[c] = (unsigned long long)label[b0 >= 0 ? b0 : b1];
+        vals[c] = (unsigned)c;
+    }
+}
+struct IslandTable {
+    int *start;      // [Cc + 1] first sorted position of island k
+    int *count;      // [4]: number of islands | sum of position iterations | sum of velocity iterations | largest island
+};
+// one CTA: flags -> exclusive scan -> island starts
+__global__ void __launch_bounds__(1024) k_island_ranges(WorldParams p, const unsigned long long *sortedKeys, IslandTable t) {
+    __shared__ int warpTotals[33];
+    const int nC = min(p.nContacts[0], p.Cc);
+    int running = 0;
+    for (int c0 = 0; c0 < nC; c0 += blockDim.x) {
+        const int c = c0 + threadIdx.x;
+        const int flag = (c < nC && (c == 0 || sortedKeys[c] != sortedKeys[c - 1])) ? 1 : 0;
+        int total;
+        const int off = block_exclusive_scan(flag, warpTotals, total);
+        if (flag) t.start[running + off] = c;
+        running += total;
+    }
+    if (threadIdx.x == 0) { t.start[running] = nC; t.count[0] = running; t.count[1] = 0; t.count[2] = 0; t.count[3] = 0; }
+}
+__global__ void k_bw_load(WorldParams p, ResolveScratch rs) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= p.B) return;
+    czr::Ctx x;
+    x.bw = rs.bw; x.bs = p.B;
+    load_body_work(x, p.st, b, b);
+}
+__global__ void k_bw_store(WorldParams p, ResolveScratch rs, IslandTable t) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b == 0) {
+        p.posIters[0] = t.count[1]; p.velIters[0] = t.count[2];
+        atomicAdd(&p.stats[ST_POS], (unsigned long long)t.count[1]);
+        atomicAdd(&p.stats[ST_VEL], (unsigned long long)t.count[2]);
+    }
+    if (b >= p.B) return;
+    czr::Ctx x;
+    x.bw = rs.bw; x.bs = p.B;
+    store_body_work(x, p.st, b, b);
+}
+template <int NT>
+__global__ void __launch_bounds__(NT) k_resolve_islands(WorldParams p, ResolveScratch rs, const unsigned *perm, IslandTable t, real dt, int hotCap) {
+    using namespace czr;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ GroupScratch gs;
+    __shared__ BigBroadcast bb;
+    __shared__ int scanScratch[NT / 32 + 1];
+    const int tid = threadIdx.x;
+    const int nIslands = t.count[0], nAll = min(p.nContacts[0], p.Cc);
+    for (int isl = blockIdx.x; isl < nIslands; isl += gridDim.x) {
+        const int s = t.start[isl], nC = t.start[isl + 1] - s;
+        Ctx x;
+        x.bs = p.B; x.nC = nC; x.dt = dt; x.store = p.st; x.body_base = 0;
+        x.xb = nullptr; x.xbs = 0; x.mlist = nullptr; x.bmask = nullptr;
+        x.bw = rs.bw;
+        real *cwbase = rs.cw + s;                               // SoA over the whole capacity: a slice keeps the field stride
+        x.cb0 = rs.cb + s; x.cb1 = rs.cb + p.Cc + s;
+        x.cold = cwbase; x.cfs = p.Cc; x.ccs = 1;
+        x.pen = cwbase + (size_t)CW_NCOLD * p.Cc; x.ddv = x.pen + p.Cc; x.fric = x.ddv + p.Cc; x.rest = x.fric + p.Cc;
+        const long long gstride = (long long)p.W * p.Cc;
+        GenView g;
+        g.pn = p.gen; g.fs = (int)gstride; g.cs = 1;
+        g.pen = p.gen + G_PEN * gstride; g.fric = p.gen + G_FRIC * gstride; g.rest = p.gen + G_REST * gstride;
+        g.b0 = p.gb0; g.b1 = p.gb1;
+        for (int j = tid; j < nC; j += NT) prepare_contact(x, j, g, (int)perm[s + j]);   // slot j <- the island's j-th contact in global order
+        __syncthreads();
+        const int maxIter = nAll * 8;          // the reference's cap is global (examples/cubedrop.go:73); the sums are checked against it afterwards
+        int status = 0, pi, vi;
+        if (nC <= hotCap) {
+            const BigShared sh = big_carve(smem_raw, NT, hotCap, p.B);
+            big_build_adjacency<NT>(x, p.B, tid, sh, scanScratch);
+            real *velPre = rs.pre ? rs.pre + (size_t)s * VP_NF : nullptr;
+            pi = resolve_loop_big<NT, false>(x, maxIter, &gs, &bb, tid, &status, sh, nullptr);
+            __syncthreads();
+            vi = resolve_loop_big<NT, true>(x, maxIter, &gs, &bb, tid, &status, sh, velPre);
+        } else {
+            pi = resolve_loop_cta<NT, false>(x, maxIter, &gs, tid, &status);
+            __syncthreads();
+            vi = resolve_loop_cta<NT, true>(x, maxIter, &gs, tid, &status);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            atomicAdd(&t.count[1], pi);
+            atomicAdd(&t.count[2], vi);
+            atomicMax(&t.count[3], nC);
+            if (status) raise_status(p.stats, status);
+        }
+        __syncthreads();
+    }
+}
+
 // After cz_resolve_contacts: copy the resolver's view of the contacts (possibly swapped
 // bodies / negated normal, updated penetration) back into the as-generated arrays so the
 // shim can mirror contact.go:61-65 and :274 into the caller's Contact structs.

@@ -115,12 +115,14 @@ CZD V3 local_velocity(const Ctx &x, int b, const V3 &rp, const V3 &n, const V3 &
 
 // contact.go:59-85 + :118-156 for contact c.  All as-generated fields are read before anything
 // is written: `g` may alias the cold record (same contact column).
-CZD void prepare_contact(const Ctx &x, int c, const GenView &g) {
-    int b0 = g.b0[c], b1 = g.b1[c];
-    const real *gp = g.pn + (size_t)c * g.cs;
+CZD void prepare_contact(const Ctx &x, int c, const GenView &g, int src = -1) {
+    // src: index of the as-generated contact when it differs from the work slot c (island slices renumber the contacts)
+    const int cs = src >= 0 ? src : c;
+    int b0 = g.b0[cs], b1 = g.b1[cs];
+    const real *gp = g.pn + (size_t)cs * g.cs;
     V3 point = mk3(gp[(G_POINT + 0) * g.fs], gp[(G_POINT + 1) * g.fs], gp[(G_POINT + 2) * g.fs]);
     V3 n = mk3(gp[(G_NORMAL + 0) * g.fs], gp[(G_NORMAL + 1) * g.fs], gp[(G_NORMAL + 2) * g.fs]);
-    const real restitution = g.rest ? g.rest[c] : R_(0.1), friction = g.fric ? g.fric[c] : R_(0.9), pen0 = g.pen[c];
+    const real restitution = g.rest ? g.rest[cs] : R_(0.1), friction = g.fric ? g.fric[cs] : R_(0.9), pen0 = g.pen[cs];
     if (b0 < 0) {   // :61-65
         v_mul(n, R_(-1.0));
         b0 = b1;

@@ -368,6 +368,12 @@ struct cz_world {
     ResolveScratch rs{};
     int resolveNT = 32;
     int resolveSmem = 0;        // dynamic shared bytes when staged in smem, 0 = global scratch
+    // contact islands of one large world (k_resolve_islands): tables, snapshot for the detected-cap fallback
+    IslandTable isl{};
+    int *h_islCount = nullptr;        // pinned [4]
+    real2 *islBackup = nullptr;       // chunks C_L2T0 .. C_W78 of the body store (what a resolve may write besides the work record)
+    bool lastCapHit = false;          // the previous frame's loops ended at the iteration cap: islands would only be thrown away
+    long long islandFrames = 0, islandFallbacks = 0;
     bool useBP = false;               // sort-based broadphase (K2) instead of the all-pairs tiles
     czbp::Broadphase bp;
     bool useFused = false;
@@ -508,6 +514,12 @@ static int world_plan(cz_world *w) {
                                            std::max<long long>(1ll << 22, 16ll * B));
             if (e != cudaSuccess) return fail(ctx, CZ_ERR_CUDA, std::string("broadphase alloc: ") + cudaGetErrorString(e));
         }
+        if (!w->isl.start) {
+            CK(ctx, cudaMalloc(&w->isl.start, sizeof(int) * ((size_t)Cc + 2)));
+            CK(ctx, cudaMalloc(&w->isl.count, sizeof(int) * 4));
+            CK(ctx, cudaHostAlloc(&w->h_islCount, sizeof(int) * 4, cudaHostAllocDefault));
+            CK(ctx, cudaMalloc(&w->islBackup, sizeof(real2) * (size_t)w->b.st.stride * 11));
+        }
         w->useBP = true;
     }
     // fused small-world kernel
@@ -639,7 +651,8 @@ int cz_world_destroy(cz_world *w) {
     if (w->bp.bounds) czbp::bp_free(w->bp);
     if (w->snap.st.base) batch_free(w->snap);
     if (w->d_phase0) cudaFree(w->d_phase0);
-    void *ptrs[] = {w->d_one, w->d_two, w->gen, w->gb0, w->gb1, w->nContacts, w->posIters, w->velIters, w->stats,
+    if (w->h_islCount) cudaFreeHost(w->h_islCount);
+    void *ptrs[] = {w->isl.start, w->isl.count, w->islBackup, w->d_one, w->d_two, w->gen, w->gb0, w->gb1, w->nContacts, w->posIters, w->velIters, w->stats,
                     w->tileCount, w->tileBase, w->hitCount, w->rs.bw, w->rs.cw, w->rs.cb, w->rs.pre, w->fused.cold, w->d_next, w->order3,
                     w->fused.coldW, w->fused.preW, w->fused.hotPen, w->fused.hotDdv, w->fused.hotCb0, w->fused.hotCb1, w->d_matFric, w->d_matRest, w->d_bodyMat, w->d_export};
     for (void *p : ptrs) if (p) cudaFree(p);
@@ -879,10 +892,61 @@ static int world_step_multi(cz_world *w, real dt, long long &launches) {
         czbp::k_bp_emit<<<nblk(std::max<long long>((long long)nCont, 1), 128), 128, 0, ctx->stream>>>(p, bp.sortContacts.keys[cur], bp.sortContacts.vals[cur], bp.payload, bp.ids, bp.counters + 1);
         launches++;
         CKL(ctx);
-        if (w->resolveNT == 32) launch_resolve<32>(w, p, -1, dt, false);
-        else launch_resolve<256>(w, p, -1, dt, false, (long long)nCont);
-        CKL(ctx);
-        launches++;
+        // Contact islands: one CTA per connected component of the contact graph, exact while the reference's loop
+        // converges within its cap (see k_resolve_islands); the cap case is detected and re-run on the single-CTA path.
+        // CUBEZ_RESOLVE_ISLANDS: 0 never, 1 when it can pay (default), 2 always.
+        const int islMode = czf::env_int("CUBEZ_RESOLVE_ISLANDS", 1);
+        bool resolved = false;
+        if (w->resolveNT != 32 && w->resolveSmem == 0 && nCont > 0 && (islMode == 2 || (islMode == 1 && nCont >= 256 && !w->lastCapHit))) {
+            long long want = ((long long)nCont + 255) / 256 * 256;
+            const size_t limit = ctx->smem_optin > 4096 ? ctx->smem_optin - 4096 : 0;
+            const size_t big = czr::big_shared_bytes(256, want, p.B);
+            if (want <= 32767 && p.B <= 12000 && big <= limit && nCont <= (unsigned long long)p.Cc) {   // labels of every body in 48 KB of shared memory
+                czs::RadixBuffers<unsigned long long> &sb = bp.sortContacts;
+                k_island_labels<<<1, 1024, sizeof(int) * (size_t)p.B, ctx->stream>>>(p, sb.keys[0], sb.vals[0]);
+                int kb = 8;
+                while (kb < 32 && (1ll << kb) < (long long)p.B) kb += 8;
+                const int cur2 = czs::radix_sort(sb, (long long)nCont, kb, ctx->stream, &launches);
+                k_island_ranges<<<1, 1024, 0, ctx->stream>>>(p, sb.keys[cur2], w->isl);
+                CK(ctx, cudaMemcpyAsync(w->islBackup, w->b.st.chunk(czb::C_L2T0), sizeof(real2) * (size_t)w->b.st.stride * 11, cudaMemcpyDeviceToDevice, ctx->stream));
+                k_bw_load<<<nblk(p.B, 256), 256, 0, ctx->stream>>>(p, w->rs);
+                cudaFuncSetAttribute(k_resolve_islands<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)big);
+                const int grid = (int)std::min<unsigned long long>(nCont, (unsigned long long)ctx->sm_count * 4);
+                k_resolve_islands<256><<<grid, 256, big, ctx->stream>>>(p, w->rs, sb.vals[cur2], w->isl, dt, (int)want);
+                launches += 5;
+                CKL(ctx);
+                CK(ctx, cudaMemcpyAsync(w->h_islCount, w->isl.count, sizeof(int) * 4, cudaMemcpyDeviceToHost, ctx->stream));
+                CK(ctx, cudaStreamSynchronize(ctx->stream));
+                const long long cap = 8ll * (long long)nCont;
+                w->islandFrames++;
+                if ((long long)w->h_islCount[1] <= cap && (long long)w->h_islCount[2] <= cap &&
+                    // a loop that ends exactly AT the cap may have been cut: only a sum strictly below it proves convergence
+                    !((long long)w->h_islCount[1] == cap || (long long)w->h_islCount[2] == cap)) {
+                    k_bw_store<<<nblk(p.B, 256), 256, 0, ctx->stream>>>(p, w->rs, w->isl);
+                    launches++;
+                    resolved = true;
+                    w->lastCapHit = false;
+                } else {   // the reference's loop would have been cut by its cap: islands cannot reproduce where — restore and run it exactly
+                    CK(ctx, cudaMemcpyAsync(w->b.st.chunk(czb::C_L2T0), w->islBackup, sizeof(real2) * (size_t)w->b.st.stride * 11, cudaMemcpyDeviceToDevice, ctx->stream));
+                    w->islandFallbacks++;
+                }
+                if (getenv("CUBEZ_RESOLVE_TRACE")) fprintf(stderr, "[islands] contacts %llu islands %d largest %d pos %d vel %d cap %lld -> %s\n", nCont, w->h_islCount[0], w->h_islCount[3], w->h_islCount[1], w->h_islCount[2], cap, resolved ? "kept" : "fallback");
+            }
+        }
+        if (!resolved) {
+            if (w->resolveNT == 32) launch_resolve<32>(w, p, -1, dt, false);
+            else launch_resolve<256>(w, p, -1, dt, false, (long long)nCont);
+            CKL(ctx);
+            launches++;
+            // did the loops end at the cap?  (decides whether islands are tried on the next frame; read with the next frame's first sync)
+            if (islMode == 1 && w->resolveNT != 32) {
+                int it[2] = {0, 0};
+                CK(ctx, cudaMemcpyAsync(&it[0], w->posIters, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+                CK(ctx, cudaMemcpyAsync(&it[1], w->velIters, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+                CK(ctx, cudaStreamSynchronize(ctx->stream));
+                w->lastCapHit = nCont > 0 && ((long long)it[0] >= 8ll * (long long)nCont || (long long)it[1] >= 8ll * (long long)nCont);
+            }
+        }
     } else if (w->nchk > 0) {
         if (w->tiles == 1) {
             k_narrow<NARROW_SINGLE><<<p.W, w->tileThreads, 0, ctx->stream>>>(p, 1, nullptr, nullptr, nullptr);
@@ -1109,6 +1173,12 @@ int cz_world_last_step_counts(cz_world *w, int32_t *n_contacts, int32_t *pos_it,
     if (n_contacts) CK(ctx, cudaMemcpy(n_contacts, w->nContacts, bytes, cudaMemcpyDeviceToHost));
     if (pos_it) CK(ctx, cudaMemcpy(pos_it, w->posIters, bytes, cudaMemcpyDeviceToHost));
     if (vel_it) CK(ctx, cudaMemcpy(vel_it, w->velIters, bytes, cudaMemcpyDeviceToHost));
+    return CZ_OK;
+}
+int cz_world_island_stats(cz_world *w, int64_t *island_frames, int64_t *fallbacks) {
+    if (!w) return CZ_ERR_INVALID;
+    if (island_frames) *island_frames = w->islandFrames;
+    if (fallbacks) *fallbacks = w->islandFallbacks;
     return CZ_OK;
 }
 int cz_world_checksum_energy(cz_world *w, uint64_t *checksum, double *energy) {

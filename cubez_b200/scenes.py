@@ -157,6 +157,28 @@ def pile(prec=_abi.F64, side: int = 16) -> Scene:
     return Scene("pile", prec, 1, n, b, c, ground_plane(prec), contacts_per_world=16 * n)
 
 
+def archipelago(prec=_abi.F64, piles: int = 6, side: int = 2, spacing: float = 12.0) -> Scene:
+    """ONE world made of piles x piles separate small piles (each a `side`^3 jittered lattice as in cfg3), far enough
+    apart never to touch: the contact graph is a set of independent islands (the case the island resolver is for)."""
+    R = prec.dtype
+    unit = pile(prec, side)
+    m = unit.bodies_per_world
+    n = m * piles * piles
+    b = _abi.Bodies.defaults(n, prec)
+    c = _abi.Colliders.defaults(n, prec)
+    for k in range(piles * piles):
+        sl = slice(k * m, (k + 1) * m)
+        off = np.array([spacing * (k % piles - (piles - 1) / 2.0), 0.0, spacing * (k // piles - (piles - 1) / 2.0)])
+        b.position[sl] = (unit.bodies.position.astype(np.float64) + off).astype(R)
+        b.position[sl, 1] += R(0.37 * (k % 5))          # piles land on different frames
+        b.inverse_inertia_tensor[sl] = unit.bodies.inverse_inertia_tensor
+        b.inverse_mass[sl] = unit.bodies.inverse_mass
+        c.shape[sl] = unit.colliders.shape
+        c.half_size[sl] = unit.colliders.half_size
+        c.radius[sl] = unit.colliders.radius
+    return Scene("archipelago", prec, 1, n, b, c, ground_plane(prec), contacts_per_world=16 * n)
+
+
 def batched_cubedrop(prec=_abi.F64, n_worlds: int = 65536, first_world: int = 0) -> Scene:
     """cfg4: world w = cubedrop-8 with a per-world perturbation from splitmix64(1234 + w).
     `first_world` lets a rank build only its shard with the same global world ids."""

@@ -472,6 +472,14 @@ func (w *World) LastStepCounts() (contacts, posIterations, velIterations []int32
 	return
 }
 
+// IslandStats — cz_world_island_stats: frames resolved as one CTA per contact island, and how many of those were
+// re-run on the single-CTA path because the reference's iteration cap would have cut the loop.
+func (w *World) IslandStats() (islandFrames, fallbacks int64) {
+	var a, b C.int64_t
+	check(C.cz_world_island_stats(w.h, &a, &b))
+	return int64(a), int64(b)
+}
+
 // ChecksumEnergy — cz_world_checksum_energy (SURVEY §8d definitions).
 func (w *World) ChecksumEnergy() (uint64, float64) {
 	var c C.uint64_t

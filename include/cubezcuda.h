@@ -269,6 +269,10 @@ int cz_world_export_gl(cz_world *w, int32_t first_world, int32_t n_worlds, float
                        int32_t dst_on_device);
 /* per-world counters of the last step (each array n_worlds long, any may be NULL) */
 int cz_world_last_step_counts(cz_world *w, int32_t *n_contacts, int32_t *pos_iterations, int32_t *vel_iterations);
+/* Contact-island statistics of a CZ_WORLD_BROADPHASE world since creation: frames whose ResolveContacts ran as one CTA
+ * per island, and how many of those had to be re-run on the single-CTA path because the reference's loop would have
+ * been cut by its iteration cap (the only case islands cannot reproduce).  Either pointer may be NULL. */
+int cz_world_island_stats(cz_world *w, int64_t *island_frames, int64_t *fallbacks);
 /* FNV-1a-64 of each world's state summed mod 2^64, and total energy. */
 int cz_world_checksum_energy(cz_world *w, uint64_t *checksum, double *energy);
 /* Host-buffer step: upload primary state, run n_steps, download state, all on the world's
