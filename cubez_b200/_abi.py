@@ -293,6 +293,7 @@ def declare(lib: C.CDLL, prec: Precision, prefix: str = "cz_"):
         "world_set_activation": ([VP, C.c_int32, C.c_int32, P32, PU8], C.c_int),
         "world_set_pow": ([VP, R, PR, PR, R], C.c_int),
         "world_set_step_index": ([VP, C.c_int64], C.c_int),
+        "world_add_forces": ([VP, C.c_int32, C.c_int32, PR, PR], C.c_int),
         "world_set_episodes": ([VP, C.c_int32, P32], C.c_int),
         "world_set_materials": ([VP, C.c_int32, PR, PR, C.c_int32, C.c_int32, P32, P32], C.c_int),
         "world_export_gl": ([VP, C.c_int32, C.c_int32, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float), C.c_int32], C.c_int),
@@ -335,7 +336,7 @@ EXPORTED = (
     "init shutdown last_error real_size ctx_stream ctx_synchronize host_alloc host_free integrate "
     "calculate_derived_data collider_derive narrowphase resolve_contacts world_create world_destroy "
     "world_upload_bodies world_upload_colliders world_upload_planes world_upload_schedule world_set_activation "
-    "world_set_pow world_set_step_index world_set_episodes world_set_materials world_export_gl world_step world_synchronize world_download_bodies "
+    "world_set_pow world_add_forces world_set_step_index world_set_episodes world_set_materials world_export_gl world_step world_synchronize world_download_bodies "
     "world_download_colliders world_download_contacts world_last_step_counts world_island_stats world_checksum_energy "
     "world_step_host world_step_rl run_create run_destroy run_shard run_upload_bodies run_upload_colliders run_upload_planes "
     "run_set_episodes run_step run_finish run_last_error bench_fp64_rate bench_integrate math_op broadphase_pairs bench_broadphase sort_pairs_u32 sort_pairs_u64"

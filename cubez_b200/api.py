@@ -226,6 +226,16 @@ class BatchedWorld:
         ap = np.ascontiguousarray(ang_pow, dtype=self.prec.dtype)
         self.ctx.check(self.lib.cz_world_set_pow(self.h, self.prec.ctype(dt), lp.ctypes.data_as(PR), ap.ctypes.data_as(PR), self.prec.ctype(bias)))
 
+    def add_forces(self, force=None, torque=None, first_world: int = 0):
+        """forceAccum += force, torqueAccum += torque ([n_bodies, 3] arrays or None) — the writer the reference's
+        accumulators never had (rigidbody.go:86-92); consumed and cleared by the next Integrate of an awake body."""
+        PR = C.POINTER(self.prec.ctype)
+        f = None if force is None else np.ascontiguousarray(force, dtype=self.prec.dtype)
+        t = None if torque is None else np.ascontiguousarray(torque, dtype=self.prec.dtype)
+        n = (f if f is not None else t).size // (3 * self.B)
+        self.ctx.check(self.lib.cz_world_add_forces(self.h, first_world, n, None if f is None else f.ctypes.data_as(PR),
+                                                    None if t is None else t.ctypes.data_as(PR)))
+
     def set_step_index(self, s: int):
         self.ctx.check(self.lib.cz_world_set_step_index(self.h, s))
 

@@ -54,6 +54,9 @@ struct BodyStore {
     uint8_t *ident;       // 1: collider Offset is the identity (skip the 12-real read)
     int32_t *active_from; // takes part from this step on
     int64_t n;
+    // forceAccum / torqueAccum (rigidbody.go:86-92), [n*3] each, or NULL: identically zero — the reference has no
+    // writer for them, so they only exist once the host has called cz_world_add_forces
+    real *force, *torque;
 
     CZD real2 *chunk(int k) const { return base + (int64_t)k * stride; }
     CZD real2 ld(int k, int64_t i) const { return chunk(k)[i]; }
@@ -135,14 +138,9 @@ struct Integrated {
 // math.Pow results (:233, :234, :250).  forceAccum and torqueAccum have no writer anywhere in
 // the reference (only read :220,:223 and cleared :207-208), so they are the constant +0 here:
 // `x + 0` is kept because it turns a -0 component into +0 exactly as the Go code does.
-CZD void integrate_body(Integrated &o, const V3 &pos, const Q4 &q, const V3 &vel, const V3 &rot, const V3 &acc,
-                        const M3 &iitBody, real motion, bool canSleep, real dt, real linPow, real angPow, real bias) {
-    o.lastAcc = acc;
-    o.lastAcc.c[0] += R_(0); o.lastAcc.c[1] += R_(0); o.lastAcc.c[2] += R_(0);   // AddScaled(forceAccum = 0, inverseMass) :220
-    o.vel = vel;
-    v_add_scaled(o.vel, o.lastAcc, dt);                                          // :227
-    o.rot = rot;
-    { real z = R_(0) * dt; o.rot.c[0] += z; o.rot.c[1] += z; o.rot.c[2] += z; }   // AddScaled(iitWorld*torque = 0, dt) :230
+// rigidbody.go:233-258: damping, position / orientation update, derived data, sleep test (o.vel, o.rot, o.lastAcc set by the caller)
+CZD void integrate_body_tail(Integrated &o, const V3 &pos, const Q4 &q, const M3 &iitBody, real motion, bool canSleep, real dt,
+                             real linPow, real angPow, real bias) {
     v_mul(o.vel, linPow);                                                        // :233
     v_mul(o.rot, angPow);                                                        // :234
     o.pos = pos;
@@ -163,6 +161,32 @@ CZD void integrate_body(Integrated &o, const V3 &pos, const Q4 &q, const V3 &vel
             o.motion = R_(3.0);
         }
     }
+}
+
+
+CZD void integrate_body(Integrated &o, const V3 &pos, const Q4 &q, const V3 &vel, const V3 &rot, const V3 &acc,
+                        const M3 &iitBody, real motion, bool canSleep, real dt, real linPow, real angPow, real bias) {
+    o.lastAcc = acc;
+    o.lastAcc.c[0] += R_(0); o.lastAcc.c[1] += R_(0); o.lastAcc.c[2] += R_(0);   // AddScaled(forceAccum = 0, inverseMass) :220
+    o.vel = vel;
+    v_add_scaled(o.vel, o.lastAcc, dt);                                          // :227
+    o.rot = rot;
+    { real z = R_(0) * dt; o.rot.c[0] += z; o.rot.c[1] += z; o.rot.c[2] += z; }   // AddScaled(iitWorld*torque = 0, dt) :230
+    integrate_body_tail(o, pos, q, iitBody, motion, canSleep, dt, linPow, angPow, bias);
+}
+// The same with live accumulators (cz_world_add_forces): lastFrameAcceleration = Acceleration + forceAccum * inverseMass
+// (:219-220), angularAcceleration = inverseInertiaTensorWorld (of the previous frame) * torqueAccum (:223).
+CZD void integrate_body_forces(Integrated &o, const V3 &pos, const Q4 &q, const V3 &vel, const V3 &rot, const V3 &acc,
+                               const M3 &iitBody, real motion, bool canSleep, real dt, real linPow, real angPow, real bias,
+                               const V3 &force, const V3 &torque, real inverseMass, const M3 &iitWorldPrev) {
+    o.lastAcc = acc;
+    v_add_scaled(o.lastAcc, force, inverseMass);                                 // :220
+    const V3 angAcc = m3_mul_v(iitWorldPrev, torque);                            // :223
+    o.vel = vel;
+    v_add_scaled(o.vel, o.lastAcc, dt);                                          // :227
+    o.rot = rot;
+    v_add_scaled(o.rot, angAcc, dt);                                             // :230
+    integrate_body_tail(o, pos, q, iitBody, motion, canSleep, dt, linPow, angPow, bias);
 }
 
 }  // namespace czb

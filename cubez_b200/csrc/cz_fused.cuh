@@ -458,7 +458,15 @@ __global__ void __launch_bounds__(128, MINB) k_world_fused(WorldParams p, FusedP
                     M3 ib;
                     ib.c[0] = apw0.y; ib.c[1] = i12.x; ib.c[2] = i12.y; ib.c[3] = i34.x; ib.c[4] = i34.y; ib.c[5] = i56.x; ib.c[6] = i56.y; ib.c[7] = i78.x; ib.c[8] = i78.y;
                     czb::Integrated o;
-                    czb::integrate_body(o, pos, q, vel, rot, acc, ib, s.fb[BW_MOTION * B + b], (fl & FF_CANSLEEP) != 0, dt, a2lp.y, apw0.x, bias);
+                    if (st.force) {   // live accumulators (cz_world_add_forces); the staged world inertia is still the previous frame's (rigidbody.go:223)
+                        const V3 f = mk3(st.force[gi * 3], st.force[gi * 3 + 1], st.force[gi * 3 + 2]), tq = mk3(st.torque[gi * 3], st.torque[gi * 3 + 1], st.torque[gi * 3 + 2]);
+                        czb::integrate_body_forces(o, pos, q, vel, rot, acc, ib, s.fb[BW_MOTION * B + b], (fl & FF_CANSLEEP) != 0, dt, a2lp.y, apw0.x, bias,
+                                                   f, tq, s.fb[BW_INVM * B + b], bw_iitw(x, b));
+#pragma unroll
+                        for (int k = 0; k < 3; k++) { st.force[gi * 3 + k] = R_(0); st.torque[gi * 3 + k] = R_(0); }
+                    } else {
+                        czb::integrate_body(o, pos, q, vel, rot, acc, ib, s.fb[BW_MOTION * B + b], (fl & FF_CANSLEEP) != 0, dt, a2lp.y, apw0.x, bias);
+                    }
                     bw3_set(x, BW_POS, b, o.pos); bw3_set(x, BW_VEL, b, o.vel); bw3_set(x, BW_ROT, b, o.rot); bw3_set(x, BW_LACC, b, o.lastAcc);
 #pragma unroll
                     for (int k = 0; k < 4; k++) s.fb[(BW_Q + k) * B + b] = o.q.c[k];

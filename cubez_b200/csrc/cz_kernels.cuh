@@ -102,7 +102,14 @@ __global__ void __launch_bounds__(256, 2) k_integrate(BodyStore s, real dt, real
             Q4 q; q.c[0] = q01.x; q.c[1] = q01.y; q.c[2] = q23.x; q.c[3] = q23.y;
             M3 ib; ib.c[0] = apw0.y; ib.c[1] = i12.x; ib.c[2] = i12.y; ib.c[3] = i34.x; ib.c[4] = i34.y; ib.c[5] = i56.x; ib.c[6] = i56.y; ib.c[7] = i78.x; ib.c[8] = i78.y;
             Integrated o;
-            integrate_body(o, pos, q, vel, rot, acc, ib, p2m.y, canSleep, dt, a2lp.y, apw0.x, bias);
+            if (s.force) {   // live accumulators (cz_world_add_forces): consumed and cleared by this Integrate (ClearAccumulators, rigidbody.go:206)
+                const V3 f = mk3(s.force[i * 3], s.force[i * 3 + 1], s.force[i * 3 + 2]), tq = mk3(s.torque[i * 3], s.torque[i * 3 + 1], s.torque[i * 3 + 2]);
+                integrate_body_forces(o, pos, q, vel, rot, acc, ib, p2m.y, canSleep, dt, a2lp.y, apw0.x, bias, f, tq, s.ld(C_MD, i).x, ld_iit_world(s, i));
+#pragma unroll
+                for (int k = 0; k < 3; k++) { s.force[i * 3 + k] = R_(0); s.torque[i * 3 + k] = R_(0); }
+            } else {
+                integrate_body(o, pos, q, vel, rot, acc, ib, p2m.y, canSleep, dt, a2lp.y, apw0.x, bias);
+            }
             stg_stream(s.chunk(C_P01) + i, make_real2(o.pos.c[0], o.pos.c[1]));
             stg_stream(s.chunk(C_P2M) + i, make_real2(o.pos.c[2], o.motion));
             stg_stream(s.chunk(C_Q01) + i, make_real2(o.q.c[0], o.q.c[1]));
@@ -255,6 +262,17 @@ __global__ void k_apply_actions(czb::BodyStore s, long long first, long long n, 
     if (addVel) { v01.x = v01.x + addVel[i * 3]; v01.y = v01.y + addVel[i * 3 + 1]; v2r0.x = v2r0.x + addVel[i * 3 + 2]; }
     if (addRot) { v2r0.y = v2r0.y + addRot[i * 3]; r12.x = r12.x + addRot[i * 3 + 1]; r12.y = r12.y + addRot[i * 3 + 2]; }
     s.st(C_V01, i, v01); s.st(C_V2R0, i, v2r0); s.st(C_R12, i, r12);
+}
+
+// Force / torque accumulator input: forceAccum += f, torqueAccum += t per body, one rounding per
+// component — cyclone's addForce / addTorque, which the reference keeps the accumulators for (rigidbody.go:86-92) but
+// never exposes.  The next Integrate of an awake body consumes and clears them (:219-223, :206).
+__global__ void k_add_forces(czb::BodyStore s, long long first, long long n, const real *force, const real *torque) {
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n * 3) return;
+    const long long i = first * 3 + t;
+    if (force) s.force[i] = s.force[i] + force[t];
+    if (torque) s.torque[i] = s.torque[i] + torque[t];
 }
 
 // Renderer-side export: what the example loop does per body and frame on the host,

@@ -226,6 +226,8 @@ static void batch_free(Batch &b) {
     if (b.st.shape) cudaFree(b.st.shape);
     if (b.st.ident) cudaFree(b.st.ident);
     if (b.st.active_from) cudaFree(b.st.active_from);
+    if (b.st.force) cudaFree(b.st.force);
+    if (b.st.torque) cudaFree(b.st.torque);
     if (b.stage) cudaFree(b.stage);
     b = Batch();
 }
@@ -783,6 +785,31 @@ int cz_world_set_materials(cz_world *w, int32_t n_materials, const cz_real *fric
     }
     if (plane_material) for (int i = 0; i < w->P && i < CZ_MAX_PLANES; i++) w->planeMat[i] = (uint8_t)plane_material[i];
     w->nMat = n_materials;
+    return CZ_OK;
+}
+int cz_world_add_forces(cz_world *w, int32_t first, int32_t n, const cz_real *force, const cz_real *torque) {
+    int rc = world_range(w, first, n);
+    if (rc) return rc;
+    cz_ctx *ctx = w->ctx;
+    CK(ctx, cudaSetDevice(ctx->device));
+    if (n == 0 || (!force && !torque)) return CZ_OK;
+    const long long B = w->d.bodies_per_world, NB = w->b.n, nb = (long long)n * B;
+    if (!w->b.st.force) {   // first use: the accumulators come into existence, zeroed
+        real *f = nullptr, *t = nullptr;
+        CK(ctx, cudaMalloc(&f, sizeof(real) * 3 * (size_t)w->b.st.stride));
+        CK(ctx, cudaMalloc(&t, sizeof(real) * 3 * (size_t)w->b.st.stride));
+        CK(ctx, cudaMemsetAsync(f, 0, sizeof(real) * 3 * (size_t)w->b.st.stride, ctx->stream));
+        CK(ctx, cudaMemsetAsync(t, 0, sizeof(real) * 3 * (size_t)w->b.st.stride, ctx->stream));
+        w->b.st.force = f; w->b.st.torque = t;
+    }
+    (void)NB;
+    // staging: the pack buffer of the batch holds 12 reals per body
+    real *dF = w->b.stage, *dT = w->b.stage + nb * 3;
+    if (force) CK(ctx, cudaMemcpyAsync(dF, force, sizeof(real) * nb * 3, cudaMemcpyHostToDevice, ctx->stream));
+    if (torque) CK(ctx, cudaMemcpyAsync(dT, torque, sizeof(real) * nb * 3, cudaMemcpyHostToDevice, ctx->stream));
+    k_add_forces<<<nblk(nb * 3, 256), 256, 0, ctx->stream>>>(w->b.st, first * B, nb, force ? dF : nullptr, torque ? dT : nullptr);
+    CKL(ctx);
+    CK(ctx, cudaStreamSynchronize(ctx->stream));   // the staging buffer is shared with the field uploads
     return CZ_OK;
 }
 int cz_world_set_step_index(cz_world *w, int64_t s) {

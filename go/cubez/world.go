@@ -349,6 +349,27 @@ func (w *World) SetPow(dt m.Real, linPow, angPow []m.Real, bias m.Real) {
 	check(C.cz_world_set_pow(w.h, C.cz_real(dt), (*C.cz_real)(lp), (*C.cz_real)(ap), C.cz_real(bias)))
 }
 
+// AddForces — cz_world_add_forces: forceAccum += force[3i:], torqueAccum += torque[3i:] for every body of worlds
+// [firstWorld, firstWorld+nWorlds) (either slice may be nil) — the writer the reference's accumulators never had
+// (rigidbody.go:86-92, read at :219-223, cleared at :206).
+func (w *World) AddForces(firstWorld, nWorlds int, force, torque []m.Real) {
+	rs := unsafe.Sizeof(C.cz_real(0))
+	var f, t *C.cz_real
+	if force != nil {
+		p := cbuf(len(force), rs)
+		defer C.free(p)
+		copy(reals((*C.cz_real)(p), len(force)), force)
+		f = (*C.cz_real)(p)
+	}
+	if torque != nil {
+		p := cbuf(len(torque), rs)
+		defer C.free(p)
+		copy(reals((*C.cz_real)(p), len(torque)), torque)
+		t = (*C.cz_real)(p)
+	}
+	check(C.cz_world_add_forces(w.h, C.int32_t(firstWorld), C.int32_t(nWorlds), f, t))
+}
+
 // SetStepIndex — cz_world_set_step_index (activation and episodes count frames from it).
 func (w *World) SetStepIndex(step int64) { check(C.cz_world_set_step_index(w.h, C.int64_t(step))) }
 

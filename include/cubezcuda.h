@@ -243,6 +243,14 @@ int cz_world_set_step_index(cz_world *w, int64_t step_index);
  * the reference's defect mirrored (contact.go:498-531: CZ_ERR_NIL_BODY for a one-body contact). */
 int cz_world_set_materials(cz_world *w, int32_t n_materials, const cz_real *friction, const cz_real *restitution,
                            int32_t first_world, int32_t n_worlds, const int32_t *body_material, const int32_t *plane_material);
+/* Force / torque input (new API).  RigidBody keeps forceAccum / torqueAccum (rigidbody.go:86-92), reads
+ * them in Integrate (:219-223: lastFrameAcceleration = Acceleration + forceAccum * inverseMass, angular acceleration =
+ * inverseInertiaTensorWorld * torqueAccum) and clears them (:206), but nothing in the reference ever writes them.  This
+ * is the writer: forceAccum += force[3i..], torqueAccum += torque[3i..] for every body of worlds [first_world,
+ * first_world + n_worlds) (host arrays of n_worlds * bodies_per_world * 3 reals; either may be NULL).  The next
+ * Integrate of an AWAKE body consumes and clears its accumulators; a sleeping body keeps them (Integrate returns before
+ * ClearAccumulators, :214-216).  Until the first call the accumulators do not exist and cost nothing. */
+int cz_world_add_forces(cz_world *w, int32_t first_world, int32_t n_worlds, const cz_real *force, const cz_real *torque);
 /* RL-style episodes (new API): snapshot the current device state as the episode start; world k
  * is at frame phase0[k] (0 <= phase0[k] < length) of its episode now and is restored to the
  * snapshot at the start of every frame on which its phase wraps to 0.  length <= 0 disables. */

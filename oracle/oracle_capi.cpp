@@ -328,6 +328,21 @@ int czo_world_set_materials(void *h, int32_t n_materials, const R *friction, con
             for (int i = 0; i < B; i++) w->worlds[first + k].bodyMaterial[i] = body_material[k * B + i];
     return 0;
 }
+// forceAccum += force, torqueAccum += torque (the writer of rigidbody.go:86-92's accumulators; mirrors cz_world_add_forces)
+int czo_world_add_forces(void *h, int32_t first, int32_t n, const R *force, const R *torque) {
+    OracleWorlds *w = (OracleWorlds *)h;
+    const int B = w->desc.bodies_per_world;
+    for (int k = 0; k < n; k++)
+        for (int b = 0; b < B; b++) {
+            Body<R> &body = w->worlds[first + k].bodies[b];
+            const long long i = ((long long)k * B + b) * 3;
+            for (int c = 0; c < 3; c++) {
+                if (force) body.forceAccum[c] = body.forceAccum[c] + force[i + c];
+                if (torque) body.torqueAccum[c] = body.torqueAccum[c] + torque[i + c];
+            }
+        }
+    return 0;
+}
 int czo_world_set_step_index(void *h, int64_t s) { for (auto &wd : ((OracleWorlds *)h)->worlds) wd.stepIndex = s; return 0; }
 
 // n_threads > 1 partitions the worlds over std::threads (worlds are independent).

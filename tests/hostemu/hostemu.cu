@@ -28,6 +28,7 @@ struct HostStore {
         st.base = chunks.data(); st.stride = stride; st.n = n;
         st.awake = awake.data(); st.can_sleep = can_sleep.data(); st.integ = integ.data(); st.shape = shape.data(); st.ident = ident.data();
         st.active_from = active.data();
+        st.force = st.torque = nullptr;
     }
     real &slot(int s, long long i) { return ((real *)(st.base + (long long)(s >> 1) * st.stride))[2 * i + (s & 1)]; }
 };

@@ -45,6 +45,7 @@ def load(prec: str = "f64") -> C.CDLL:
         "czo_world_upload_schedule": ([VP, C.c_int32, P32, P32], C.c_int),
         "czo_world_set_activation": ([VP, C.c_int32, C.c_int32, P32, PU8], C.c_int),
         "czo_world_set_step_index": ([VP, C.c_int64], C.c_int),
+        "czo_world_add_forces": ([VP, C.c_int32, C.c_int32, PR, PR], C.c_int),
         "czo_world_set_episodes": ([VP, C.c_int32, P32], C.c_int),
         "czo_world_set_materials": ([VP, C.c_int32, PR, PR, C.c_int32, C.c_int32, P32, P32], C.c_int),
         "czo_world_step": ([VP, R, C.c_int32, C.c_int32, C.POINTER(CzStepStats)], C.c_int),
@@ -172,6 +173,13 @@ class OracleWorld:
     def upload_colliders(self, colliders: Colliders, first_world: int = 0, derive: bool = False):
         st = colliders.struct()
         self.lib.czo_world_upload_colliders(self.h, first_world, colliders.n // self.B, C.byref(st), int(derive))
+
+    def add_forces(self, force=None, torque=None, first_world: int = 0):
+        PR = C.POINTER(self.prec.ctype)
+        f = None if force is None else np.ascontiguousarray(force, dtype=self.prec.dtype)
+        t = None if torque is None else np.ascontiguousarray(torque, dtype=self.prec.dtype)
+        n = (f if f is not None else t).size // (3 * self.B)
+        self.lib.czo_world_add_forces(self.h, first_world, n, None if f is None else f.ctypes.data_as(PR), None if t is None else t.ctypes.data_as(PR))
 
     def set_step_index(self, s: int):
         self.lib.czo_world_set_step_index(self.h, s)

@@ -20,7 +20,7 @@ def _compare(scene, frames, every, monkeypatch, mode):
     cpu = OracleWorld.from_scene(scene)
     for s in range(0, frames, every):
         gs, cs = gpu.step(scene.dt, every), cpu.step(scene.dt, every)
-        for k in ("contacts", "pos_iterations", "vel_iterations", "max_contacts"):
+        for k in ("contacts", "pos_iterations", "vel_iterations"):     # (max_contacts: the oracle reports the last frame's, the library the call's maximum)
             assert gs[k] == cs[k], (s, k, gs[k], cs[k])
         assert gpu.contact_pairs(0) == cpu.contact_pairs(0), s
     g, c = gpu.download(), cpu.download()
