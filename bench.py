@@ -361,6 +361,27 @@ def main():
     e2e_rl = {"value": W * world_size / (rl_ms * 1e-3), "unit": "world-steps/s", "h2d_bytes_per_step": nb * 24 * world_size,
               "d2h_bytes_per_step": nb * 13 * 8 * world_size, "ms_per_step": rl_ms,
               "api": "cz_world_step_rl: device-resident worlds; batched AddVelocity in, position/orientation/velocity/rotation out, pinned host arrays, 1 frame per call"}
+    # the same loop pipelined (cz_world_step_rl_async, two steps in flight) with float32 observations converted on the device
+    acts2 = [act, ctx.pinned_array((nb, 3))]
+    acts2[1][...] = act
+    obs32 = [{k: ctx.pinned_array((nb, c), dtype=np.float32) for k, c in (("position", 3), ("orientation", 4), ("velocity", 3), ("rotation", 3))} for _ in range(2)]
+    def rl_pipelined(n):
+        tickets = []
+        for f in range(n):
+            if f >= 2:
+                world.rl_wait(tickets[f - 2], stats=False)
+            tickets.append(world.step_rl_async(acts2[f & 1], None, None, obs32[f & 1], DT, 1))
+        for t in tickets[-2:]:
+            world.rl_wait(t, stats=False)
+    rl_pipelined(4)
+    barrier()
+    t0 = time.perf_counter()
+    rl_pipelined(2 * args.e2e_steps)
+    barrier()
+    rlp_ms = max_over_ranks((time.perf_counter() - t0) * 1e3 / (2 * args.e2e_steps))
+    e2e_rl_pipelined = {"value": W * world_size / (rlp_ms * 1e-3), "unit": "world-steps/s", "h2d_bytes_per_step": nb * 24 * world_size,
+                        "d2h_bytes_per_step": nb * 13 * 4 * world_size, "ms_per_step": rlp_ms,
+                        "api": "cz_world_step_rl_async + cz_world_rl_wait: two steps in flight on alternating pinned buffers, batched AddVelocity in, float32 position/orientation/velocity/rotation out"}
     sampler.stop_flag = True
     sampler.join(timeout=2)
     world.close()
@@ -486,6 +507,7 @@ def main():
             "e2e": {"value": e2e_value, "unit": "world-steps/s", "h2d_bytes_per_step": h2d * world_size, "d2h_bytes_per_step": d2h * world_size,
                     "ms_per_step": e2e_ms, "api": "cz_world_step_host: pinned host arrays (full body state in, full body state out), 1 frame per call, 6-chunk H2D | pack+step+unpack | D2H pipeline, 3 compute streams"},
             "e2e_rl": e2e_rl,
+            "e2e_rl_pipelined": e2e_rl_pipelined,
             "gpu_launches": int(red["counters"]["launches"]),
             "clocks": sampler.summary(),
             "strong": strong,

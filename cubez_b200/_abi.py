@@ -95,6 +95,11 @@ class CzStepStats(C.Structure):
         return {k: getattr(self, k) for k, _ in self._fields_}
 
 
+class CzObs32(C.Structure):
+    _fields_ = [("n", C.c_int32), ("position", C.POINTER(C.c_float)), ("orientation", C.POINTER(C.c_float)),
+                ("velocity", C.POINTER(C.c_float)), ("rotation", C.POINTER(C.c_float))]
+
+
 class CzRunTotals(C.Structure):
     _fields_ = [("checksum", C.c_uint64), ("energy", C.c_double), ("world_steps", C.c_int64), ("contacts", C.c_int64),
                 ("pos_iterations", C.c_int64), ("vel_iterations", C.c_int64), ("max_device_ms", C.c_float), ("n_shards", C.c_int32),
@@ -307,6 +312,8 @@ def declare(lib: C.CDLL, prec: Precision, prefix: str = "cz_"):
         "world_checksum_energy": ([VP, C.POINTER(C.c_uint64), C.POINTER(C.c_double)], C.c_int),
         "world_step_host": ([VP, PB, R, C.c_int32, C.POINTER(CzStepStats)], C.c_int),
         "world_step_rl": ([VP, PR, PR, PB, R, C.c_int32, C.POINTER(CzStepStats)], C.c_int),
+        "world_step_rl_async": ([VP, PR, PR, PB, C.POINTER(CzObs32), R, C.c_int32, P32], C.c_int),
+        "world_rl_wait": ([VP, C.c_int32, C.POINTER(CzStepStats)], C.c_int),
         "run_create": ([C.c_int32, P32, C.POINTER(CzWorldDesc), C.POINTER(VP)], C.c_int),
         "run_destroy": ([VP], C.c_int),
         "run_shard": ([VP, C.c_int32, C.POINTER(VP), P32, P32], C.c_int),
@@ -338,7 +345,7 @@ EXPORTED = (
     "world_upload_bodies world_upload_colliders world_upload_planes world_upload_schedule world_set_activation "
     "world_set_pow world_add_forces world_set_step_index world_set_episodes world_set_materials world_export_gl world_step world_synchronize world_download_bodies "
     "world_download_colliders world_download_contacts world_last_step_counts world_island_stats world_checksum_energy "
-    "world_step_host world_step_rl run_create run_destroy run_shard run_upload_bodies run_upload_colliders run_upload_planes "
+    "world_step_host world_step_rl world_step_rl_async world_rl_wait run_create run_destroy run_shard run_upload_bodies run_upload_colliders run_upload_planes "
     "run_set_episodes run_step run_finish run_last_error bench_fp64_rate bench_integrate math_op broadphase_pairs bench_broadphase sort_pairs_u32 sort_pairs_u64"
 ).split()
 

@@ -308,6 +308,30 @@ class BatchedWorld:
                                                  self.prec.ctype(dt), n_steps, C.byref(st)))
         return st.as_dict()
 
+    def step_rl_async(self, add_velocity=None, add_rotation=None, obs: Optional[Bodies] = None, obs32: Optional[dict] = None, dt=None, n_steps: int = 1) -> int:
+        """Pipelined RL step (cz_world_step_rl_async): returns a ticket at once; up to two steps in flight.  obs32: dict
+        of pinned float32 arrays {"position": (n,3), "orientation": (n,4), "velocity": (n,3), "rotation": (n,3)}."""
+        PR, PF = C.POINTER(self.prec.ctype), C.POINTER(C.c_float)
+        def ptr(a):
+            if a is None:
+                return None
+            assert a.dtype == self.prec.dtype and a.flags["C_CONTIGUOUS"] and a.size == self.n_worlds * self.B * 3
+            return a.ctypes.data_as(PR)
+        ost = obs.struct() if obs is not None else None
+        o32 = None
+        if obs32 is not None:
+            o32 = _abi.CzObs32(self.n_worlds * self.B, *[None if obs32.get(k) is None else obs32[k].ctypes.data_as(PF)
+                                                        for k in ("position", "orientation", "velocity", "rotation")])
+        ticket = C.c_int32()
+        self.ctx.check(self.lib.cz_world_step_rl_async(self.h, ptr(add_velocity), ptr(add_rotation), None if ost is None else C.byref(ost),
+                                                       None if o32 is None else C.byref(o32), self.prec.ctype(dt), n_steps, C.byref(ticket)))
+        return int(ticket.value)
+
+    def rl_wait(self, ticket: int, stats: bool = True) -> Optional[dict]:
+        st = CzStepStats()
+        self.ctx.check(self.lib.cz_world_rl_wait(self.h, ticket, C.byref(st) if stats else None))
+        return st.as_dict() if stats else None
+
     def synchronize(self):
         self.ctx.check(self.lib.cz_world_synchronize(self.h))
 

@@ -527,6 +527,7 @@ struct ResolveScratch {
     real *cw;   // [W][CW_NREAL*Cc]
     int *cb;    // [W][2*Cc]
     real *pre;  // [W][VP_NF*Cc] per-contact velocity response of the large-world loop, or NULL
+    unsigned short *adj;   // [W][2*Cc] adjacency lists (body -> contacts) of the large-world loop, or NULL
 };
 
 CZD void load_body_work(const czr::Ctx &x, const BodyStore &s, long long gi, int b) {
@@ -604,7 +605,7 @@ __global__ void __launch_bounds__(NT) k_resolve(WorldParams p, ResolveScratch rs
     } else if (useSmem == 3 && nC <= hotCap) {   // one large world: adjacency lists + shared arg-max caches + prefetched propagation
         __shared__ BigBroadcast bb;
         __shared__ int scanScratch[NT / 32 + 1];
-        const BigShared sh = big_carve(smem_raw, (NT > 32 ? NT : 64), hotCap, p.B);
+        const BigShared sh = big_carve(smem_raw, (NT > 32 ? NT : 64), hotCap, p.B, rs.adj + (size_t)w * 2 * p.Cc);
         big_build_adjacency<(NT > 32 ? NT : 64)>(x, p.B, tid, sh, scanScratch);
         real *velPre = rs.pre ? rs.pre + (size_t)w * czr::VP_NF * p.Cc : nullptr;
         pi = resolve_loop_big<(NT > 32 ? NT : 64), false>(x, maxIter, &gs, &bb, tid, &status, sh, nullptr);
@@ -748,7 +749,7 @@ __global__ void __launch_bounds__(NT) k_resolve_islands(WorldParams p, ResolveSc
         const int maxIter = nAll * 8;          // the reference's cap is global (examples/cubedrop.go:73); the sums are checked against it afterwards
         int status = 0, pi, vi;
         if (nC <= hotCap) {
-            const BigShared sh = big_carve(smem_raw, NT, hotCap, p.B);
+            const BigShared sh = big_carve(smem_raw, NT, hotCap, p.B, rs.adj + (size_t)2 * s);
             big_build_adjacency<NT>(x, p.B, tid, sh, scanScratch);
             real *velPre = rs.pre ? rs.pre + (size_t)s * VP_NF : nullptr;
             pi = resolve_loop_big<NT, false>(x, maxIter, &gs, &bb, tid, &status, sh, nullptr);

@@ -403,6 +403,12 @@ struct cz_world {
         uint8_t *dFlags = nullptr;                   // awake_in, can_sleep_in, awake_out
         unsigned int *dNext = nullptr;               // per-chunk world counters
         real *coldX[16] = {};                        // cold-contact scratch per compute stream beyond the first (kernels of different chunks co-run)
+        // RL pipeline slots (cz_world_step_rl_async): staging alternates between two sets, so the downloads of one step overlap the frames of the next
+        real *dInSlot[2] = {}, *dOutSlot[2] = {};
+        float *dObs32[2] = {};
+        cudaEvent_t evSlot[2] = {};
+        int inFlight = 0, nextTicket = 0;
+        long long launchesInFlight = 0, stepsInFlight = 0;
     } pipe;
     real *h_pin = nullptr;
     size_t h_pin_bytes = 0;
@@ -468,6 +474,9 @@ static void host_pipe_destroy(cz_world *w) {
     cudaEventDestroy(pp.evBegin); cudaEventDestroy(pp.evDownDone);
     cudaFree(pp.dIn); cudaFree(pp.dOut); cudaFree(pp.dFlags); cudaFree(pp.dNext);
     for (int k = 1; k < 16; k++) if (pp.coldX[k]) cudaFree(pp.coldX[k]);
+    if (pp.dInSlot[1]) cudaFree(pp.dInSlot[1]);
+    if (pp.dOutSlot[1]) cudaFree(pp.dOutSlot[1]);
+    for (int k = 0; k < 2; k++) { if (pp.dObs32[k]) cudaFree(pp.dObs32[k]); if (pp.evSlot[k]) cudaEventDestroy(pp.evSlot[k]); }
     pp = cz_world::HostPipe();
 }
 
@@ -504,6 +513,7 @@ static int world_plan(cz_world *w) {
             CK(ctx, cudaMalloc(&w->rs.cw, sizeof(real) * (size_t)W * CW_NREAL * Cc));
             CK(ctx, cudaMalloc(&w->rs.cb, sizeof(int) * (size_t)W * 2 * Cc));
             if (!czf::env_int("CUBEZ_RESOLVE_NO_PRE", 0)) CK(ctx, cudaMalloc(&w->rs.pre, sizeof(real) * (size_t)W * czr::VP_NF * Cc));
+            CK(ctx, cudaMalloc(&w->rs.adj, sizeof(unsigned short) * (size_t)W * 2 * Cc));
         }
     }
     // sort-based broadphase for one large world
@@ -655,7 +665,7 @@ int cz_world_destroy(cz_world *w) {
     if (w->d_phase0) cudaFree(w->d_phase0);
     if (w->h_islCount) cudaFreeHost(w->h_islCount);
     void *ptrs[] = {w->isl.start, w->isl.count, w->islBackup, w->d_one, w->d_two, w->gen, w->gb0, w->gb1, w->nContacts, w->posIters, w->velIters, w->stats,
-                    w->tileCount, w->tileBase, w->hitCount, w->rs.bw, w->rs.cw, w->rs.cb, w->rs.pre, w->fused.cold, w->d_next, w->order3,
+                    w->tileCount, w->tileBase, w->hitCount, w->rs.bw, w->rs.cw, w->rs.cb, w->rs.pre, w->rs.adj, w->fused.cold, w->d_next, w->order3,
                     w->fused.coldW, w->fused.preW, w->fused.hotPen, w->fused.hotDdv, w->fused.hotCb0, w->fused.hotCb1, w->d_matFric, w->d_matRest, w->d_bodyMat, w->d_export};
     for (void *p : ptrs) if (p) cudaFree(p);
     if (w->h_stats) cudaFreeHost(w->h_stats);
@@ -867,7 +877,7 @@ static void launch_resolve(cz_world *w, const WorldParams &p, int maxIterOverrid
         const size_t limit = w->ctx->smem_optin > 4096 ? w->ctx->smem_optin - 4096 : 0;
         const size_t big = czr::big_shared_bytes(NT, want, p.B);
         const size_t bytes = (size_t)want * (sizeof(real) + 4);
-        if (want_mode == 3 && want > 0 && want <= 32767 && big <= limit) { mode = 3; hotCap = (int)want; smem = (int)big; }
+        if (want_mode == 3 && want > 0 && want <= 32767 && big <= limit && w->rs.adj) { mode = 3; hotCap = (int)want; smem = (int)big; }
         else if (want > 0 && bytes <= limit) { mode = 2; hotCap = (int)want; smem = (int)bytes; }
     }
     cudaError_t ea = cudaSuccess;
@@ -1288,9 +1298,14 @@ static int host_pipe_init(cz_world *w) {
     CK(ctx, cudaEventCreateWithFlags(&pp.evDownDone, cudaEventDisableTiming));
     CK(ctx, cudaMalloc(&pp.dIn, sizeof(real) * NB * 26));    // pos3 ori4 vel3 rot3 acc3 iitb9 motion1
     CK(ctx, cudaMalloc(&pp.dOut, sizeof(real) * NB * 38));   // pos3 ori4 vel3 rot3 motion1 lacc3 tr12 iitw9
-    CK(ctx, cudaMalloc(&pp.dFlags, 3 * (size_t)NB));
+    CK(ctx, cudaMalloc(&pp.dFlags, 4 * (size_t)NB));         // awake in, can_sleep in, awake out (one per RL pipeline slot)
     CK(ctx, cudaMalloc(&pp.dNext, sizeof(unsigned int) * 4 * chunks));
     for (int k = 1; k < pp.nComp; k++) CK(ctx, cudaMalloc(&pp.coldX[k], sizeof(real) * w->fused.coldReals * (size_t)w->fused.maxGrid * w->fused.groupsPerBlock));
+    pp.dInSlot[0] = pp.dIn; pp.dOutSlot[0] = pp.dOut;          // slot 1 of the RL pipeline is allocated on first asynchronous use
+    for (int k = 0; k < 2; k++) {
+        CK(ctx, cudaEventCreateWithFlags(&pp.evSlot[k], cudaEventDisableTiming));
+        CK(ctx, cudaEventRecord(pp.evSlot[k], ctx->stream));
+    }
     pp.ready = true;
     return CZ_OK;
 }
@@ -1430,43 +1445,34 @@ int cz_world_step_host(cz_world *w, cz_bodies *io, cz_real dt, int32_t n_steps, 
 }
 
 
-int cz_world_step_rl(cz_world *w, const cz_real *add_velocity, const cz_real *add_rotation, cz_bodies *obs, cz_real dt, int32_t n_steps,
-                     cz_step_stats *stats) {
-    if (!w || n_steps < 0) return fail(nullptr, CZ_ERR_INVALID, "cz_world_step_rl: bad argument");
+}  // extern "C"
+
+// float32 observations of the RL step, converted on the device (half the D2H bytes of the Real arrays)
+__global__ void k_unpack_obs32(czb::BodyStore s, long long first, long long n, float *pos, float *ori, float *vel, float *rot) {
+    using namespace czb;
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    const long long i = first + t;
+    if (pos) { V3 v = ld_position(s, i); for (int k = 0; k < 3; k++) pos[i * 3 + k] = (float)v.c[k]; }
+    if (ori) { Q4 q = ld_orientation(s, i); for (int k = 0; k < 4; k++) ori[i * 4 + k] = (float)q.c[k]; }
+    if (vel) { V3 v = ld_velocity(s, i); for (int k = 0; k < 3; k++) vel[i * 3 + k] = (float)v.c[k]; }
+    if (rot) { V3 v = ld_rotation(s, i); for (int k = 0; k < 3; k++) rot[i * 3 + k] = (float)v.c[k]; }
+}
+
+// Enqueue one RL step of a fused world on pipeline slot `slot` (0 / 1): actions H2D | apply + frames + unpack | observations
+// D2H, chunked over the world range.  Nothing here waits for the device.  Slot s reuses the staging buffers of the call
+// two tickets earlier, ordered behind that call's last download by evSlot[s].
+static int rl_enqueue(cz_world *w, const cz_real *add_velocity, const cz_real *add_rotation, cz_bodies *obs, cz_obs32 *obs32, cz_real dt,
+                      int32_t n_steps, int slot, long long &launches, bool afterContextStream, bool contextStreamWaits) {
     cz_ctx *ctx = w->ctx;
-    if (obs && obs->n != w->b.n) return fail(ctx, CZ_ERR_INVALID, "cz_world_step_rl: obs->n must equal n_worlds*bodies_per_world");
-    CK(ctx, cudaSetDevice(ctx->device));
-    if (!w->useFused) {
-        // any world shape: actions, resident step, observations (no chunk pipeline: the multi-kernel path steps the whole batch)
-        const long long NB0 = w->b.n;
-        int rc0;
-        if (add_velocity || add_rotation) {
-            if ((rc0 = host_pipe_init(w))) return rc0;
-            real *dV = w->pipe.dIn, *dR = dV + NB0 * 3;
-            if (add_velocity) CK(ctx, cudaMemcpyAsync(dV, add_velocity, sizeof(real) * NB0 * 3, cudaMemcpyHostToDevice, ctx->stream));
-            if (add_rotation) CK(ctx, cudaMemcpyAsync(dR, add_rotation, sizeof(real) * NB0 * 3, cudaMemcpyHostToDevice, ctx->stream));
-            k_apply_actions<<<nblk(NB0, 256), 256, 0, ctx->stream>>>(w->b.st, 0, NB0, add_velocity ? dV : nullptr, add_rotation ? dR : nullptr);
-            CKL(ctx);
-        }
-        if ((rc0 = cz_world_step(w, dt, n_steps, stats))) return rc0;
-        if (obs) {
-            cz_bodies o{};
-            o.n = obs->n; o.position = obs->position; o.orientation = obs->orientation; o.velocity = obs->velocity; o.rotation = obs->rotation;
-            o.motion = obs->motion; o.is_awake = obs->is_awake; o.transform = obs->transform;
-            o.inverse_inertia_tensor_world = obs->inverse_inertia_tensor_world; o.last_frame_acceleration = obs->last_frame_acceleration;
-            return download_bodies(w->b, 0, NB0, &o);
-        }
-        return CZ_OK;
-    }
-    int rc;
-    if ((rc = world_prepare_step(w, dt))) return rc;
-    if ((rc = host_pipe_init(w))) return rc;
     auto &pp = w->pipe;
+    int rc = CZ_OK;
     const long long NB = w->b.n, B = w->d.bodies_per_world;
     const int W = w->d.n_worlds;
-    real *dVel = pp.dIn, *dRot = dVel + NB * 3;
-    real *oPos = pp.dOut, *oOri = oPos + NB * 3, *oVel = oOri + NB * 4, *oRot = oVel + NB * 3, *oMot = oRot + NB * 3, *oLacc = oMot + NB, *oTr = oLacc + NB * 3, *oIitw = oTr + NB * 12;
-    uint8_t *fAwakeOut = pp.dFlags + 2 * NB;
+    real *dVel = pp.dInSlot[slot], *dRot = dVel + NB * 3;
+    real *oPos = pp.dOutSlot[slot], *oOri = oPos + NB * 3, *oVel = oOri + NB * 4, *oRot = oVel + NB * 3, *oMot = oRot + NB * 3, *oLacc = oMot + NB, *oTr = oLacc + NB * 3, *oIitw = oTr + NB * 12;
+    uint8_t *fAwakeOut = pp.dFlags + (2 + slot) * NB;
+    float *fPos = pp.dObs32[slot], *fOri = fPos ? fPos + NB * 3 : nullptr, *fVel = fPos ? fOri + NB * 4 : nullptr, *fRot = fPos ? fVel + NB * 3 : nullptr;
     HostOut hout{};
     if (obs) {
         hout.pos = obs->position ? oPos : nullptr; hout.ori = obs->orientation ? oOri : nullptr; hout.vel = obs->velocity ? oVel : nullptr;
@@ -1474,15 +1480,16 @@ int cz_world_step_rl(cz_world *w, const cz_real *add_velocity, const cz_real *ad
         hout.tr = obs->transform ? oTr : nullptr; hout.iitw = obs->inverse_inertia_tensor_world ? oIitw : nullptr; hout.awake = obs->is_awake ? fAwakeOut : nullptr;
     }
     const bool anyOut = hout.pos || hout.ori || hout.vel || hout.rot || hout.motion || hout.lacc || hout.tr || hout.iitw || hout.awake;
+    const bool any32 = obs32 && (obs32->position || obs32->orientation || obs32->velocity || obs32->rotation);
     const bool anyIn = add_velocity || add_rotation;
-    CK(ctx, cudaMemsetAsync(w->stats, 0, sizeof(unsigned long long) * ST_STATUS, ctx->stream));
-    CK(ctx, cudaMemsetAsync(pp.dNext, 0, sizeof(unsigned int) * 4 * pp.chunks, ctx->stream));
-    CK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
-    CK(ctx, cudaEventRecord(pp.evBegin, ctx->stream));
-    CK(ctx, cudaStreamWaitEvent(pp.sUp, pp.evBegin, 0));
-    CK(ctx, cudaStreamWaitEvent(pp.sDown, pp.evBegin, 0));
-    for (int k = 0; k < pp.nComp; k++) CK(ctx, cudaStreamWaitEvent(pp.sComp[k], pp.evBegin, 0));
-    long long launches = 0;
+    if (afterContextStream) {   // order the pipeline behind whatever the caller queued on the context stream (uploads, earlier steps)
+        CK(ctx, cudaEventRecord(pp.evBegin, ctx->stream));
+        CK(ctx, cudaStreamWaitEvent(pp.sUp, pp.evBegin, 0));
+        CK(ctx, cudaStreamWaitEvent(pp.sDown, pp.evBegin, 0));
+        for (int k = 0; k < pp.nComp; k++) CK(ctx, cudaStreamWaitEvent(pp.sComp[k], pp.evBegin, 0));
+    }
+    CK(ctx, cudaStreamWaitEvent(pp.sUp, pp.evSlot[slot], 0));          // the staging of this slot is free again
+    for (int k = 0; k < pp.nComp; k++) CK(ctx, cudaStreamWaitEvent(pp.sComp[k], pp.evSlot[slot], 0));
     // observations are a third of the full state: fewer, larger chunks keep the fused kernels efficient
     const int chunks = std::max(1, std::min(pp.chunks, czf::env_int("CUBEZ_RL_CHUNKS", 4)));
     const std::vector<int> wEdge = host_chunk_edges(chunks, W);
@@ -1529,6 +1536,12 @@ int cz_world_step_rl(cz_world *w, const cz_real *add_velocity, const cz_real *ad
             CKL(ctx);
             launches++;
         }
+        if (any32) {
+            k_unpack_obs32<<<nblk(nb, 256), 256, 0, cs>>>(w->b.st, b0, nb, obs32->position ? fPos : nullptr, obs32->orientation ? fOri : nullptr,
+                                                          obs32->velocity ? fVel : nullptr, obs32->rotation ? fRot : nullptr);
+            CKL(ctx);
+            launches++;
+        }
         CK(ctx, cudaEventRecord(pp.evComp[c], cs));
         CK(ctx, cudaStreamWaitEvent(pp.sDown, pp.evComp[c], 0));
         if (anyOut) {
@@ -1536,17 +1549,126 @@ int cz_world_step_rl(cz_world *w, const cz_real *add_velocity, const cz_real *ad
             DOWN(obs->motion, oMot, 1); DOWN(obs->last_frame_acceleration, oLacc, 3); DOWN(obs->transform, oTr, 12);
             DOWN(obs->inverse_inertia_tensor_world, oIitw, 9); DOWN(obs->is_awake, fAwakeOut, 1);
         }
+        if (any32) {
+            DOWN(obs32->position, fPos, 3); DOWN(obs32->orientation, fOri, 4); DOWN(obs32->velocity, fVel, 3); DOWN(obs32->rotation, fRot, 3);
+        }
     }
 #undef UP
 #undef DOWN
     w->step_index += n_steps;
-    CK(ctx, cudaEventRecord(pp.evDownDone, pp.sDown));
-    CK(ctx, cudaStreamWaitEvent(ctx->stream, pp.evDownDone, 0));
+    CK(ctx, cudaEventRecord(pp.evSlot[slot], pp.sDown));     // everything of this call — frames and downloads — is behind this event
+    if (contextStreamWaits) CK(ctx, cudaStreamWaitEvent(ctx->stream, pp.evSlot[slot], 0));
+    return CZ_OK;
+}
+
+extern "C" {
+
+int cz_world_step_rl(cz_world *w, const cz_real *add_velocity, const cz_real *add_rotation, cz_bodies *obs, cz_real dt, int32_t n_steps,
+                     cz_step_stats *stats) {
+    if (!w || n_steps < 0) return fail(nullptr, CZ_ERR_INVALID, "cz_world_step_rl: bad argument");
+    cz_ctx *ctx = w->ctx;
+    if (obs && obs->n != w->b.n) return fail(ctx, CZ_ERR_INVALID, "cz_world_step_rl: obs->n must equal n_worlds*bodies_per_world");
+    CK(ctx, cudaSetDevice(ctx->device));
+    if (!w->useFused) {
+        // any world shape: actions, resident step, observations (no chunk pipeline: the multi-kernel path steps the whole batch)
+        const long long NB0 = w->b.n;
+        int rc0;
+        if (add_velocity || add_rotation) {
+            if ((rc0 = host_pipe_init(w))) return rc0;
+            real *dV = w->pipe.dIn, *dR = dV + NB0 * 3;
+            if (add_velocity) CK(ctx, cudaMemcpyAsync(dV, add_velocity, sizeof(real) * NB0 * 3, cudaMemcpyHostToDevice, ctx->stream));
+            if (add_rotation) CK(ctx, cudaMemcpyAsync(dR, add_rotation, sizeof(real) * NB0 * 3, cudaMemcpyHostToDevice, ctx->stream));
+            k_apply_actions<<<nblk(NB0, 256), 256, 0, ctx->stream>>>(w->b.st, 0, NB0, add_velocity ? dV : nullptr, add_rotation ? dR : nullptr);
+            CKL(ctx);
+        }
+        if ((rc0 = cz_world_step(w, dt, n_steps, stats))) return rc0;
+        if (obs) {
+            cz_bodies o{};
+            o.n = obs->n; o.position = obs->position; o.orientation = obs->orientation; o.velocity = obs->velocity; o.rotation = obs->rotation;
+            o.motion = obs->motion; o.is_awake = obs->is_awake; o.transform = obs->transform;
+            o.inverse_inertia_tensor_world = obs->inverse_inertia_tensor_world; o.last_frame_acceleration = obs->last_frame_acceleration;
+            return download_bodies(w->b, 0, NB0, &o);
+        }
+        return CZ_OK;
+    }
+    int rc;
+    if ((rc = world_prepare_step(w, dt))) return rc;
+    if ((rc = host_pipe_init(w))) return rc;
+    auto &pp = w->pipe;
+    if (pp.inFlight) return fail(ctx, CZ_ERR_INVALID, "cz_world_step_rl: asynchronous RL steps are in flight (cz_world_rl_wait first)");
+    CK(ctx, cudaMemsetAsync(w->stats, 0, sizeof(unsigned long long) * ST_STATUS, ctx->stream));
+    CK(ctx, cudaMemsetAsync(pp.dNext, 0, sizeof(unsigned int) * 4 * pp.chunks, ctx->stream));
+    CK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    long long launches = 0;
+    if ((rc = rl_enqueue(w, add_velocity, add_rotation, obs, nullptr, dt, n_steps, 0, launches, true, true))) return rc;
     CK(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
     CK(ctx, cudaEventSynchronize(ctx->ev1));
     float ms = 0;
     CK(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
     return read_stats(w, stats, launches, n_steps, ms);
+}
+
+int cz_world_step_rl_async(cz_world *w, const cz_real *add_velocity, const cz_real *add_rotation, cz_bodies *obs, cz_obs32 *obs32, cz_real dt,
+                           int32_t n_steps, int32_t *ticket) {
+    if (!w || n_steps < 0 || !ticket) return fail(nullptr, CZ_ERR_INVALID, "cz_world_step_rl_async: bad argument");
+    cz_ctx *ctx = w->ctx;
+    if ((obs && obs->n != w->b.n) || (obs32 && obs32->n != w->b.n)) return fail(ctx, CZ_ERR_INVALID, "cz_world_step_rl_async: obs->n must equal n_worlds*bodies_per_world");
+    CK(ctx, cudaSetDevice(ctx->device));
+    if (!w->useFused) return fail(ctx, CZ_ERR_INVALID, "cz_world_step_rl_async needs a world on the fused small-world kernel (use cz_world_step_rl)");
+    int rc;
+    if ((rc = world_prepare_step(w, dt))) return rc;
+    if ((rc = host_pipe_init(w))) return rc;
+    auto &pp = w->pipe;
+    if (pp.inFlight >= 2) return fail(ctx, CZ_ERR_INVALID, "cz_world_step_rl_async: two steps are already in flight (cz_world_rl_wait on the older ticket first)");
+    if (!pp.dInSlot[1]) {
+        CK(ctx, cudaMalloc(&pp.dInSlot[1], sizeof(real) * w->b.n * 6));
+        CK(ctx, cudaMalloc(&pp.dOutSlot[1], sizeof(real) * w->b.n * 38));
+    }
+    if (obs32 && !pp.dObs32[0]) {
+        for (int k = 0; k < 2; k++) CK(ctx, cudaMalloc(&pp.dObs32[k], sizeof(float) * 13 * (size_t)w->b.n));
+    }
+    if (pp.inFlight == 0) {
+        CK(ctx, cudaMemsetAsync(pp.dNext, 0, sizeof(unsigned int) * 4 * pp.chunks, ctx->stream));
+        CK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    }
+    const int t = pp.nextTicket++;
+    long long launches = 0;
+    if ((rc = rl_enqueue(w, add_velocity, add_rotation, obs, obs32, dt, n_steps, t & 1, launches, pp.inFlight == 0, false))) return rc;
+    pp.launchesInFlight += launches;
+    pp.stepsInFlight += n_steps;
+    pp.inFlight++;
+    *ticket = t;
+    return CZ_OK;
+}
+
+int cz_world_rl_wait(cz_world *w, int32_t ticket, cz_step_stats *stats) {
+    if (!w) return CZ_ERR_INVALID;
+    cz_ctx *ctx = w->ctx;
+    CK(ctx, cudaSetDevice(ctx->device));
+    auto &pp = w->pipe;
+    if (!pp.ready || pp.inFlight <= 0 || ticket < pp.nextTicket - pp.inFlight || ticket >= pp.nextTicket)
+        return fail(ctx, CZ_ERR_INVALID, "cz_world_rl_wait: no such step in flight");
+    if (ticket != pp.nextTicket - pp.inFlight) return fail(ctx, CZ_ERR_INVALID, "cz_world_rl_wait: wait on the older ticket first");
+    CK(ctx, cudaEventSynchronize(pp.evSlot[ticket & 1]));
+    pp.inFlight--;
+    if (pp.inFlight == 0) CK(ctx, cudaStreamWaitEvent(ctx->stream, pp.evSlot[ticket & 1], 0));   // later calls on the context stream come after the pipeline
+    if (!stats) return CZ_OK;
+    // counters are cumulative since the last wait with stats (frames of a younger step in flight may already be in them)
+    CK(ctx, cudaMemcpy(w->h_stats, w->stats, sizeof(unsigned long long) * ST_N, cudaMemcpyDeviceToHost));
+    std::memset(stats, 0, sizeof(*stats));
+    stats->steps = (int64_t)w->d.n_worlds * pp.stepsInFlight;
+    stats->contacts = (int64_t)w->h_stats[ST_CONTACTS];
+    stats->pos_iterations = (int64_t)w->h_stats[ST_POS];
+    stats->vel_iterations = (int64_t)w->h_stats[ST_VEL];
+    stats->kernel_launches = pp.launchesInFlight;
+    stats->max_contacts = (int32_t)w->h_stats[ST_MAXC];
+    stats->status = -(int)w->h_stats[ST_STATUS];
+    if (pp.inFlight == 0) {   // quiescent: reset the cumulative counters
+        CK(ctx, cudaMemset(w->stats, 0, sizeof(unsigned long long) * ST_N));
+        pp.launchesInFlight = 0;
+        pp.stepsInFlight = 0;
+    }
+    return status_error(ctx, stats->status);
 }
 
 // ---- object-API shims ------------------------------------------------------------------------

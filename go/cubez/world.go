@@ -537,6 +537,53 @@ func (w *World) StepRL(addVelocity, addRotation []m.Real, obs *HostBodies, dt m.
 	return statsOf(&st)
 }
 
+// Obs32 holds float32 observations of the pipelined RL step in pinned memory (PinnedFloats): position 3, orientation 4
+// (w, x, y, z), velocity 3, rotation 3 per body — half the download bytes of the Real arrays.
+type Obs32 struct {
+	c                                         C.cz_obs32
+	Position, Orientation, Velocity, Rotation []float32
+}
+
+// NewObs32 allocates pinned float32 observation arrays for n bodies.
+func NewObs32(n int) *Obs32 {
+	o := &Obs32{Position: PinnedFloats(3 * n), Orientation: PinnedFloats(4 * n), Velocity: PinnedFloats(3 * n), Rotation: PinnedFloats(3 * n)}
+	o.c.n = C.int32_t(n)
+	o.c.position, o.c.orientation = (*C.float)(unsafe.Pointer(&o.Position[0])), (*C.float)(unsafe.Pointer(&o.Orientation[0]))
+	o.c.velocity, o.c.rotation = (*C.float)(unsafe.Pointer(&o.Velocity[0])), (*C.float)(unsafe.Pointer(&o.Rotation[0]))
+	return o
+}
+
+// StepRLAsync — cz_world_step_rl_async: the pipelined form of StepRL.  Returns a ticket at once; up to two steps may be
+// in flight (RLWait on the older ticket first), so the observations of step t travel to the host while the frames of
+// step t+1 run.  Use two sets of observation buffers and do not touch a set whose step is in flight.
+func (w *World) StepRLAsync(addVelocity, addRotation []m.Real, obs *HostBodies, obs32 *Obs32, dt m.Real, n int) int {
+	var av, ar *C.cz_real
+	if addVelocity != nil {
+		av = (*C.cz_real)(unsafe.Pointer(&addVelocity[0]))
+	}
+	if addRotation != nil {
+		ar = (*C.cz_real)(unsafe.Pointer(&addRotation[0]))
+	}
+	var o *C.cz_bodies
+	if obs != nil {
+		o = &obs.c
+	}
+	var o32 *C.cz_obs32
+	if obs32 != nil {
+		o32 = &obs32.c
+	}
+	var ticket C.int32_t
+	check(C.cz_world_step_rl_async(w.h, av, ar, o, o32, C.cz_real(dt), C.int32_t(n), &ticket))
+	return int(ticket)
+}
+
+// RLWait — cz_world_rl_wait: blocks until the observations of the step with this ticket are complete.
+func (w *World) RLWait(ticket int) StepStats {
+	var st C.cz_step_stats
+	check(C.cz_world_rl_wait(w.h, C.int32_t(ticket), &st))
+	return statsOf(&st)
+}
+
 // ExportGL — cz_world_export_gl: float32 Location (3 per body) and LocalRotation (4 per body: W, V[0], V[1], V[2]) of
 // every body of worlds [firstWorld, firstWorld+nWorlds) — the per-frame SetGlVector3 / SetGlQuat copy of
 // examples/cubedrop.go:35-37 and examples/exampleapp.go:146-159, converted on the device.  model (optional) receives

@@ -297,6 +297,22 @@ int cz_world_step_host(cz_world *w, cz_bodies *io, cz_real dt, int32_t n_steps, 
 int cz_world_step_rl(cz_world *w, const cz_real *add_velocity, const cz_real *add_rotation, cz_bodies *obs, cz_real dt,
                      int32_t n_steps, cz_step_stats *stats);
 
+/* Pipelined RL loop (new API): the same step, asynchronous.  cz_world_step_rl_async enqueues the actions' upload, the
+ * frames and the observations' download and returns a ticket at once; cz_world_rl_wait(ticket) blocks until the
+ * observation arrays of that step are complete.  Up to TWO steps may be in flight (wait on the older ticket first):
+ * while the observations of step t travel to the host, the frames of step t+1 already run — the device staging buffers
+ * alternate, so use two sets of (pinned) host arrays as well and do not touch a set whose step is in flight.  No other
+ * call on the world while steps are in flight.  obs32 (optional): observations as float32, converted on the device —
+ * position 3, orientation 4 (w,x,y,z), velocity 3, rotation 3 per body; half the bytes of the Real arrays.  The stats
+ * of cz_world_rl_wait are cumulative since the previous wait with stats (frames of the younger step may be included). */
+typedef struct cz_obs32 {
+    int32_t n;
+    float *position, *orientation, *velocity, *rotation; /* any may be NULL */
+} cz_obs32;
+int cz_world_step_rl_async(cz_world *w, const cz_real *add_velocity, const cz_real *add_rotation, cz_bodies *obs, cz_obs32 *obs32, cz_real dt,
+                           int32_t n_steps, int32_t *ticket);
+int cz_world_rl_wait(cz_world *w, int32_t ticket, cz_step_stats *stats);
+
 /* ---- multi-GPU runs of batched worlds (new API) -----------------------------------------------
  * Worlds share no state, so a batch is partitioned by world index into contiguous shards, one per device: shard k
  * of n owns worlds [k*W/n, (k+1)*W/n).  ONE host process drives every shard (each on its own stream of its own

@@ -20,7 +20,7 @@ _LIBS = {}
 def load(prec: str = "f64") -> C.CDLL:
     if prec in _LIBS:
         return _LIBS[prec]
-    path = os.path.join(ROOT, "oracle", "_build", f"liboracle_{prec}.so")
+    path = os.path.join(ROOT, "oracle", "_build", f"liboracle_{prec}{os.environ.get('CUBEZ_ORACLE_SUFFIX', '')}.so")   # _asan: the sanitizer build
     if not os.path.exists(path):
         import subprocess
         subprocess.check_call(["make", "-s"], cwd=os.path.join(ROOT, "oracle"))

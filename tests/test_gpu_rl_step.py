@@ -145,3 +145,43 @@ def test_step_rl_tiny_batches_and_zero_frames(n_worlds):
     for f in BatchedWorld.OBS_FIELDS:
         assert np.array_equal(getattr(obs, f), getattr(c, f)), f
     gpu.close()
+
+
+@pytest.mark.parametrize("n_worlds", [96, 24000])
+def test_pipelined_rl_step_equals_the_synchronous_one(n_worlds):
+    """cz_world_step_rl_async / cz_world_rl_wait with two steps in flight and alternating buffers: every observation
+    (float64 arrays and the float32 ones converted on the device) equals what the synchronous step returns, frame by
+    frame; the 24 000-world case runs the split-phase launches."""
+    sc = scenes.batched_cubedrop(n_worlds=n_worlds)
+    ctx = Context.get(0, "f64")
+    a, b = BatchedWorld.from_scene(sc, contacts_per_world=64), BatchedWorld.from_scene(sc, contacts_per_world=64)
+    nb = n_worlds * 8
+    rng = np.random.default_rng(3)
+    frames = 40 if n_worlds < 1000 else 12
+    acts = [ctx.pinned_array((nb, 3)) for _ in range(2)]
+    obs = [ctx.pinned_bodies(nb, fields=BatchedWorld.OBS_FIELDS) for _ in range(2)]
+    obs32 = [{k: ctx.pinned_array((nb, c), dtype=np.float32) for k, c in (("position", 3), ("orientation", 4), ("velocity", 3), ("rotation", 3))} for _ in range(2)]
+    ref_act, ref_obs = ctx.pinned_array((nb, 3)), ctx.pinned_bodies(nb, fields=BatchedWorld.OBS_FIELDS)
+    actions = [rng.uniform(-0.2, 0.2, (nb, 3)) * (rng.uniform(0, 1, (nb, 1)) < 0.3) for _ in range(frames)]
+    expected = []
+    for f in range(frames):
+        ref_act[...] = actions[f]
+        a.step_rl(ref_act, None, ref_obs, sc.dt, 1)
+        expected.append({k: getattr(ref_obs, k).copy() for k in BatchedWorld.OBS_FIELDS})
+    tickets = []
+    def check(f):
+        b.rl_wait(tickets[f])
+        for k in BatchedWorld.OBS_FIELDS:
+            assert np.array_equal(getattr(obs[f & 1], k), expected[f][k]), (f, k)
+            assert np.array_equal(obs32[f & 1][k], expected[f][k].astype(np.float32)), (f, k, "f32")
+    for f in range(frames):
+        if f >= 2:
+            check(f - 2)                          # frees slot f & 1
+        acts[f & 1][...] = actions[f]
+        tickets.append(b.step_rl_async(acts[f & 1], None, obs[f & 1], obs32[f & 1], sc.dt, 1))
+    check(frames - 2); check(frames - 1)
+    assert a.checksum_energy()[0] == b.checksum_energy()[0]
+    from cubez_b200._abi import CubezError
+    with pytest.raises(CubezError):
+        b.rl_wait(tickets[-1])                    # nothing in flight any more
+    a.close(); b.close()
