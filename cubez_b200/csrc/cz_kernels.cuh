@@ -602,10 +602,11 @@ __global__ void __launch_bounds__(NT) k_resolve(WorldParams p, ResolveScratch rs
         pi = resolve_loop<32, false>(x, true, maxIter, tid, &status);
         __syncthreads();
         vi = resolve_loop<32, true>(x, true, maxIter, tid, &status);
-    } else if (useSmem == 3 && nC <= hotCap) {   // one large world: adjacency lists + shared arg-max caches + prefetched propagation
+    } else if ((useSmem == 3 || useSmem == 4) && nC <= hotCap) {   // one large world: adjacency lists + shared arg-max caches + prefetched propagation (4: list offsets in global memory too)
         __shared__ BigBroadcast bb;
         __shared__ int scanScratch[NT / 32 + 1];
-        const BigShared sh = big_carve(smem_raw, (NT > 32 ? NT : 64), hotCap, p.B, rs.adj + (size_t)w * 2 * p.Cc);
+        unsigned short *adjW = rs.adj + (size_t)w * (2 * (size_t)p.Cc + p.B + 2);
+        const BigShared sh = big_carve(smem_raw, (NT > 32 ? NT : 64), hotCap, p.B, adjW, useSmem == 4 ? adjW + 2 * (size_t)p.Cc : nullptr);
         big_build_adjacency<(NT > 32 ? NT : 64)>(x, p.B, tid, sh, scanScratch);
         real *velPre = rs.pre ? rs.pre + (size_t)w * czr::VP_NF * p.Cc : nullptr;
         pi = resolve_loop_big<(NT > 32 ? NT : 64), false>(x, maxIter, &gs, &bb, tid, &status, sh, nullptr);
@@ -749,7 +750,7 @@ __global__ void __launch_bounds__(NT) k_resolve_islands(WorldParams p, ResolveSc
         const int maxIter = nAll * 8;          // the reference's cap is global (examples/cubedrop.go:73); the sums are checked against it afterwards
         int status = 0, pi, vi;
         if (nC <= hotCap) {
-            const BigShared sh = big_carve(smem_raw, NT, hotCap, p.B, rs.adj + (size_t)2 * s);
+            const BigShared sh = big_carve(smem_raw, NT, hotCap, p.B, rs.adj + (size_t)2 * s);   // (W = 1 on this path)
             big_build_adjacency<NT>(x, p.B, tid, sh, scanScratch);
             real *velPre = rs.pre ? rs.pre + (size_t)s * VP_NF : nullptr;
             pi = resolve_loop_big<NT, false>(x, maxIter, &gs, &bb, tid, &status, sh, nullptr);

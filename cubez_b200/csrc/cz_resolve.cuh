@@ -856,22 +856,25 @@ struct BigShared {
     unsigned char *dirty;       // [NT] owner must be re-scanned
 };
 // shared-memory bytes of the plan for `cap` contacts (cap <= 32767) and B bodies (B < 65535)
-static inline size_t big_shared_bytes(int NT, long long cap, long long B) {
+// offsetsInGlobal: the list offsets live in global memory too (used when keeping them would push the CTA over the next
+// shared-memory carve-out step and take the L1 away from the cold records: 196 -> 228 KB leaves 28 KB of L1)
+static inline size_t big_shared_bytes(int NT, long long cap, long long B, bool offsetsInGlobal = false) {
     size_t hotBytes = (size_t)cap * sizeof(real);
     if (hotBytes < (size_t)B * sizeof(int)) hotBytes = (size_t)B * sizeof(int);   // the CSR build borrows the region for its counters
     size_t bytes = (hotBytes + 15) / 16 * 16;
-    bytes += ((size_t)(B + 1) * sizeof(unsigned short) + 15) / 16 * 16;
+    if (!offsetsInGlobal) bytes += ((size_t)(B + 1) * sizeof(unsigned short) + 15) / 16 * 16;
     bytes += (size_t)NT * (sizeof(real) + sizeof(int) + 1) + 16;
     return (bytes + 15) / 16 * 16;
 }
-__device__ __forceinline__ BigShared big_carve(unsigned char *base, int NT, int cap, int B, unsigned short *adjListGlobal) {
+__device__ __forceinline__ BigShared big_carve(unsigned char *base, int NT, int cap, int B, unsigned short *adjListGlobal, unsigned short *adjOffGlobal = nullptr) {
     BigShared s;
     size_t hotBytes = (size_t)cap * sizeof(real);
     if (hotBytes < (size_t)B * sizeof(int)) hotBytes = (size_t)B * sizeof(int);
     size_t off = 0;
     s.hot = (real *)base; off += (hotBytes + 15) / 16 * 16;
     s.adjList = adjListGlobal;
-    s.adjOff = (unsigned short *)(base + off); off += ((size_t)(B + 1) * sizeof(unsigned short) + 15) / 16 * 16;
+    if (adjOffGlobal) s.adjOff = adjOffGlobal;
+    else { s.adjOff = (unsigned short *)(base + off); off += ((size_t)(B + 1) * sizeof(unsigned short) + 15) / 16 * 16; }
     s.cacheV = (real *)(base + off); off += (size_t)NT * sizeof(real);
     s.cacheI = (int *)(base + off); off += (size_t)NT * sizeof(int);
     s.dirty = base + off;

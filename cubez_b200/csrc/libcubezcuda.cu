@@ -513,7 +513,7 @@ static int world_plan(cz_world *w) {
             CK(ctx, cudaMalloc(&w->rs.cw, sizeof(real) * (size_t)W * CW_NREAL * Cc));
             CK(ctx, cudaMalloc(&w->rs.cb, sizeof(int) * (size_t)W * 2 * Cc));
             if (!czf::env_int("CUBEZ_RESOLVE_NO_PRE", 0)) CK(ctx, cudaMalloc(&w->rs.pre, sizeof(real) * (size_t)W * czr::VP_NF * Cc));
-            CK(ctx, cudaMalloc(&w->rs.adj, sizeof(unsigned short) * (size_t)W * 2 * Cc));
+            CK(ctx, cudaMalloc(&w->rs.adj, sizeof(unsigned short) * (size_t)W * (2 * (size_t)Cc + B + 2)));   // lists, then the list offsets
         }
     }
     // sort-based broadphase for one large world
@@ -868,16 +868,24 @@ static void launch_resolve(cz_world *w, const WorldParams &p, int maxIterOverrid
     int smem = forceGlobal ? 0 : w->resolveSmem;
     int mode = smem > 0 ? 1 : 0, hotCap = 0;
     // CUBEZ_RESOLVE_MODE: 0 plain CTA loop, 2 staged hot values + cached arg-max (round 1), 3 adjacency lists (default)
-    const int want_mode = czf::env_int("CUBEZ_RESOLVE_NO_CACHE", 0) ? 0 : czf::env_int("CUBEZ_RESOLVE_MODE", 3);
+    int want_mode = czf::env_int("CUBEZ_RESOLVE_NO_CACHE", 0) ? 0 : czf::env_int("CUBEZ_RESOLVE_MODE", 3);
+    if (want_mode == 4) want_mode = 3;   // 4 = mode 3 with the list offsets forced into global memory (test hook)
     if (NT > 32 && mode == 0 && p.B < 0xffff && want_mode != 0) {
         // one large world: the loop's working set in shared memory.  The host knows the contact count on the
         // broadphase path; otherwise size for the capacity.
         long long want = contactsHint >= 0 ? std::min<long long>(contactsHint, p.Cc) : p.Cc;
         want = (want + 255) / 256 * 256;
         const size_t limit = w->ctx->smem_optin > 4096 ? w->ctx->smem_optin - 4096 : 0;
-        const size_t big = czr::big_shared_bytes(NT, want, p.B);
+        size_t big = czr::big_shared_bytes(NT, want, p.B);
         const size_t bytes = (size_t)want * (sizeof(real) + 4);
-        if (want_mode == 3 && want > 0 && want <= 32767 && big <= limit && w->rs.adj) { mode = 3; hotCap = (int)want; smem = (int)big; }
+        // shared-memory carve-out steps of the SM: what is not carved stays L1 for the cold contact records
+        auto carve = [](size_t b) { for (size_t kb : {8, 16, 32, 64, 100, 132, 164, 196, 228}) if (b + 2048 <= kb * 1024) return kb; return (size_t)256; };
+        bool offsetsInGlobal = false;
+        if (want_mode == 3 && w->rs.adj) {
+            const size_t lean = czr::big_shared_bytes(NT, want, p.B, true);
+            if (big > limit || carve(lean) < carve(big) || czf::env_int("CUBEZ_RESOLVE_MODE", 3) == 4) { big = lean; offsetsInGlobal = true; }
+        }
+        if (want_mode == 3 && want > 0 && want <= 32767 && big <= limit && w->rs.adj) { mode = offsetsInGlobal ? 4 : 3; hotCap = (int)want; smem = (int)big; }
         else if (want > 0 && bytes <= limit) { mode = 2; hotCap = (int)want; smem = (int)bytes; }
     }
     cudaError_t ea = cudaSuccess;

@@ -117,7 +117,7 @@ def test_large_world_resolver_variants_make_identical_choices(monkeypatch):
     from cubez_b200.api import BatchedWorld
     scene = scenes.pile(side=8)
     runs = []
-    for mode in ("3", "2", "0"):
+    for mode in ("3", "4", "2", "0"):       # 4: mode 3 with the adjacency offsets in global memory as well (what > 23 k contacts use)
         monkeypatch.setenv("CUBEZ_RESOLVE_MODE", mode)
         gpu = BatchedWorld.from_scene(scene, flags=_abi.WORLD_BROADPHASE)
         counts = []
