@@ -256,8 +256,11 @@ int czo_world_upload_bodies(void *h, int32_t first, int32_t n, const cz_bodies *
     const int B = w->desc.bodies_per_world;
     for (int k = 0; k < n; k++)
         for (int i = 0; i < B; i++) {
-            load_body(w->worlds[first + k].bodies[i], b, k * B + i);
-            if (derive) body_calculate_derived(w->worlds[first + k].bodies[i]);
+            Body<R> &body = w->worlds[first + k].bodies[i];
+            const V3<R> fAcc = body.forceAccum, tAcc = body.torqueAccum;   // a state upload does not touch pending accumulators
+            load_body(body, b, k * B + i);                                  // (they are not part of cz_bodies; cz_world_add_forces owns them)
+            body.forceAccum = fAcc; body.torqueAccum = tAcc;
+            if (derive) body_calculate_derived(body);
         }
     return 0;
 }
