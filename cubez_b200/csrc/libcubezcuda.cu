@@ -708,6 +708,7 @@ int cz_world_upload_colliders(cz_world *w, int32_t first, int32_t n, const cz_co
 int cz_world_upload_planes(cz_world *w, const cz_planes *p) {
     if (!w || !p) return CZ_ERR_INVALID;
     if (p->n > CZ_MAX_PLANES) return fail(w->ctx, CZ_ERR_INVALID, "too many planes (max 8)");
+    CK(w->ctx, cudaSetDevice(w->ctx->device));   // the re-plan below allocates: on THIS world's device, whatever the calling thread's current one is
     w->P = p->n;
     for (int i = 0; i < p->n; i++) {
         w->planes[i].n = czm::mk3(p->normal[i * 3], p->normal[i * 3 + 1], p->normal[i * 3 + 2]);

@@ -4,14 +4,24 @@
 // link or call this file.  Only tests/, __graft_entry__.smoke() and bench.py's
 // cpu_baseline / --impl reference legs use it, and only as the checker / CPU baseline.
 //
-// *** PARITY STATUS ***  The reference (tbogdala/cubez) is Go; there is no Go toolchain in
-// this image, so the reference itself can not be run here.  The math layer of this oracle
-// is pinned against the reference's own known-answer tests (math/vector_test.go,
-// math/quaternion_test.go, math/matrix_test.go — see tests/test_oracle_math_kat.py).
-// For Integrate, every narrowphase routine and the resolver the reference holds no test,
-// golden vector or fixture: for those functions this oracle is "PARITY UNPINNED" — it is a
-// line-by-line restatement of the Go source in the same expression order (left to right,
-// one IEEE rounding per operation, no FMA contraction: build with -ffp-contract=off).
+// *** PARITY STATUS: PINNED AGAINST THE REFERENCE'S OWN SOURCE, RUN HERE ***
+// The reference (tbogdala/cubez) is Go and no Go toolchain exists in this image.  Its sources are therefore run
+// through oracle/go2cpp.py, a syntax-directed Go -> C++ translator (it knows Go, not physics; see its header), together
+// with the headless harness mains of go/harness/ — oracle/Makefile target `ref`, outputs in oracle/_ref/ only.
+//   * math layer: the reference's own 22 known-answer tests (math/vector_test.go, quaternion_test.go, matrix_test.go)
+//     pass on the translation, and are ported as KATs for this restatement and for the device math
+//     (tests/test_oracle_math_kat.py, tests/test_gpu_math_kat.py);
+//   * Integrate, every narrowphase routine, the resolver, the frame loops: the reference holds no test or vector for
+//     them, so the pins are dumps PRINTED BY THE TRANSLATED REFERENCE (tests/golden/ref/*.txt, made by
+//     oracle/make_ref_golden.py): this restatement reproduces them bit for bit — per frame the contact count, the
+//     (body, body) sequence, the as-generated contact geometry and the raw bits of every body's state — on
+//     cubedrop (600 frames), ballistic-64 (600), piles of 27 / 216 bodies, 256 batched perturbed worlds (600) and
+//     65 536 free bodies (tests/test_oracle_vs_reference_dump.py); the 4 096-body pile (80 frames) is checked from the GPU side.
+// What is not covered: the Go compiler itself (the harnesses are ready for it: tools/compare_go_dump.py) and math.Pow,
+// which is C pow() here and in the translation (<= 1 ulp from Go's; the library takes the Pow factors as host inputs).
+// The restatement keeps the Go source's expression order (left to right, one IEEE rounding per operation, no FMA
+// contraction: build with -ffp-contract=off).  The float32 instantiation has no translated counterpart (the reference
+// does not compile as float32 without edits): it is pinned only through the shared template.
 //
 // Every function cites the reference file:line (paths relative to /root/reference) it
 // restates.  The structures keep the reference's AoS layout and the per-contact heap

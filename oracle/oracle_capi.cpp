@@ -2,7 +2,7 @@
 //
 // TEST INFRASTRUCTURE ONLY (see the header of cubez_oracle.hpp).  Mirrors the product ABI of
 // include/cubezcuda.h with a czo_ prefix so the parity tests can drive both with the same
-// numpy arrays.  PARITY UNPINNED beyond the math layer (no Go toolchain in this image).
+// numpy arrays.  Parity status: pinned against the mechanically translated reference (see cubez_oracle.hpp).
 //
 // Build: g++ -O2 -ffp-contract=off -fPIC -shared [-DCUBEZ_REAL_FLOAT] oracle_capi.cpp
 #include "../include/cubezcuda.h"

@@ -1,10 +1,10 @@
 """Generates the golden fixtures under tests/golden/ from the CPU oracle.
 
-There is no Go toolchain in this image, so the reference itself can not produce vectors; the
-fixtures pin the *oracle* (oracle/cubez_oracle.hpp, a line-by-line restatement of the Go
-source) so that neither it nor the CUDA path can drift silently.  Anyone with Go can
-regenerate the same files from the unmodified reference with go/harness (same dump fields)
-and diff them.   Usage:  python tests/golden/make_golden.py
+These .npz fixtures are ORACLE-DERIVED regression pins (per-world counters, iteration counts, final state; also the
+float32 and materials cases, which the reference cannot produce): they keep the oracle and the CUDA path from drifting
+silently.  Independent evidence of matching the reference is elsewhere: tests/golden/ref/*.txt are dumps printed by the
+reference's own Go sources (translated mechanically, oracle/go2cpp.py) and both the oracle and the CUDA path reproduce
+them bit for bit.   Usage:  python tests/golden/make_golden.py
 """
 import os
 import sys
