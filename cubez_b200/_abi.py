@@ -308,6 +308,7 @@ def declare(lib: C.CDLL, prec: Precision, prefix: str = "cz_"):
         "world_download_colliders": ([VP, C.c_int32, C.c_int32, PC], C.c_int),
         "world_download_contacts": ([VP, C.c_int32, PK], C.c_int),
         "world_last_step_counts": ([VP, P32, P32, P32], C.c_int),
+        "world_count_nonfinite": ([VP, C.POINTER(C.c_int64)], C.c_int),
         "world_island_stats": ([VP, C.POINTER(C.c_int64), C.POINTER(C.c_int64)], C.c_int),
         "world_checksum_energy": ([VP, C.POINTER(C.c_uint64), C.POINTER(C.c_double)], C.c_int),
         "world_step_host": ([VP, PB, R, C.c_int32, C.POINTER(CzStepStats)], C.c_int),
@@ -344,7 +345,7 @@ EXPORTED = (
     "calculate_derived_data collider_derive narrowphase resolve_contacts world_create world_destroy "
     "world_upload_bodies world_upload_colliders world_upload_planes world_upload_schedule world_set_activation "
     "world_set_pow world_add_forces world_set_step_index world_set_episodes world_set_materials world_export_gl world_step world_synchronize world_download_bodies "
-    "world_download_colliders world_download_contacts world_last_step_counts world_island_stats world_checksum_energy "
+    "world_download_colliders world_download_contacts world_last_step_counts world_count_nonfinite world_island_stats world_checksum_energy "
     "world_step_host world_step_rl world_step_rl_async world_rl_wait run_create run_destroy run_shard run_upload_bodies run_upload_colliders run_upload_planes "
     "run_set_episodes run_step run_finish run_last_error bench_fp64_rate bench_integrate math_op broadphase_pairs bench_broadphase sort_pairs_u32 sort_pairs_u64"
 ).split()

@@ -368,6 +368,12 @@ class BatchedWorld:
         self.ctx.check(self.lib.cz_world_last_step_counts(self.h, nc.ctypes.data_as(P32), pi.ctypes.data_as(P32), vi.ctypes.data_as(P32)))
         return nc, pi, vi
 
+    def count_nonfinite(self) -> int:
+        """Bodies with a NaN / infinite component in position, orientation, velocity or rotation (the reference propagates NaN silently)."""
+        n = C.c_int64()
+        self.ctx.check(self.lib.cz_world_count_nonfinite(self.h, C.byref(n)))
+        return int(n.value)
+
     def island_stats(self) -> Tuple[int, int]:
         """(frames resolved as one CTA per contact island, of which re-run on the single-CTA path because the cap cut the loop)"""
         a, b = C.c_int64(), C.c_int64()

@@ -829,6 +829,24 @@ __global__ void k_checksum_energy(BodyStore s, int W, int B, unsigned long long 
     energy[w] = e;
 }
 
+// NaN / overflow watch: the reference propagates NaN silently (0/0 when both bodies of a contact are
+// static, contact.go:286-386; a zero fallback normal in cube-sphere, colliders.go:417-421).  Counts the bodies whose
+// position, orientation, velocity or rotation holds a non-finite component.
+__global__ void k_count_nonfinite(BodyStore s, long long n, unsigned long long *count) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    bool bad = false;
+    if (i < n) {
+        V3 pos = czb::ld_position(s, i), vel = czb::ld_velocity(s, i), rot = czb::ld_rotation(s, i);
+        Q4 q = czb::ld_orientation(s, i);
+        real sum = R_(0);
+        for (int k = 0; k < 3; k++) sum += pos.c[k] * R_(0) + vel.c[k] * R_(0) + rot.c[k] * R_(0);
+        for (int k = 0; k < 4; k++) sum += q.c[k] * R_(0);
+        bad = !(sum == R_(0));      // x * 0 is NaN exactly when x is NaN or infinite
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, bad);
+    if ((threadIdx.x & 31) == 0 && m) atomicAdd(count, (unsigned long long)__popc(m));
+}
+
 // --------------------------------------------------------------------------------------
 // cfg5 initial state on the device: the same splitmix64 stream as scenes.free_bodies().
 // --------------------------------------------------------------------------------------

@@ -1221,6 +1221,21 @@ int cz_world_last_step_counts(cz_world *w, int32_t *n_contacts, int32_t *pos_it,
     if (vel_it) CK(ctx, cudaMemcpy(vel_it, w->velIters, bytes, cudaMemcpyDeviceToHost));
     return CZ_OK;
 }
+int cz_world_count_nonfinite(cz_world *w, int64_t *bodies) {
+    if (!w || !bodies) return CZ_ERR_INVALID;
+    cz_ctx *ctx = w->ctx;
+    CK(ctx, cudaSetDevice(ctx->device));
+    unsigned long long *d = nullptr, h = 0;
+    CK(ctx, cudaMalloc(&d, sizeof(unsigned long long)));
+    CK(ctx, cudaMemsetAsync(d, 0, sizeof(unsigned long long), ctx->stream));
+    k_count_nonfinite<<<nblk(w->b.n, 256), 256, 0, ctx->stream>>>(w->b.st, w->b.n, d);
+    CKL(ctx);
+    CK(ctx, cudaMemcpyAsync(&h, d, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    cudaFree(d);
+    *bodies = (int64_t)h;
+    return CZ_OK;
+}
 int cz_world_island_stats(cz_world *w, int64_t *island_frames, int64_t *fallbacks) {
     if (!w) return CZ_ERR_INVALID;
     if (island_frames) *island_frames = w->islandFrames;

@@ -493,6 +493,14 @@ func (w *World) LastStepCounts() (contacts, posIterations, velIterations []int32
 	return
 }
 
+// CountNonFinite — cz_world_count_nonfinite: bodies with a NaN / infinite component in their state (the reference, and
+// therefore the library, propagate NaN silently: this is how a host notices).
+func (w *World) CountNonFinite() int64 {
+	var n C.int64_t
+	check(C.cz_world_count_nonfinite(w.h, &n))
+	return int64(n)
+}
+
 // IslandStats — cz_world_island_stats: frames resolved as one CTA per contact island, and how many of those were
 // re-run on the single-CTA path because the reference's iteration cap would have cut the loop.
 func (w *World) IslandStats() (islandFrames, fallbacks int64) {

@@ -277,6 +277,10 @@ int cz_world_export_gl(cz_world *w, int32_t first_world, int32_t n_worlds, float
                        int32_t dst_on_device);
 /* per-world counters of the last step (each array n_worlds long, any may be NULL) */
 int cz_world_last_step_counts(cz_world *w, int32_t *n_contacts, int32_t *pos_iterations, int32_t *vel_iterations);
+/* NaN / overflow watch: the number of bodies whose position, orientation, velocity or rotation holds a non-finite
+ * component.  The reference propagates NaN silently (e.g. 0/0 when both bodies of a contact are static); so does the
+ * library, bit for bit — this is how a host notices. */
+int cz_world_count_nonfinite(cz_world *w, int64_t *bodies);
 /* Contact-island statistics of a CZ_WORLD_BROADPHASE world since creation: frames whose ResolveContacts ran as one CTA
  * per island, and how many of those had to be re-run on the single-CTA path because the reference's loop would have
  * been cut by its iteration cap (the only case islands cannot reproduce).  Either pointer may be NULL. */

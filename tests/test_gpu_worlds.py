@@ -368,3 +368,24 @@ def test_device_status_is_sticky_across_async_steps():
     assert e.value.code == _abi.CZ_ERR_CAPACITY
     w.synchronize()                                    # observed once: cleared
     w.close()
+
+
+def test_nonfinite_body_count():
+    """cz_world_count_nonfinite: the NaN / overflow watch of SURVEY section 5.  Two static cubes in contact make 0/0 = NaN
+    moves in applyPositionChange (contact.go:329-330) — silently, in the reference and here; the counter is how a host notices."""
+    scene = scenes.cubedrop()
+    w = make_world(scene, "multi")
+    w.step(scene.dt, 30)
+    assert w.count_nonfinite() == 0
+    b = w.download()
+    b.inverse_mass[:2] = 0.0                                  # two infinite-mass cubes ...
+    b.inverse_inertia_tensor[:2] = 0.0
+    b.position[0] = (0.0, 5.0, 0.0); b.position[1] = (0.3, 5.2, 0.0)    # ... overlapping
+    b.velocity[7] = (np.inf, 0.0, 0.0)                        # and an overflowed velocity
+    w.upload_bodies(b, derive=True)
+    w.upload_colliders(scene.colliders, derive=True)
+    w.step(scene.dt, 2)
+    g = w.download()
+    expected = int((~np.isfinite(np.concatenate([g.position, g.orientation, g.velocity, g.rotation], axis=1))).any(axis=1).sum())
+    assert expected >= 3 and w.count_nonfinite() == expected
+    w.close()
