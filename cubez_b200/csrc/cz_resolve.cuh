@@ -999,12 +999,19 @@ __device__ __forceinline__ real big_propagate_velocity(const Touched &t, const C
     return -cv.c[0] - rest * (cv.c[0] - vfa);
 }
 
+// Owner of a contact.  A resolve touches the contacts of one or two bodies, and those were generated together
+// (consecutive indices: the 4 or 8 plane contacts of a cube, the two checks of a pair), so owners are dealt round-robin
+// over the WARPS: consecutive contacts belong to owners in different warps and their re-scans run side by side instead of
+// one after the other in a single warp (ncu before: a quarter of an iteration was the other warps waiting for that warp).
+template <int NT> __device__ __forceinline__ int big_owner(int c) { return (c % (NT / 32)) * 32 + (c / (NT / 32)) % 32; }
+template <int NT> __device__ __forceinline__ int big_owner_first(int o) { return (o >> 5) + (o & 31) * (NT / 32); }   // its contacts: first, first + NT, ...
+
 // warp-cooperative re-scan of owner `o`: lanes stride the owner's contacts, arg-max with ties to the lowest index
 template <int NT>
 __device__ __forceinline__ void big_rescan_owner(const BigShared &sh, int nC, int o, int lane) {
     real v = R_(0.01);    // positionEpsilon / velocityEpsilon (contact.go:12-13)
     int i = 0x7fffffff;
-    for (int c = o + lane * NT; c < nC; c += 32 * NT) {
+    for (int c = big_owner_first<NT>(o) + lane * NT; c < nC; c += 32 * NT) {
         const real hv = sh.hot[c];
         if (hv > v) { v = hv; i = c; }
     }
@@ -1040,7 +1047,7 @@ __device__ __forceinline__ int resolve_loop_big(const Ctx &x0, int maxIterations
     {   // every thread is an owner: initial cache
         real v = R_(0.01);
         int i = 0x7fffffff;
-        for (int c = tid; c < x.nC; c += NT) {
+        for (int c = big_owner_first<NT>(tid); c < x.nC; c += NT) {
             const real hv = sh.hot[c];
             if (hv > v) { v = hv; i = c; }
         }
@@ -1099,7 +1106,7 @@ __device__ __forceinline__ int resolve_loop_big(const Ctx &x0, int maxIterations
         // ---- propagation: arithmetic on the prefetched records ------------------------------------------------------
         auto publish = [&](int c, real v) {
             sh.hot[c] = v;
-            const int o = c & (NT - 1);
+            const int o = big_owner<NT>(c);
             const real cv0 = sh.cacheV[o];
             const int ci = sh.cacheI[o];
             if (c == ci || v > cv0 || (v == cv0 && c < ci)) sh.dirty[o] = 1;
