@@ -17,6 +17,7 @@
 #include <string>
 #include <vector>
 #include <map>
+#include <atomic>
 #include <mutex>
 #include <unordered_map>
 #include <cuda_runtime.h>
@@ -139,6 +140,52 @@ template <class T> static inline cudaError_t pool_host_alloc_t(T **p, size_t byt
 #include "cz_kernels.cuh"
 #include "cz_fused.cuh"
 #include "cz_broadphase.cuh"
+
+// The host pipelines move a chunk as one copy per field (the caller's arrays are separate allocations).  Submitted one
+// by one, every copy costs ~5 us of copy-engine time on top of its bytes: 6 chunks x 9 fields x 2 directions = 108
+// copies = 0.4-1.0 ms of a 4.6 ms frame (tools/probes/memcpy_batch_probe.cu: 71.7 -> 80.6 GB/s in both directions at
+// once).  cudaMemcpyBatchAsync (CUDA 12.8) submits a chunk's fields as ONE operation; it needs page-locked or
+// CUDA-allocated operands, so a batch with a pageable pointer in it, a driver without the entry point, or
+// CUBEZ_COPY_BATCH=0 goes out as plain cudaMemcpyAsync calls — same bytes, same stream order.
+struct CopyBatch {
+    static constexpr int MAXN = 16;
+    void *dst[MAXN], *src[MAXN];
+    size_t size[MAXN];
+    int n = 0;
+    template <class T> void add(T *d, const T *s, long long first, long long count, int comps) {
+        if (!d || !s || count <= 0 || n >= MAXN) return;
+        dst[n] = (void *)(d + first * comps); src[n] = (void *)(s + first * comps); size[n] = sizeof(T) * (size_t)count * comps;
+        n++;
+    }
+};
+static std::atomic<int> g_copyBatchState{-1};   // -1 not probed, 0 off, 1 on
+static bool host_ptr_pinned(const void *p) {
+    cudaPointerAttributes a{};
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged || a.type == cudaMemoryTypeDevice;
+}
+static cudaError_t copy_batch_submit(CopyBatch &b, cudaMemcpyKind kind, cudaStream_t stream, bool pinned) {
+    if (b.n == 0) return cudaSuccess;
+    int st = g_copyBatchState.load();
+    if (st < 0) { st = czf::env_int("CUBEZ_COPY_BATCH", 1) ? 1 : 0; g_copyBatchState.store(st); }
+    if (st == 1 && pinned && b.n > 1) {
+        cudaMemcpyAttributes at{};
+        at.srcAccessOrder = cudaMemcpySrcAccessOrderStream;
+        size_t idx0 = 0, failIdx = 0;
+        const cudaError_t e = cudaMemcpyBatchAsync(b.dst, b.src, b.size, (size_t)b.n, &at, &idx0, 1, &failIdx, stream);
+        if (e == cudaSuccess) { b.n = 0; return e; }
+        if (e != cudaErrorNotSupported && e != cudaErrorCallRequiresNewerDriver && e != cudaErrorInvalidValue && e != cudaErrorSymbolNotFound) return e;
+        cudaGetLastError();
+        g_copyBatchState.store(0);   // this driver cannot: plain copies from now on
+    }
+    for (int i = 0; i < b.n; i++) {
+        const cudaError_t e = cudaMemcpyAsync(b.dst[i], b.src[i], b.size[i], kind, stream);
+        if (e != cudaSuccess) return e;
+    }
+    b.n = 0;
+    return cudaSuccess;
+}
+
 
 using namespace czk;
 
@@ -1277,10 +1324,26 @@ int cz_world_checksum_energy(cz_world *w, uint64_t *checksum, double *energy) {
 // (cz_host_alloc); pageable memory works but the copies then serialise in the driver.
 // chunk boundaries of the host pipelines: short first and last chunks (pipeline fill = first upload,
 // drain = last download)
-static std::vector<int> host_chunk_edges(int chunks, int W) {
-    std::vector<int> wEdge(chunks + 1, 0);
-    std::vector<double> wt(chunks, 1.0);
+static std::vector<double> host_chunk_weights(int chunks, bool fromEnv = true) {
+    std::vector<double> wt;
+    if (const char *e = fromEnv ? getenv("CUBEZ_HOST_CHUNK_WEIGHTS") : nullptr) {   // probe hook: "0.1,0.2,0.5,1,1,1,0.5"
+        for (const char *q = e; *q;) {
+            char *end = nullptr;
+            const double v = strtod(q, &end);
+            if (end == q) break;
+            if (v > 0) wt.push_back(v);
+            q = *end == ',' ? end + 1 : end;
+        }
+        if (!wt.empty()) return wt;
+    }
+    wt.assign(chunks, 1.0);
     if (chunks >= 4 && !czf::env_int("CUBEZ_HOST_EVEN_CHUNKS", 0)) { wt[0] = wt[chunks - 1] = 0.5; wt[1] = wt[chunks - 2] = 0.85; }
+    return wt;
+}
+static std::vector<int> host_chunk_edges(int chunks, int W) {
+    std::vector<double> wt = host_chunk_weights(chunks);
+    if ((int)wt.size() != chunks) wt = host_chunk_weights(chunks, false);   // a caller with its own chunk count (the RL step)
+    std::vector<int> wEdge(chunks + 1, 0);
     double tot = 0, run = 0;
     for (double v : wt) tot += v;
     for (int c = 0; c < chunks; c++) { run += wt[c]; wEdge[c + 1] = (int)((double)W * run / tot + 0.5); }
@@ -1293,7 +1356,7 @@ static int host_pipe_init(cz_world *w) {
     auto &pp = w->pipe;
     if (pp.ready) return CZ_OK;
     const long long NB = w->b.n;
-    int chunks = czf::env_int("CUBEZ_HOST_CHUNKS", 6);
+    int chunks = (int)host_chunk_weights(czf::env_int("CUBEZ_HOST_CHUNKS", 6)).size();
     if (!w->useFused) chunks = 1;
     if (chunks > w->d.n_worlds) chunks = w->d.n_worlds;
     if (chunks < 1) chunks = 1;
@@ -1372,16 +1435,19 @@ int cz_world_step_host(cz_world *w, cz_bodies *io, cz_real dt, int32_t n_steps, 
     long long launches = 0;
     std::vector<cudaEvent_t> trEv;   // trace only: [chunk][up end, compute begin, compute end, down end]
     if (hostTrace) { trEv.resize((size_t)pp.chunks * 4); for (auto &e : trEv) cudaEventCreate(&e); }
-#define UP(dst, src, comps) CK(ctx, cudaMemcpyAsync((dst) + b0 * (comps), (src) + b0 * (comps), sizeof(*(src)) * nb * (comps), cudaMemcpyHostToDevice, pp.sUp))
-#define DOWN(dst, src, comps) CK(ctx, cudaMemcpyAsync((dst) + b0 * (comps), (src) + b0 * (comps), sizeof(*(src)) * nb * (comps), cudaMemcpyDeviceToHost, pp.sDown))
+    // every array of the call page-locked (cz_host_alloc / cudaHostRegister)?  Asked once per call, on the first arrays
+    // of each kind; a caller mixing pinned and pageable arrays gets what plain cudaMemcpyAsync gives for pageable memory.
+    const bool pinned = host_ptr_pinned(io->position) && host_ptr_pinned(io->transform) && host_ptr_pinned(io->is_awake);
     const std::vector<int> wEdge = host_chunk_edges(pp.chunks, W);
     for (int c = 0; c < pp.chunks; c++) {
         const int w0 = wEdge[c], w1 = wEdge[c + 1];
         const long long b0 = w0 * B, nb = (w1 - w0) * B;
         if (nb <= 0) continue;
-        UP(dPos, io->position, 3); UP(dOri, io->orientation, 4); UP(dVel, io->velocity, 3); UP(dRot, io->rotation, 3);
-        UP(dAcc, io->acceleration, 3); UP(dIitb, io->inverse_inertia_tensor, 9); UP(dMot, io->motion, 1);
-        UP(fAwake, io->is_awake, 1); UP(fSleep, io->can_sleep, 1);
+        CopyBatch up;
+        up.add(dPos, io->position, b0, nb, 3); up.add(dOri, io->orientation, b0, nb, 4); up.add(dVel, io->velocity, b0, nb, 3); up.add(dRot, io->rotation, b0, nb, 3);
+        up.add(dAcc, io->acceleration, b0, nb, 3); up.add(dIitb, io->inverse_inertia_tensor, b0, nb, 9); up.add(dMot, io->motion, b0, nb, 1);
+        up.add(fAwake, io->is_awake, b0, nb, 1); up.add(fSleep, io->can_sleep, b0, nb, 1);
+        CK(ctx, copy_batch_submit(up, cudaMemcpyHostToDevice, pp.sUp, pinned));
         CK(ctx, cudaEventRecord(pp.evUp[c], pp.sUp));
         if (hostTrace) cudaEventRecord(trEv[c * 4 + 0], pp.sUp);
         // this chunk's damping slice, compared while its upload is in flight
@@ -1405,7 +1471,8 @@ int cz_world_step_host(cz_world *w, cz_bodies *io, cz_real dt, int32_t n_steps, 
             p.wFirst = w0; p.wCount = w1 - w0;
             czf::FusedPlan fpl = w->fused;
             if (c % pp.nComp) fpl.cold = pp.coldX[c % pp.nComp];
-            if (w->fused.split && !czf::env_int("CUBEZ_HOST_NO_SPLIT", 0)) {   // one launch per phase and frame, as cz_world_step does for large batches
+            static const int splitMin = czf::env_int("CUBEZ_HOST_SPLIT_MIN", 0);   // chunks below this many worlds: one persistent launch
+            if (w->fused.split && !czf::env_int("CUBEZ_HOST_NO_SPLIT", 0) && w1 - w0 >= splitMin) {   // one launch per phase and frame, as cz_world_step does for large batches
                 for (int s2 = 0; s2 < n_steps && !rc; s2++) {
                     p.step_index = w->step_index + s2;
                     const bool zeroed = order_worlds(w, p, cs, launches, pp.dNext + 4 * c);
@@ -1437,13 +1504,13 @@ int cz_world_step_host(cz_world *w, cz_bodies *io, cz_real dt, int32_t n_steps, 
         CK(ctx, cudaEventRecord(pp.evComp[c], cs));
         if (hostTrace) cudaEventRecord(trEv[c * 4 + 2], cs);
         CK(ctx, cudaStreamWaitEvent(pp.sDown, pp.evComp[c], 0));
-        DOWN(io->position, oPos, 3); DOWN(io->orientation, oOri, 4); DOWN(io->velocity, oVel, 3); DOWN(io->rotation, oRot, 3);
-        DOWN(io->motion, oMot, 1); DOWN(io->last_frame_acceleration, oLacc, 3); DOWN(io->transform, oTr, 12);
-        DOWN(io->inverse_inertia_tensor_world, oIitw, 9); DOWN(io->is_awake, fAwakeOut, 1);
+        CopyBatch down;
+        down.add(io->position, oPos, b0, nb, 3); down.add(io->orientation, oOri, b0, nb, 4); down.add(io->velocity, oVel, b0, nb, 3); down.add(io->rotation, oRot, b0, nb, 3);
+        down.add(io->motion, oMot, b0, nb, 1); down.add(io->last_frame_acceleration, oLacc, b0, nb, 3); down.add(io->transform, oTr, b0, nb, 12);
+        down.add(io->inverse_inertia_tensor_world, oIitw, b0, nb, 9); down.add(io->is_awake, fAwakeOut, b0, nb, 1);
+        CK(ctx, copy_batch_submit(down, cudaMemcpyDeviceToHost, pp.sDown, pinned));
         if (hostTrace) cudaEventRecord(trEv[c * 4 + 3], pp.sDown);
     }
-#undef UP
-#undef DOWN
     w->step_index += n_steps;
     CK(ctx, cudaEventRecord(pp.evDownDone, pp.sDown));
     CK(ctx, cudaStreamWaitEvent(ctx->stream, pp.evDownDone, 0));
@@ -1517,16 +1584,20 @@ static int rl_enqueue(cz_world *w, const cz_real *add_velocity, const cz_real *a
     // observations are a third of the full state: fewer, larger chunks keep the fused kernels efficient
     const int chunks = std::max(1, std::min(pp.chunks, czf::env_int("CUBEZ_RL_CHUNKS", 4)));
     const std::vector<int> wEdge = host_chunk_edges(chunks, W);
-#define UP(dst, src, comps) CK(ctx, cudaMemcpyAsync((dst) + b0 * (comps), (src) + b0 * (comps), sizeof(*(src)) * nb * (comps), cudaMemcpyHostToDevice, pp.sUp))
-#define DOWN(dst, src, comps) if (dst) CK(ctx, cudaMemcpyAsync((dst) + b0 * (comps), (src) + b0 * (comps), sizeof(*(src)) * nb * (comps), cudaMemcpyDeviceToHost, pp.sDown))
+    // page-locked arrays go out as one batched copy per chunk and direction (see CopyBatch)
+    const void *firstOut = obs ? (obs->position ? (const void *)obs->position : obs->orientation ? (const void *)obs->orientation : obs->velocity ? (const void *)obs->velocity : (const void *)obs->rotation) : nullptr;
+    const void *first32 = obs32 ? (obs32->position ? (const void *)obs32->position : obs32->orientation ? (const void *)obs32->orientation : obs32->velocity ? (const void *)obs32->velocity : (const void *)obs32->rotation) : nullptr;
+    const bool pinnedIn = (!add_velocity || host_ptr_pinned(add_velocity)) && (!add_rotation || host_ptr_pinned(add_rotation));
+    const bool pinnedOut = (!firstOut || host_ptr_pinned(firstOut)) && (!first32 || host_ptr_pinned(first32)) && (!obs || !obs->is_awake || host_ptr_pinned(obs->is_awake));
     for (int c = 0; c < chunks; c++) {
         const int w0 = wEdge[c], w1 = wEdge[c + 1];
         const long long b0 = w0 * B, nb = (w1 - w0) * B;
         if (nb <= 0) continue;
         cudaStream_t cs = pp.sComp[c % pp.nComp];
         if (anyIn) {
-            if (add_velocity) UP(dVel, add_velocity, 3);
-            if (add_rotation) UP(dRot, add_rotation, 3);
+            CopyBatch up;
+            up.add(dVel, add_velocity, b0, nb, 3); up.add(dRot, add_rotation, b0, nb, 3);
+            CK(ctx, copy_batch_submit(up, cudaMemcpyHostToDevice, pp.sUp, pinnedIn));
             CK(ctx, cudaEventRecord(pp.evUp[c], pp.sUp));
             CK(ctx, cudaStreamWaitEvent(cs, pp.evUp[c], 0));
             k_apply_actions<<<nblk(nb, 256), 256, 0, cs>>>(w->b.st, b0, nb, add_velocity ? dVel : nullptr, add_rotation ? dRot : nullptr);
@@ -1568,17 +1639,17 @@ static int rl_enqueue(cz_world *w, const cz_real *add_velocity, const cz_real *a
         }
         CK(ctx, cudaEventRecord(pp.evComp[c], cs));
         CK(ctx, cudaStreamWaitEvent(pp.sDown, pp.evComp[c], 0));
+        CopyBatch down;   // add() skips the arrays the caller did not ask for (NULL)
         if (anyOut) {
-            DOWN(obs->position, oPos, 3); DOWN(obs->orientation, oOri, 4); DOWN(obs->velocity, oVel, 3); DOWN(obs->rotation, oRot, 3);
-            DOWN(obs->motion, oMot, 1); DOWN(obs->last_frame_acceleration, oLacc, 3); DOWN(obs->transform, oTr, 12);
-            DOWN(obs->inverse_inertia_tensor_world, oIitw, 9); DOWN(obs->is_awake, fAwakeOut, 1);
+            down.add(obs->position, oPos, b0, nb, 3); down.add(obs->orientation, oOri, b0, nb, 4); down.add(obs->velocity, oVel, b0, nb, 3); down.add(obs->rotation, oRot, b0, nb, 3);
+            down.add(obs->motion, oMot, b0, nb, 1); down.add(obs->last_frame_acceleration, oLacc, b0, nb, 3); down.add(obs->transform, oTr, b0, nb, 12);
+            down.add(obs->inverse_inertia_tensor_world, oIitw, b0, nb, 9); down.add(obs->is_awake, fAwakeOut, b0, nb, 1);
         }
         if (any32) {
-            DOWN(obs32->position, fPos, 3); DOWN(obs32->orientation, fOri, 4); DOWN(obs32->velocity, fVel, 3); DOWN(obs32->rotation, fRot, 3);
+            down.add(obs32->position, fPos, b0, nb, 3); down.add(obs32->orientation, fOri, b0, nb, 4); down.add(obs32->velocity, fVel, b0, nb, 3); down.add(obs32->rotation, fRot, b0, nb, 3);
         }
+        CK(ctx, copy_batch_submit(down, cudaMemcpyDeviceToHost, pp.sDown, pinnedOut));
     }
-#undef UP
-#undef DOWN
     w->step_index += n_steps;
     CK(ctx, cudaEventRecord(pp.evSlot[slot], pp.sDown));     // everything of this call — frames and downloads — is behind this event
     if (contextStreamWaits) CK(ctx, cudaStreamWaitEvent(ctx->stream, pp.evSlot[slot], 0));
