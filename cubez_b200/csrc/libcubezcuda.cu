@@ -457,6 +457,16 @@ struct cz_world {
         int inFlight = 0, nextTicket = 0;
         long long launchesInFlight = 0, stepsInFlight = 0;
     } pipe;
+    // Resident split-mode steps run the batch as a few independent slices on their own streams (see cz_world_step):
+    // the tail of one slice's phase launch is filled by the other slices' launches.
+    struct StepLanes {
+        bool ready = false;
+        int n = 1;
+        cudaStream_t s[4] = {};
+        real *cold[4] = {};                  // group scratch of the launches of lane k (lane 0 uses the plan's)
+        unsigned int *dNext = nullptr;       // [4 * n] world counters
+        cudaEvent_t evBegin = nullptr, evDone[4] = {};
+    } lanes;
     real *h_pin = nullptr;
     size_t h_pin_bytes = 0;
     // per-pair surface materials (cz_world_set_materials); nMat == 0: the reference's constants
@@ -527,10 +537,49 @@ static void host_pipe_destroy(cz_world *w) {
     pp = cz_world::HostPipe();
 }
 
+static void step_lanes_destroy(cz_world *w) {
+    auto &ln = w->lanes;
+    if (!ln.ready) return;
+    cudaStreamSynchronize(w->ctx->stream);
+    for (int k = 0; k < ln.n; k++) {
+        if (ln.s[k]) { cudaStreamSynchronize(ln.s[k]); cudaStreamDestroy(ln.s[k]); }
+        if (k > 0 && ln.cold[k]) cudaFree(ln.cold[k]);
+        if (ln.evDone[k]) cudaEventDestroy(ln.evDone[k]);
+    }
+    if (ln.evBegin) cudaEventDestroy(ln.evBegin);
+    if (ln.dNext) cudaFree(ln.dNext);
+    ln = cz_world::StepLanes();
+}
+// Lanes of the resident split-mode step.  Measured (tools/lanes_probe.py, us per frame at 1 / 2 / 3 / 4 lanes):
+// 65 536 worlds 1920 / 1720 / 1766 / 1795, 49 152: 1532 / 1362 / 1392 / 1374, 32 768: 1153 / 1049 / 1008 / 1002,
+// 24 576: 964 / 879 / 851 / 820, 16 384: 809 / 749 / 698 / 675, 12 288: 713 / 647 / 619 / 593 -> two slices for
+// large batches, four below 40 960 worlds (CUBEZ_STEP_LANES overrides).
+static int step_lanes_init(cz_world *w) {
+    cz_ctx *ctx = w->ctx;
+    auto &ln = w->lanes;
+    if (ln.ready) return CZ_OK;
+    int n = czf::env_int("CUBEZ_STEP_LANES", w->d.n_worlds >= 40960 ? 2 : 4);
+    n = std::max(1, std::min(4, std::min(n, w->d.n_worlds / std::max(1, czf::env_int("CUBEZ_STEP_LANE_MIN", 2048)))));
+    ln.n = n;
+    if (n > 1) {
+        CK(ctx, cudaMalloc(&ln.dNext, sizeof(unsigned int) * 4 * n));
+        CK(ctx, cudaEventCreateWithFlags(&ln.evBegin, cudaEventDisableTiming));
+        for (int k = 0; k < n; k++) {
+            CK(ctx, cudaStreamCreateWithFlags(&ln.s[k], cudaStreamNonBlocking));
+            CK(ctx, cudaEventCreateWithFlags(&ln.evDone[k], cudaEventDisableTiming));
+            if (k == 0) ln.cold[0] = w->fused.cold;
+            else CK(ctx, cudaMalloc(&ln.cold[k], sizeof(real) * w->fused.coldReals * (size_t)w->fused.maxGrid * w->fused.groupsPerBlock));
+        }
+    }
+    ln.ready = true;
+    return CZ_OK;
+}
+
 // (Re)derive everything that depends on the schedule size / capacities.
 static int world_plan(cz_world *w) {
     cz_ctx *ctx = w->ctx;
     host_pipe_destroy(w);
+    step_lanes_destroy(w);
     const int B = w->d.bodies_per_world, Cc = w->d.contacts_per_world, W = w->d.n_worlds;
     if (w->d.schedule == CZ_SCHED_ALL_PAIRS_ORDERED) w->nchk = B * (w->P + B);
     // narrowphase tiling
@@ -706,6 +755,7 @@ int cz_world_destroy(cz_world *w) {
     if (!w) return CZ_ERR_INVALID;
     cudaSetDevice(w->ctx->device);
     cudaStreamSynchronize(w->ctx->stream);
+    step_lanes_destroy(w);
     batch_free(w->b);
     if (w->bp.bounds) czbp::bp_free(w->bp);
     if (w->snap.st.base) batch_free(w->snap);
@@ -1134,7 +1184,39 @@ int cz_world_step(cz_world *w, cz_real dt, int32_t n_steps, cz_step_stats *stats
     }
     if (w->useFused) {
         WorldParams p = world_params(w);
-        if (w->fused.split) {   // one launch per phase and frame: every warp of the GPU runs the same code region
+        if (w->fused.split && (rc = step_lanes_init(w))) return rc;
+        if (w->fused.split && w->lanes.n > 1) {
+            // Worlds share nothing, so the batch runs as a few slices, each with its own stream, world counters and group
+            // scratch and its own order -> A -> B -> C chain per frame.  A phase launch ends with a tail (the last CTAs
+            // finish their worlds while the other SMs idle; the next phase cannot start before it); with two chains the
+            // other slices' launches fill it.  65 536 worlds: 1.92 -> 1.72 ms per frame (tools/lanes_probe.py).
+            auto &ln = w->lanes;
+            const int W = w->d.n_worlds;
+            CK(ctx, cudaMemsetAsync(ln.dNext, 0, sizeof(unsigned int) * 4 * ln.n, ctx->stream));
+            CK(ctx, cudaEventRecord(ln.evBegin, ctx->stream));
+            for (int k = 0; k < ln.n; k++) CK(ctx, cudaStreamWaitEvent(ln.s[k], ln.evBegin, 0));
+            for (int s = 0; s < n_steps && !rc; s++) {
+                for (int k = 0; k < ln.n && !rc; k++) {
+                    WorldParams pk = p;
+                    pk.step_index = w->step_index + s;
+                    pk.wFirst = (int)((long long)W * k / ln.n);
+                    pk.wCount = (int)((long long)W * (k + 1) / ln.n) - pk.wFirst;
+                    czf::FusedPlan fpl = w->fused;
+                    fpl.cold = ln.cold[k];
+                    const bool zeroed = order_worlds(w, pk, ln.s[k], launches, ln.dNext + 4 * k);
+                    for (int ph : {czf::PH_A, czf::PH_B, czf::PH_C}) {
+                        pk.order = phase_order(w, ph);
+                        rc = czf::launch(fpl, pk, dt, w->bias, 1, ln.dNext + 4 * k, ln.s[k], ph, zeroed);
+                        if (rc) break;
+                        launches++;
+                    }
+                }
+            }
+            for (int k = 0; k < ln.n; k++) {
+                CK(ctx, cudaEventRecord(ln.evDone[k], ln.s[k]));
+                CK(ctx, cudaStreamWaitEvent(ctx->stream, ln.evDone[k], 0));
+            }
+        } else if (w->fused.split) {   // one launch per phase and frame: every warp of the GPU runs the same code region
             for (int s = 0; s < n_steps && !rc; s++) {
                 p.step_index = w->step_index + s;
                 const bool zeroed = order_worlds(w, p, ctx->stream, launches, w->d_next);
@@ -1554,7 +1636,7 @@ __global__ void k_unpack_obs32(czb::BodyStore s, long long first, long long n, f
 // D2H, chunked over the world range.  Nothing here waits for the device.  Slot s reuses the staging buffers of the call
 // two tickets earlier, ordered behind that call's last download by evSlot[s].
 static int rl_enqueue(cz_world *w, const cz_real *add_velocity, const cz_real *add_rotation, cz_bodies *obs, cz_obs32 *obs32, cz_real dt,
-                      int32_t n_steps, int slot, long long &launches, bool afterContextStream, bool contextStreamWaits) {
+                      int32_t n_steps, int slot, long long &launches, bool afterContextStream, bool contextStreamWaits, int chunkLimit = 0) {
     cz_ctx *ctx = w->ctx;
     auto &pp = w->pipe;
     int rc = CZ_OK;
@@ -1582,7 +1664,10 @@ static int rl_enqueue(cz_world *w, const cz_real *add_velocity, const cz_real *a
     CK(ctx, cudaStreamWaitEvent(pp.sUp, pp.evSlot[slot], 0));          // the staging of this slot is free again
     for (int k = 0; k < pp.nComp; k++) CK(ctx, cudaStreamWaitEvent(pp.sComp[k], pp.evSlot[slot], 0));
     // observations are a third of the full state: fewer, larger chunks keep the fused kernels efficient
-    const int chunks = std::max(1, std::min(pp.chunks, czf::env_int("CUBEZ_RL_CHUNKS", 4)));
+    // (a step enqueued behind another one does not need chunks to hide its transfers — they overlap the neighbour's
+    // frames — so it runs as the resident step does, in two slices whose launches fill each other's tails: chunkLimit;
+    // 2.28 -> 1.84 ms per step at 65 536 worlds, tools/rl_async_probe.py)
+    const int chunks = std::max(1, std::min(pp.chunks, chunkLimit > 0 ? chunkLimit : czf::env_int("CUBEZ_RL_CHUNKS", 4)));
     const std::vector<int> wEdge = host_chunk_edges(chunks, W);
     // page-locked arrays go out as one batched copy per chunk and direction (see CopyBatch)
     const void *firstOut = obs ? (obs->position ? (const void *)obs->position : obs->orientation ? (const void *)obs->orientation : obs->velocity ? (const void *)obs->velocity : (const void *)obs->rotation) : nullptr;
@@ -1728,7 +1813,8 @@ int cz_world_step_rl_async(cz_world *w, const cz_real *add_velocity, const cz_re
     }
     const int t = pp.nextTicket++;
     long long launches = 0;
-    if ((rc = rl_enqueue(w, add_velocity, add_rotation, obs, obs32, dt, n_steps, t & 1, launches, pp.inFlight == 0, false))) return rc;
+    const int behind = pp.inFlight > 0 ? std::max(1, czf::env_int("CUBEZ_RL_ASYNC_CHUNKS", 2)) : 0;
+    if ((rc = rl_enqueue(w, add_velocity, add_rotation, obs, obs32, dt, n_steps, t & 1, launches, pp.inFlight == 0, false, behind))) return rc;
     pp.launchesInFlight += launches;
     pp.stepsInFlight += n_steps;
     pp.inFlight++;

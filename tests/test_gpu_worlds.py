@@ -234,6 +234,32 @@ def test_split_phase_launches_equal_persistent_kernel():
     assert sums[1][0] == cpu.checksum_energy()[0] and sums[1][1:4] == (cs["contacts"], cs["pos_iterations"], cs["vel_iterations"])
 
 
+@pytest.mark.parametrize("lanes", ["2", "3", "4"])
+def test_split_step_in_lanes_matches_the_oracle(lanes, monkeypatch):
+    """The resident split-mode step runs the batch as independent slices on their own streams (world counters, group
+    scratch and ordering per slice).  Uneven slices, episode resets, several calls: state, counters and the last
+    frame's contacts must be the oracle's, exactly as with one lane."""
+    scene = scenes.batched_cubedrop(n_worlds=250)
+    phase0 = (np.arange(250) * 7) % 150
+    monkeypatch.setenv("CUBEZ_FUSED_SPLIT", "1")
+    monkeypatch.setenv("CUBEZ_STEP_LANES", lanes)
+    monkeypatch.setenv("CUBEZ_STEP_LANE_MIN", "16")
+    gpu = make_world(scene, "fused8")
+    cpu = OracleWorld.from_scene(scene)
+    gpu.set_episodes(150, phase0)
+    cpu.set_episodes(150, phase0)
+    for n in (1, 60, 3, 140):
+        gs, cs = gpu.step(scene.dt, n), cpu.step(scene.dt, n, n_threads=8)
+        for k in ("contacts", "pos_iterations", "vel_iterations"):
+            assert gs[k] == cs[k], (n, k, gs[k], cs[k])
+    g, c = gpu.download(), cpu.download()
+    for f in STATE_FIELDS:
+        assert np.array_equal(getattr(g, f), getattr(c, f)), f
+    for wi in (0, 83, 84, 249):   # around the slice edges
+        assert gpu.contact_pairs(wi) == cpu.contact_pairs(wi)
+    gpu.close()
+
+
 def test_cost_ordered_scheduling_is_result_neutral(monkeypatch):
     """czf::k_order_worlds only permutes the order in which worlds are fetched: state, counters and
     checksum are identical with and without it, resident and chunked."""

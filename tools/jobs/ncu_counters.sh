@@ -2,8 +2,9 @@
 # ncu captures behind profiles/ncu_counters.json (DRAM bytes and FP64 instruction counts of the code as built)
 mkdir -p gpurun_out
 M=dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum,smsp__sass_thread_inst_executed_op_dadd_pred_on.sum,smsp__sass_thread_inst_executed_op_dmul_pred_on.sum,smsp__sass_thread_inst_executed_op_dfma_pred_on.sum
-# one frame (A | B | C) of the stationary 65 536-world population: the profile script runs 600 + 1 + 1 frames, 3 launches each
-PROF_WORLDS=65536 PROF_FRAMES=1 timeout 900 ncu --metrics $M --clock-control none --print-units base --csv --page raw -k regex:k_world_fused --launch-skip 1803 --launch-count 3 --log-file gpurun_out/ncu_fused.csv python tools/profile_fused.py > gpurun_out/ncu_fused.log 2>&1
+# one frame (A | B | C) of the stationary 65 536-world population as ONE lane (CUBEZ_STEP_LANES=1: same instructions and bytes as the
+# two-lane step, three launches per frame to pick): the profile script runs 600 + 1 + 1 frames, 3 launches each
+CUBEZ_STEP_LANES=1 PROF_WORLDS=65536 PROF_FRAMES=1 timeout 900 ncu --metrics $M --clock-control none --print-units base --csv --page raw -k regex:k_world_fused --launch-skip 1803 --launch-count 3 --log-file gpurun_out/ncu_fused.csv python tools/profile_fused.py > gpurun_out/ncu_fused.log 2>&1
 timeout 600 ncu --metrics $M --clock-control none --print-units base --csv --page raw -k regex:k_integrate --launch-skip 3 --launch-count 1 --log-file gpurun_out/ncu_k1.csv python -c "
 import sys; sys.path.insert(0,'.')
 from cubez_b200.api import Context

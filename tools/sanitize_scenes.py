@@ -22,6 +22,8 @@ CASES = {
     "fused16": lambda: run("fused persistent G=16", scenes.batched_cubedrop(n_worlds=6), 110, _abi.WORLD_FUSED, {"CUBEZ_FUSED_G": "16"}),
     "fused32": lambda: run("fused persistent G=32", scenes.ballistic(n_bullets=6), 100, _abi.WORLD_FUSED, {"CUBEZ_FUSED_G": "32"}),
     "split": lambda: run("fused split phases", scenes.batched_cubedrop(n_worlds=40), 105, _abi.WORLD_FUSED, {"CUBEZ_FUSED_SPLIT": "1", "CUBEZ_FUSED_G": "8"}, contacts_per_world=64),
+    "lanes": lambda: run("fused split phases in 3 lanes", scenes.batched_cubedrop(n_worlds=48), 105, _abi.WORLD_FUSED,
+                         {"CUBEZ_FUSED_SPLIT": "1", "CUBEZ_FUSED_G": "8", "CUBEZ_STEP_LANES": "3", "CUBEZ_STEP_LANE_MIN": "8"}, contacts_per_world=64),
     "resolve32": lambda: run("k_resolve<32> + k_narrow", scenes.cubedrop(), 110, _abi.WORLD_NO_FUSED),
     "resolve256": lambda: run("k_resolve<256> adjacency loop + broadphase", scenes.pile(side=4), 60, _abi.WORLD_BROADPHASE, {"CUBEZ_RESOLVE_ISLANDS": "0"}),
     "islands": lambda: run("k_resolve_islands", scenes.archipelago(piles=3, side=2), 70, _abi.WORLD_BROADPHASE, {"CUBEZ_RESOLVE_ISLANDS": "2"}),
