@@ -168,8 +168,8 @@ static inline bool plan(FusedPlan &fp, int B, int P, int Cc, int nchk, int sched
     // crossover on B200 with the split step running as independent slices on their own streams (cz_world_step, "lanes";
     // tools/lanes_probe.py, staggered episodes, us per frame persistent vs split): 8 192 worlds 511 vs 573, 12 288 worlds
     // 737 vs 593, 16 384 worlds 887 vs 675; episodes in step from t = 0 (tools/strong_probe.py): 8 192 worlds 262 vs
-    // 265 ms per 600 frames, 16 384 worlds 474 vs 380 -> split from 12 288 worlds on.
-    fp.split = env_int("CUBEZ_FUSED_SPLIT", W >= 12288 ? 1 : 0);
+    // 265 ms per 600 frames, 16 384 worlds 474 vs 380; 10 240 worlds 602 vs 572 us -> split from 10 240 worlds on.
+    fp.split = env_int("CUBEZ_FUSED_SPLIT", W >= 10240 ? 1 : 0);
     fp.splitMinb = env_int("CUBEZ_FUSED_SPLIT_MINB", 3);
     if (fp.splitMinb < 2 || fp.splitMinb > 4 || G != 8) fp.splitMinb = 2;   // instantiated for G = 8 only
     fp.phaseAMinb = env_int("CUBEZ_FUSED_PHASE_A_MINB", 3);
