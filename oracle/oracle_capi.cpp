@@ -10,6 +10,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <atomic>
 #include <thread>
 
 using namespace czo;
@@ -353,20 +354,18 @@ int czo_world_step(void *h, R dt, int32_t n_steps, int32_t n_threads, cz_step_st
     OracleWorlds *w = (OracleWorlds *)h;
     const int W = (int)w->worlds.size();
     auto t0 = std::chrono::steady_clock::now();
-    auto run = [&](int lo, int hi) {
-        for (int i = lo; i < hi; i++) {
+    // worlds are handed out one at a time from a shared counter (they differ in cost: a static split left threads idle)
+    std::atomic<int> next{0};
+    auto run = [&]() {
+        for (int i = next.fetch_add(1); i < W; i = next.fetch_add(1)) {
             w->worlds[i].totalContacts = w->worlds[i].totalPosIters = w->worlds[i].totalVelIters = 0;
             for (int s = 0; s < n_steps; s++) w->worlds[i].step(dt);
         }
     };
-    if (n_threads <= 1 || W == 1) run(0, W);
+    if (n_threads <= 1 || W == 1) run();
     else {
         std::vector<std::thread> th;
-        int per = (W + n_threads - 1) / n_threads;
-        for (int t = 0; t < n_threads; t++) {
-            int lo = t * per, hi = std::min(W, lo + per);
-            if (lo < hi) th.emplace_back(run, lo, hi);
-        }
+        for (int t = 0; t < std::min<int>(n_threads, W); t++) th.emplace_back(run);
         for (auto &t : th) t.join();
     }
     auto t1 = std::chrono::steady_clock::now();
