@@ -234,12 +234,12 @@ def test_split_phase_launches_equal_persistent_kernel():
     assert sums[1][0] == cpu.checksum_energy()[0] and sums[1][1:4] == (cs["contacts"], cs["pos_iterations"], cs["vel_iterations"])
 
 
-@pytest.mark.parametrize("lanes", ["2", "3", "4"])
-def test_split_step_in_lanes_matches_the_oracle(lanes, monkeypatch):
+@pytest.mark.parametrize("lanes,prec", [("2", _abi.F64), ("3", _abi.F64), ("4", _abi.F64), ("3", _abi.F32)])
+def test_split_step_in_lanes_matches_the_oracle(lanes, prec, monkeypatch):
     """The resident split-mode step runs the batch as independent slices on their own streams (world counters, group
     scratch and ordering per slice).  Uneven slices, episode resets, several calls: state, counters and the last
     frame's contacts must be the oracle's, exactly as with one lane."""
-    scene = scenes.batched_cubedrop(n_worlds=250)
+    scene = scenes.batched_cubedrop(prec, n_worlds=250)
     phase0 = (np.arange(250) * 7) % 150
     monkeypatch.setenv("CUBEZ_FUSED_SPLIT", "1")
     monkeypatch.setenv("CUBEZ_STEP_LANES", lanes)
