@@ -444,6 +444,10 @@ __global__ void __launch_bounds__(128, MINB) k_world_fused(WorldParams p, FusedP
                 for (int b = tid; b < B; b += G) {   // the body transform lives in the global store
 #pragma unroll
                     for (int k = czb::C_L2T0; k <= czb::C_T11W0; k++) st.st(k, gbase + b, p.snap.ld(k, gbase + b));
+                    if (st.force) {   // forces still waiting in the accumulators do not survive a reset
+#pragma unroll
+                        for (int k = 0; k < 3; k++) { st.force[(gbase + b) * 3 + k] = R_(0); st.torque[(gbase + b) * 3 + k] = R_(0); }
+                    }
                 }
             }
             __syncwarp(mask);   // (warp-wide collectives only at warp-uniform points)

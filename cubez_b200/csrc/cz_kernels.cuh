@@ -149,6 +149,10 @@ __global__ void k_episode_reset(WorldParams p) {
 #pragma unroll 4
     for (int k = 0; k < czb::N_CHUNKS; k++) p.st.st(k, i, p.snap.ld(k, i));
     p.st.awake[i] = p.snap.awake[i];
+    if (p.st.force) {   // forces still waiting in the accumulators do not survive a reset
+#pragma unroll
+        for (int k = 0; k < 3; k++) { p.st.force[i * 3 + k] = R_(0); p.st.torque[i * 3 + k] = R_(0); }
+    }
 }
 
 // CalculateDerivedData for n bodies + collider transforms (upload with derive=1, and the

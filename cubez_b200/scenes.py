@@ -246,6 +246,75 @@ def free_bodies(prec=_abi.F64, n: int = 1 << 16, seed: int = 5) -> Scene:
                  contacts_per_world=1)
 
 
+def random_worlds(prec=_abi.F64, n_worlds: int = 64, bodies_per_world: int = 8, seed: int = 11, n_planes: int = 2) -> Scene:
+    """Fuzz scene (no counterpart in the reference's examples): every world a random mix of cubes, spheres and
+    collider-less bodies with their own sizes, masses, dampings, gravity, spin, sleep flags, activation steps and
+    collider Offset matrices (rotation + translation), above one to three half-spaces (ground, a wall, a ramp).  It
+    drives branches the five configs never reach together: sphere-sphere and cube-sphere contacts, non-identity
+    Offsets, several planes, bodies that start asleep or cannot sleep, per-body damping.  Inputs only — the parity
+    tests run the oracle and the CUDA path on the same arrays."""
+    R = prec.dtype
+    B, W = bodies_per_world, n_worlds
+    n = W * B
+    b = _abi.Bodies.defaults(n, prec)
+    c = _abi.Colliders.defaults(n, prec)
+    idx = np.arange(n, dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        seeds = np.uint64(seed) * np.uint64(0x100000001B3) + idx * np.uint64(0x9E3779B97F4A7C15)
+    u = splitmix64_draws(seeds, 40)
+    kind = uniform(u[:, 0], 0, 1)
+    cube, sphere = kind < 0.47, (kind >= 0.47) & (kind < 0.92)
+    half = uniform(u[:, 1:4], 0.25, 0.75)
+    radius = uniform(u[:, 4], 0.25, 0.7)
+    mass = uniform(u[:, 5], 1.0, 10.0).astype(R)
+    c.shape[:] = _abi.SHAPE_NONE
+    c.shape[cube] = _abi.SHAPE_CUBE
+    c.shape[sphere] = _abi.SHAPE_SPHERE
+    c.half_size[cube] = half[cube].astype(R)
+    c.radius[sphere] = radius[sphere].astype(R)
+    c.body[:] = np.tile(np.arange(B, dtype=np.int32), W)
+    b.inverse_mass[:] = R(1.0) / mass
+    for i in range(n):   # host-side setup arithmetic, as SetBlockInertiaTensor / the sphere coefficients of the examples do it
+        if cube[i]:
+            b.inverse_inertia_tensor[i] = _cube_inverse_inertia(tuple(c.half_size[i]), mass[i], prec)
+        else:
+            r = R(radius[i]) if sphere[i] else R(0.5)
+            coeff = R(0.4) * mass[i] * r * r
+            b.inverse_inertia_tensor[i] = m3_invert(inertia_tensor_coeffs(coeff, coeff, coeff, 0.0, 0.0, 0.0, R), R)
+    b.position[:, 0] = uniform(u[:, 6], -1.8, 1.8).astype(R)
+    b.position[:, 2] = uniform(u[:, 7], -1.8, 1.8).astype(R)
+    b.position[:, 1] = uniform(u[:, 8], 0.9, 6.0).astype(R)
+    q = uniform(u[:, 9:13], -1, 1)
+    q[np.sqrt((q * q).sum(axis=1)) < 0.1] = (1.0, 0.0, 0.0, 0.0)
+    q = q.astype(R)
+    ln = np.sqrt(((q[:, 0] * q[:, 0] + q[:, 1] * q[:, 1]) + q[:, 2] * q[:, 2]) + q[:, 3] * q[:, 3])
+    b.orientation[:] = q / ln[:, None]
+    b.velocity[:] = uniform(u[:, 13:16], -2, 2).astype(R)
+    b.rotation[:] = uniform(u[:, 16:19], -2, 2).astype(R)
+    b.linear_damping[:] = uniform(u[:, 19], 0.90, 0.99).astype(R)
+    b.angular_damping[:] = uniform(u[:, 20], 0.85, 0.99).astype(R)
+    b.acceleration[uniform(u[:, 21], 0, 1) < 0.1] = (0.0, 0.0, 0.0)          # a few float
+    b.can_sleep[:] = (uniform(u[:, 22], 0, 1) < 0.8).astype(np.uint8)
+    asleep = uniform(u[:, 23], 0, 1) < 0.1
+    b.is_awake[asleep] = 0
+    b.velocity[asleep] = 0                                                      # SetAwake(false) zeroes them (rigidbody.go:188-190)
+    b.rotation[asleep] = 0
+    # collider Offset: a rotation about z by a random angle and a small translation, for a third of the colliders
+    off = uniform(u[:, 24], 0, 1) < 0.33
+    ang = uniform(u[:, 25], -0.6, 0.6)
+    cs, sn = np.cos(ang), np.sin(ang)
+    o = c.offset
+    o[off, 0] = cs[off].astype(R); o[off, 1] = sn[off].astype(R); o[off, 3] = (-sn[off]).astype(R); o[off, 4] = cs[off].astype(R)
+    o[off, 9:12] = uniform(u[:, 26:29], -0.2, 0.2)[off].astype(R)
+    active = np.zeros(n, dtype=np.int32)
+    late = uniform(u[:, 29], 0, 1) < 0.3
+    active[late] = uniform(u[:, 30], 1, 40)[late].astype(np.int32)
+    normals = [[0.0, 1.0, 0.0], [1.0, 0.0, 0.0], [-0.6, 0.8, 0.0]][:max(1, min(3, n_planes))]
+    offsets = [0.0, -3.0, -1.5][:len(normals)]
+    return Scene("random_worlds", prec, W, B, b, c, _abi.Planes(normals, offsets, prec), active_from=active,
+                 contacts_per_world=max(64, 12 * B), notes={"seed": seed})
+
+
 def with_materials(scene: Scene, seed: int = 7) -> Scene:
     """Three surface materials on any scene (0: the reference's 0.9 / 0.1, 1: slippery, 2: bouncy) with a
     deliberately asymmetric table, ids drawn per body from splitmix64; the first plane is slippery."""

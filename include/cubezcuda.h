@@ -253,7 +253,9 @@ int cz_world_set_materials(cz_world *w, int32_t n_materials, const cz_real *fric
 int cz_world_add_forces(cz_world *w, int32_t first_world, int32_t n_worlds, const cz_real *force, const cz_real *torque);
 /* RL-style episodes (new API): snapshot the current device state as the episode start; world k
  * is at frame phase0[k] (0 <= phase0[k] < length) of its episode now and is restored to the
- * snapshot at the start of every frame on which its phase wraps to 0.  length <= 0 disables. */
+ * snapshot at the start of every frame on which its phase wraps to 0.  A reset also clears the force / torque
+ * accumulators of the world (forces still waiting — of sleeping bodies, or added just before that frame — do not
+ * survive it).  length <= 0 disables. */
 int cz_world_set_episodes(cz_world *w, int32_t length, const int32_t *phase0);
 /* n_steps frames of updateCallback (examples/cubedrop.go:69-75). Asynchronous unless stats != NULL.
  * Device-side errors (CZ_ERR_CAPACITY, CZ_ERR_NIL_BODY) are STICKY: an asynchronous step cannot return them, so the

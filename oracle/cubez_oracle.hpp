@@ -920,6 +920,9 @@ template <class R> struct World {
         if (episodeLength > 0 && (episodePhase0 + (stepIndex - episodeStep0)) % episodeLength == 0) {
             bodies = episodeBodies;
             colliders = episodeColliders;
+            // (new API, no reference counterpart) a reset also drops forces that were still waiting in the accumulators —
+            // of sleeping bodies, or added just before this frame: the episode starts from the snapshot, at rest
+            for (auto &b : bodies) { v_clear(b.forceAccum); v_clear(b.torqueAccum); }
         }
         fix_pointers();
         // updateObjects — cubedrop.go:29-39 / ballistic.go:27-44

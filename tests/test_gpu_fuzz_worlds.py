@@ -1,0 +1,84 @@
+"""GPU: random worlds (scenes.random_worlds — cubes, spheres, collider-less bodies, collider Offsets, several planes,
+sleeping / non-sleeping bodies, late activation, per-body damping and gravity) stepped on every execution path of the
+library against the CPU oracle: counters per block of frames, contact sets of a few worlds, every body's state bits."""
+import os
+
+import numpy as np
+import pytest
+
+from cubez_b200 import _abi, scenes
+from golden_cases import STATE_FIELDS
+from oracle_lib import OracleWorld
+
+pytestmark = pytest.mark.gpu
+
+# (bodies per world, worlds, contact capacity, environment of the plan, world flags); capacities on both sides of 64 and
+# 256 pick the three propagation variants of the fused loops (per-body bitmasks, match list, plain scan)
+PATHS = {
+    "fused8": (8, 96, 64, {"CUBEZ_FUSED_G": "8", "CUBEZ_FUSED_SPLIT": "0"}, _abi.WORLD_FUSED),
+    "split-lanes": (8, 200, 64, {"CUBEZ_FUSED_G": "8", "CUBEZ_FUSED_SPLIT": "1", "CUBEZ_STEP_LANES": "3", "CUBEZ_STEP_LANE_MIN": "16"}, _abi.WORLD_FUSED),
+    "split-matchlist": (8, 150, 192, {"CUBEZ_FUSED_G": "8", "CUBEZ_FUSED_SPLIT": "1", "CUBEZ_STEP_LANES": "2", "CUBEZ_STEP_LANE_MIN": "16"}, _abi.WORLD_FUSED),
+    "fused16": (13, 40, 128, {"CUBEZ_FUSED_G": "16"}, _abi.WORLD_FUSED),
+    "fused32": (24, 20, 320, {"CUBEZ_FUSED_G": "32"}, _abi.WORLD_FUSED),
+    "multi": (10, 24, 240, {}, _abi.WORLD_NO_FUSED),
+}
+
+
+@pytest.mark.parametrize("prec", [_abi.F64, _abi.F32], ids=["f64", "f32"])
+@pytest.mark.parametrize("seed", [3, 17, 40, 101])
+@pytest.mark.parametrize("path", sorted(PATHS))
+def test_random_worlds_match_the_oracle(path, seed, prec, monkeypatch):
+    from cubez_b200.api import BatchedWorld
+    B, W, cap, env, flags = PATHS[path]
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    scene = scenes.random_worlds(prec, n_worlds=W, bodies_per_world=B, seed=seed, n_planes=1 + seed % 3)
+    gpu = BatchedWorld.from_scene(scene, flags=flags, contacts_per_world=cap)
+    cpu = OracleWorld.from_scene(scene)
+    for block in range(6):
+        gs, cs = gpu.step(scene.dt, 20), cpu.step(scene.dt, 20, n_threads=8)
+        assert cs["status"] == 0 and cs["max_contacts"] <= cap
+        for k in ("contacts", "pos_iterations", "vel_iterations"):
+            assert gs[k] == cs[k], (block, k, gs[k], cs[k])
+        for wi in (0, W // 2, W - 1):
+            assert gpu.contact_pairs(wi) == cpu.contact_pairs(wi), (block, wi)
+    g, c = gpu.download(), cpu.download()
+    for f in STATE_FIELDS + ("transform", "inverse_inertia_tensor_world", "last_frame_acceleration"):
+        assert np.array_equal(getattr(g, f), getattr(c, f)), f
+    assert np.array_equal(gpu.download_colliders().transform, cpu.download_colliders().transform)
+    assert gpu.checksum_energy()[0] == cpu.checksum_energy()[0]
+    gpu.close()
+
+
+@pytest.mark.parametrize("prec", [_abi.F64, _abi.F32], ids=["f64", "f32"])
+@pytest.mark.parametrize("path", ["fused8", "split-lanes", "fused16", "multi"])
+def test_random_worlds_with_materials_episodes_and_forces(path, prec, monkeypatch):
+    """The same random worlds with everything the world handle adds on top of the reference's loop switched on together:
+    per-pair surface materials, episode resets at staggered phases, and force / torque accumulators fed between calls."""
+    from cubez_b200.api import BatchedWorld
+    B, W, cap, env, flags = PATHS[path]
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    scene = scenes.with_materials(scenes.random_worlds(prec, n_worlds=W, bodies_per_world=B, seed=29, n_planes=2), seed=5)
+    gpu = BatchedWorld.from_scene(scene, flags=flags, contacts_per_world=cap)
+    cpu = OracleWorld.from_scene(scene)
+    phase0 = (np.arange(W) * 11) % 70
+    gpu.set_episodes(70, phase0)
+    cpu.set_episodes(70, phase0)
+    rng = np.random.default_rng(9)
+    for block, n in enumerate((1, 30, 2, 45, 1, 60)):
+        if block % 2 == 0:   # a push and a twist for one body in five
+            sel = rng.uniform(0, 1, (W * B, 1)) < 0.2
+            f, t = rng.uniform(-40, 40, (W * B, 3)) * sel, rng.uniform(-5, 5, (W * B, 3)) * sel
+            gpu.add_forces(f, t)
+            cpu.add_forces(f, t)
+        gs, cs = gpu.step(scene.dt, n), cpu.step(scene.dt, n, n_threads=8)
+        assert cs["status"] == 0 and cs["max_contacts"] <= cap
+        for k in ("contacts", "pos_iterations", "vel_iterations"):
+            assert gs[k] == cs[k], (block, k, gs[k], cs[k])
+    g, c = gpu.download(), cpu.download()
+    for f in STATE_FIELDS + ("transform", "inverse_inertia_tensor_world", "last_frame_acceleration"):
+        assert np.array_equal(getattr(g, f), getattr(c, f)), f
+    for wi in (0, W - 1):
+        assert gpu.contact_pairs(wi) == cpu.contact_pairs(wi), wi
+    gpu.close()
