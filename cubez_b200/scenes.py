@@ -246,7 +246,8 @@ def free_bodies(prec=_abi.F64, n: int = 1 << 16, seed: int = 5) -> Scene:
                  contacts_per_world=1)
 
 
-def random_worlds(prec=_abi.F64, n_worlds: int = 64, bodies_per_world: int = 8, seed: int = 11, n_planes: int = 2) -> Scene:
+def random_worlds(prec=_abi.F64, n_worlds: int = 64, bodies_per_world: int = 8, seed: int = 11, n_planes: int = 2,
+                  extent: float = 1.8, height: float = 6.0) -> Scene:
     """Fuzz scene (no counterpart in the reference's examples): every world a random mix of cubes, spheres and
     collider-less bodies with their own sizes, masses, dampings, gravity, spin, sleep flags, activation steps and
     collider Offset matrices (rotation + translation), above one to three half-spaces (ground, a wall, a ramp).  It
@@ -281,9 +282,9 @@ def random_worlds(prec=_abi.F64, n_worlds: int = 64, bodies_per_world: int = 8, 
             r = R(radius[i]) if sphere[i] else R(0.5)
             coeff = R(0.4) * mass[i] * r * r
             b.inverse_inertia_tensor[i] = m3_invert(inertia_tensor_coeffs(coeff, coeff, coeff, 0.0, 0.0, 0.0, R), R)
-    b.position[:, 0] = uniform(u[:, 6], -1.8, 1.8).astype(R)
-    b.position[:, 2] = uniform(u[:, 7], -1.8, 1.8).astype(R)
-    b.position[:, 1] = uniform(u[:, 8], 0.9, 6.0).astype(R)
+    b.position[:, 0] = uniform(u[:, 6], -extent, extent).astype(R)
+    b.position[:, 2] = uniform(u[:, 7], -extent, extent).astype(R)
+    b.position[:, 1] = uniform(u[:, 8], 0.9, height).astype(R)
     q = uniform(u[:, 9:13], -1, 1)
     q[np.sqrt((q * q).sum(axis=1)) < 0.1] = (1.0, 0.0, 0.0, 0.0)
     q = q.astype(R)
@@ -310,7 +311,7 @@ def random_worlds(prec=_abi.F64, n_worlds: int = 64, bodies_per_world: int = 8, 
     late = uniform(u[:, 29], 0, 1) < 0.3
     active[late] = uniform(u[:, 30], 1, 40)[late].astype(np.int32)
     normals = [[0.0, 1.0, 0.0], [1.0, 0.0, 0.0], [-0.6, 0.8, 0.0]][:max(1, min(3, n_planes))]
-    offsets = [0.0, -3.0, -1.5][:len(normals)]
+    offsets = [0.0, -(extent + 1.2), -1.5][:len(normals)]
     return Scene("random_worlds", prec, W, B, b, c, _abi.Planes(normals, offsets, prec), active_from=active,
                  contacts_per_world=max(64, 12 * B), notes={"seed": seed})
 

@@ -82,3 +82,79 @@ def test_random_worlds_with_materials_episodes_and_forces(path, prec, monkeypatc
     for wi in (0, W - 1):
         assert gpu.contact_pairs(wi) == cpu.contact_pairs(wi), wi
     gpu.close()
+
+
+@pytest.mark.parametrize("islands", ["0", "1", "2"])
+@pytest.mark.parametrize("n_bodies,seed,prec", [(300, 7, _abi.F64), (700, 8, _abi.F64), (300, 9, _abi.F32)], ids=["300-f64", "700-f64", "300-f32"])
+def test_one_large_random_world_through_the_broadphase(n_bodies, seed, prec, islands, monkeypatch):
+    """ONE large world of random cubes, spheres and collider-less bodies of different sizes, a third of them with a
+    rotated and shifted collider Offset, three half-spaces: the sort-based broadphase (cell size from the largest bound),
+    the plane pass and the large-world resolver (single CTA, or islands) against the oracle's O(n^2) loop — contact
+    sequence every five frames, state bits at the end."""
+    from cubez_b200.api import BatchedWorld
+    monkeypatch.setenv("CUBEZ_RESOLVE_ISLANDS", islands)
+    scene = scenes.random_worlds(prec, n_worlds=1, bodies_per_world=n_bodies, seed=seed, n_planes=3, extent=5.0, height=9.0)
+    gpu = BatchedWorld.from_scene(scene, flags=_abi.WORLD_BROADPHASE, contacts_per_world=8 * n_bodies)
+    cpu = OracleWorld.from_scene(scene)
+    for s in range(0, 40, 5):
+        gs, cs = gpu.step(scene.dt, 5), cpu.step(scene.dt, 5)
+        assert (gs["contacts"], gs["pos_iterations"], gs["vel_iterations"]) == (cs["contacts"], cs["pos_iterations"], cs["vel_iterations"]), s
+        assert gpu.contact_pairs(0) == cpu.contact_pairs(0), s
+    g, c = gpu.download(), cpu.download()
+    for f in STATE_FIELDS:
+        assert np.array_equal(getattr(g, f), getattr(c, f)), f
+    gpu.close()
+
+
+@pytest.mark.parametrize("path", ["fused8", "split-lanes", "multi"])
+def test_random_worlds_rl_loop_and_host_step(path, monkeypatch):
+    """Random worlds through the two host-facing steps: the RL step (AddVelocity + AddRotation on every body, episode
+    resets, observations back) and the host-resident step (state up, frame, state down), against the oracle doing the
+    same edits on its own copy."""
+    from cubez_b200.api import BatchedWorld, Context
+    B, W, cap, env, flags = PATHS[path]
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    scene = scenes.random_worlds(_abi.F64, n_worlds=W, bodies_per_world=B, seed=57, n_planes=2)
+    ctx = Context.get(0, "f64")
+    gpu = BatchedWorld.from_scene(scene, flags=flags, contacts_per_world=cap)
+    cpu = OracleWorld.from_scene(scene)
+    phase0 = (np.arange(W) * 5) % 45
+    gpu.set_episodes(45, phase0)
+    cpu.set_episodes(45, phase0)
+    nb = W * B
+    rng = np.random.default_rng(2)
+    av, ar = ctx.pinned_array((nb, 3)), ctx.pinned_array((nb, 3))
+    obs = ctx.pinned_bodies(nb, fields=BatchedWorld.OBS_FIELDS)
+    for it, n in enumerate((1, 2, 25, 1, 40, 3)):
+        a = rng.uniform(-0.4, 0.4, (nb, 3)) * (rng.uniform(0, 1, (nb, 1)) < 0.15)
+        r = rng.uniform(-0.6, 0.6, (nb, 3)) * (rng.uniform(0, 1, (nb, 1)) < 0.15)
+        av[...] = a
+        ar[...] = r
+        gs = gpu.step_rl(av, ar, obs, scene.dt, n)
+        d = cpu.download()
+        d.velocity[...] = d.velocity + a.astype(d.velocity.dtype)
+        d.rotation[...] = d.rotation + r.astype(d.rotation.dtype)
+        cpu.upload_bodies(d)
+        cs = cpu.step(scene.dt, n, n_threads=8)
+        for k in ("contacts", "pos_iterations", "vel_iterations"):
+            assert gs[k] == cs[k], (it, k, gs[k], cs[k])
+        c = cpu.download()
+        for f in BatchedWorld.OBS_FIELDS:
+            assert np.array_equal(getattr(obs, f), getattr(c, f)), (it, f)
+    # host-resident stepping from here on: the host copy is edited (a nudge), uploaded, stepped, downloaded
+    host = gpu.download(out=ctx.pinned_bodies(nb))
+    for it in range(4):
+        nudge = rng.uniform(-0.05, 0.05, (nb, 3)) * (rng.uniform(0, 1, (nb, 1)) < 0.1)
+        host.velocity[...] = host.velocity + nudge
+        d = cpu.download()
+        d.velocity[...] = d.velocity + nudge
+        cpu.upload_bodies(d)
+        gs = gpu.step_host(host, scene.dt, 1)
+        cs = cpu.step(scene.dt, 1, n_threads=8)
+        for k in ("contacts", "pos_iterations", "vel_iterations"):
+            assert gs[k] == cs[k], ("host", it, k)
+        c = cpu.download()
+        for f in STATE_FIELDS + ("transform", "inverse_inertia_tensor_world", "last_frame_acceleration"):
+            assert np.array_equal(getattr(host, f), getattr(c, f)), ("host", it, f)
+    gpu.close()
