@@ -42,6 +42,9 @@ def test_random_worlds_match_the_oracle(path, seed, prec, monkeypatch):
             assert gs[k] == cs[k], (block, k, gs[k], cs[k])
         for wi in (0, W // 2, W - 1):
             assert gpu.contact_pairs(wi) == cpu.contact_pairs(wi), (block, wi)
+        gc, cc = gpu.contacts(W // 3), cpu.contacts(W // 3)       # the as-generated contacts of the block's last frame, bit for bit
+        for f in ("point", "normal", "penetration", "friction", "restitution"):
+            assert np.array_equal(gc.valid(f), cc.valid(f)), (block, f)
     g, c = gpu.download(), cpu.download()
     for f in STATE_FIELDS + ("transform", "inverse_inertia_tensor_world", "last_frame_acceleration"):
         assert np.array_equal(getattr(g, f), getattr(c, f)), f
@@ -157,4 +160,49 @@ def test_random_worlds_rl_loop_and_host_step(path, monkeypatch):
         c = cpu.download()
         for f in STATE_FIELDS + ("transform", "inverse_inertia_tensor_world", "last_frame_acceleration"):
             assert np.array_equal(getattr(host, f), getattr(c, f)), ("host", it, f)
+    gpu.close()
+
+
+@pytest.mark.parametrize("prec", [_abi.F64, _abi.F32], ids=["f64", "f32"])
+@pytest.mark.parametrize("path", ["fused8", "split-lanes", "fused16", "multi"])
+def test_random_explicit_schedule(path, prec, monkeypatch):
+    """An explicit check list drawn at random — both orders of a pair, repeated entries (each repeat appends its contacts
+    again, as calling CheckForCollisions twice does), a plane as the first or the second operand (colliders.go:116-125
+    hands (plane, body) to the body's own check), plane against plane (no contact, :111-113)."""
+    from cubez_b200.api import BatchedWorld
+    B, W, cap, env, flags = PATHS[path]
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    scene = scenes.random_worlds(prec, n_worlds=W, bodies_per_world=B, seed=71, n_planes=2)
+    rng = np.random.default_rng(B)
+    one, two = [], []
+    for _ in range(5 * B):
+        kind = rng.uniform()
+        a, b2 = (int(v) for v in rng.choice(B, 2, replace=False))
+        pl = -1 - int(rng.integers(0, 2))
+        if kind < 0.55:
+            one.append(a); two.append(b2)
+        elif kind < 0.75:
+            one.append(a); two.append(pl)
+        elif kind < 0.92:
+            one.append(pl); two.append(a)
+        else:
+            one.append(-1); two.append(-2)
+        if rng.uniform() < 0.15:            # the same check again, right behind
+            one.append(one[-1]); two.append(two[-1])
+    scene.schedule = _abi.SCHED_EXPLICIT
+    scene.check_one, scene.check_two = np.asarray(one, dtype=np.int32), np.asarray(two, dtype=np.int32)
+    cap = max(cap, 160)
+    gpu = BatchedWorld.from_scene(scene, flags=flags, contacts_per_world=cap)
+    cpu = OracleWorld.from_scene(scene)
+    for block in range(5):
+        gs, cs = gpu.step(scene.dt, 20), cpu.step(scene.dt, 20, n_threads=8)
+        assert cs["status"] == 0
+        for k in ("contacts", "pos_iterations", "vel_iterations"):
+            assert gs[k] == cs[k], (block, k, gs[k], cs[k])
+        for wi in (0, W - 1):
+            assert gpu.contact_pairs(wi) == cpu.contact_pairs(wi), (block, wi)
+    g, c = gpu.download(), cpu.download()
+    for f in STATE_FIELDS:
+        assert np.array_equal(getattr(g, f), getattr(c, f), equal_nan=True), f
     gpu.close()
