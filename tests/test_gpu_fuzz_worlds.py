@@ -206,3 +206,41 @@ def test_random_explicit_schedule(path, prec, monkeypatch):
     for f in STATE_FIELDS:
         assert np.array_equal(getattr(g, f), getattr(c, f), equal_nan=True), f
     gpu.close()
+
+
+@pytest.mark.parametrize("path", ["fused8", "split-lanes", "multi"])
+def test_random_worlds_partial_uploads_mid_run(path, monkeypatch):
+    """Edits in the middle of a run: a range of worlds is downloaded, changed on the host and uploaded again — primary
+    state only with derived data recomputed on the device (derive = 1), or the whole record as it is (derive = 0) — while
+    the other worlds go on untouched; the oracle gets the same edits."""
+    from cubez_b200.api import BatchedWorld
+    B, W, cap, env, flags = PATHS[path]
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    scene = scenes.random_worlds(_abi.F64, n_worlds=W, bodies_per_world=B, seed=83, n_planes=2)
+    gpu = BatchedWorld.from_scene(scene, flags=flags, contacts_per_world=cap)
+    cpu = OracleWorld.from_scene(scene)
+    rng = np.random.default_rng(4)
+    for it, (first, n, derive) in enumerate(((3, 10, True), (W - 7, 7, False), (0, W, True), (W // 2, 1, False))):
+        gs, cs = gpu.step(scene.dt, 25), cpu.step(scene.dt, 25, n_threads=8)
+        for k in ("contacts", "pos_iterations", "vel_iterations"):
+            assert gs[k] == cs[k], (it, k)
+        d = gpu.download(first, n)
+        e = cpu.download(first, n)
+        for f in STATE_FIELDS + ("transform", "inverse_inertia_tensor_world", "last_frame_acceleration"):
+            assert np.array_equal(getattr(d, f), getattr(e, f)), (it, f)
+        # the edit: lift and spin every body of the range, wake it
+        d.position[:, 1] += rng.uniform(0.5, 1.5, d.position.shape[0]).astype(d.position.dtype)
+        d.rotation[...] = rng.uniform(-1, 1, d.rotation.shape).astype(d.rotation.dtype)
+        d.is_awake[:] = 1
+        d.motion[:] = 0.6
+        gpu.upload_bodies(d, first_world=first, derive=derive)
+        cpu.upload_bodies(d, first_world=first, derive=derive)
+    gs, cs = gpu.step(scene.dt, 30), cpu.step(scene.dt, 30, n_threads=8)
+    for k in ("contacts", "pos_iterations", "vel_iterations"):
+        assert gs[k] == cs[k], k
+    g, c = gpu.download(), cpu.download()
+    for f in STATE_FIELDS + ("transform", "inverse_inertia_tensor_world", "last_frame_acceleration"):
+        assert np.array_equal(getattr(g, f), getattr(c, f)), f
+    assert np.array_equal(gpu.download_colliders().transform, cpu.download_colliders().transform)
+    gpu.close()
