@@ -300,10 +300,12 @@ def random_worlds(prec=_abi.F64, n_worlds: int = 64, bodies_per_world: int = 8, 
     b.is_awake[asleep] = 0
     b.velocity[asleep] = 0                                                      # SetAwake(false) zeroes them (rigidbody.go:188-190)
     b.rotation[asleep] = 0
-    # collider Offset: a rotation about z by a random angle and a small translation, for a third of the colliders
+    # collider Offset: a rotation about z and a small translation, for a third of the colliders.  The angle comes from a
+    # table of Pythagorean pairs (cos, sin): no transcendental, so the Go harness builds the very same matrix
     off = uniform(u[:, 24], 0, 1) < 0.33
-    ang = uniform(u[:, 25], -0.6, 0.6)
-    cs, sn = np.cos(ang), np.sin(ang)
+    table = np.array([[0.8, 0.6], [0.6, 0.8], [0.96, 0.28], [0.8, -0.6], [0.6, -0.8], [0.96, -0.28]])
+    pick = np.minimum((uniform(u[:, 25], 0.0, 6.0)).astype(np.int64), 5)
+    cs, sn = table[pick, 0], table[pick, 1]
     o = c.offset
     o[off, 0] = cs[off].astype(R); o[off, 1] = sn[off].astype(R); o[off, 3] = (-sn[off]).astype(R); o[off, 4] = cs[off].astype(R)
     o[off, 9:12] = uniform(u[:, 26:29], -0.2, 0.2)[off].astype(R)

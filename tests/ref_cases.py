@@ -16,6 +16,13 @@ REF_CASES = {
     "pile216_120": (lambda: scenes.pile(side=6), 120),
     "pile4096_80": (lambda: scenes.pile(side=16), 80),
     "free65536_16": (lambda: scenes.free_bodies(n=65536), 16),
+    # the fuzz scene through the reference's own sources (go/harness/random_headless.go): cubes, spheres and collider-less
+    # bodies of random sizes and masses, rotated and shifted collider Offsets, one to three planes, sleeping and
+    # late-activated bodies, per-body damping and gravity
+    "random8x8_120": (lambda: scenes.random_worlds(n_worlds=8, bodies_per_world=8, seed=11, n_planes=2), 120),
+    "random6x13_3planes_150": (lambda: scenes.random_worlds(n_worlds=6, bodies_per_world=13, seed=23, n_planes=3), 150),
+    "random4x24_100": (lambda: scenes.random_worlds(n_worlds=4, bodies_per_world=24, seed=5, n_planes=1), 100),
+    "random1x300_big_40": (lambda: scenes.random_worlds(n_worlds=1, bodies_per_world=300, seed=7, n_planes=3, extent=5.0, height=9.0), 40),
 }
 
 

@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 
 
 def _flags(name):
-    if name.startswith("pile4096") or name.startswith("pile216"):
+    if name.startswith("pile4096") or name.startswith("pile216") or name.startswith("random1x300"):
         return _abi.WORLD_BROADPHASE
     return 0
 

@@ -9,6 +9,7 @@ mechanically translated reference, tests/golden/ref/).
     go run go/harness/ballistic_headless.go 600           > d.txt ; python tools/compare_go_dump.py d.txt
     go run go/harness/pile_headless.go 60 16              > d.txt ; python tools/compare_go_dump.py d.txt [--gpu]
     go run go/harness/integrate_bench_headless.go 16 65536 > d.txt ; python tools/compare_go_dump.py d.txt
+    go run go/harness/random_headless.go 120 8 8 11 2     > d.txt ; python tools/compare_go_dump.py d.txt [--gpu]
 
 The header line of the dump names the scene; --worlds / --first-world / --bullets / --second-fire repeat the harness
 arguments that the header does not carry.  A committed dump of the translated reference can be compared the same way
@@ -45,11 +46,16 @@ def main():
         scene = scenes.pile(side=round(bodies ** (1 / 3)))
     elif name == "free_bodies":
         scene = scenes.free_bodies(n=bodies)
+    elif name == "random_worlds":
+        worlds = int(header.get("worlds", 1))
+        big = worlds == 1 and bodies >= 100        # the harness's sixth argument: one large world, spread out
+        scene = scenes.random_worlds(n_worlds=worlds, bodies_per_world=bodies // worlds, seed=int(header.get("seed", 11)), n_planes=int(header.get("planes", 2)),
+                                     **({"extent": 5.0, "height": 9.0} if big else {}))
     else:
         raise SystemExit(f"unknown scene in the dump header: {header}")
     if a.gpu:
         from cubez_b200.api import BatchedWorld
-        world = BatchedWorld.from_scene(scene, flags=_abi.WORLD_BROADPHASE if name == "pile" else 0)
+        world = BatchedWorld.from_scene(scene, flags=_abi.WORLD_BROADPHASE if name == "pile" or (name == "random_worlds" and scene.n_worlds == 1 and scene.bodies_per_world >= 100) else 0)
     else:
         from oracle_lib import OracleWorld
         world = OracleWorld.from_scene(scene)
