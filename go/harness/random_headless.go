@@ -4,7 +4,7 @@
 // branches the five BASELINE configs never reach together.  Same frame loop (examples/cubedrop.go:29-75, every
 // collider against every plane, then against every other collider) and same dump as cubedrop_headless.go.
 //
-//	go run random_headless.go <steps> <worlds> <bodies per world> <seed> <planes> > dump.txt
+//	go run random_headless.go <steps> <worlds> <bodies per world> <seed> <planes> [big 0|1] [material seed] > dump.txt
 //
 // Also translated by oracle/go2cpp.py into oracle/_ref/random_headless: keep it inside that tool's Go subset.
 package main
@@ -89,6 +89,19 @@ type world struct {
 	colliders  []cubez.Collider
 	owner      []int
 	index      map[*cubez.RigidBody]int
+	material   []int // per body, when surface materials are on (scenes.with_materials)
+}
+
+// Per-pair surface materials as a host of the reference applies them: the contacts a check (one, two) has just
+// appended get Friction / Restitution of table[material(one)][material(two)] instead of the test constants 0.9 / 0.1
+// (the FIXME at colliders.go:199-202 and its five copies).  The tables are deliberately asymmetric.
+func paint(contacts []*cubez.Contact, from int, one int, two int) {
+	friction := [9]m.Real{0.9, 0.35, 0.8, 0.3, 0.05, 0.5, 0.8, 0.45, 1.1} // row = material of `one`
+	restitution := [9]m.Real{0.1, 0.2, 0.55, 0.25, 0.0, 0.4, 0.6, 0.35, 0.7}
+	for k := from; k < len(contacts); k++ {
+		contacts[k].Friction = friction[one*3+two]
+		contacts[k].Restitution = restitution[one*3+two]
+	}
 }
 
 // one frame of updateCallback (examples/cubedrop.go:69-75); returns the number of contacts generated
@@ -112,19 +125,31 @@ func (w *world) step(planes []*cubez.CollisionPlane, step int, dt m.Real, pairs 
 			continue
 		}
 		var f bool
-		for _, p := range planes {
+		for pi, p := range planes {
+			before := len(contacts)
 			f, contacts = c.CheckAgainstHalfSpace(p, contacts)
 			if f {
 				found = true
+			}
+			if len(w.material) > 0 {
+				planeMaterial := 0
+				if pi == 0 {
+					planeMaterial = 1 // the first plane is slippery
+				}
+				paint(contacts, before, w.material[w.owner[k]], planeMaterial)
 			}
 		}
 		for j, o := range w.colliders {
 			if j == k || step < w.activeFrom[w.owner[j]] {
 				continue
 			}
+			before := len(contacts)
 			f, contacts = cubez.CheckForCollisions(c, o, contacts)
 			if f {
 				found = true
+			}
+			if len(w.material) > 0 {
+				paint(contacts, before, w.material[w.owner[k]], w.material[w.owner[j]])
 			}
 		}
 	}
@@ -149,9 +174,17 @@ func (w *world) step(planes []*cubez.CollisionPlane, step int, dt m.Real, pairs 
 }
 
 // scenes.random_worlds: body g (global index) draws 40 uniforms from splitmix64(seed*0x100000001B3 + g*0x9E3779B97F4A7C15)
-func build(w *world, first int, count int, seed uint64, extent float64, height float64) {
+func build(w *world, first int, count int, seed uint64, extent float64, height float64, matSeed int) {
 	for i := 0; i < count; i++ {
 		g := uint64(first + i)
+		if matSeed > 0 { // scenes.with_materials: id = min(int(U(0,3)), 2) from splitmix64(matSeed + g)
+			ms := uint64(matSeed) + g
+			id := int(uniform(draw(&ms), 0.0, 3.0))
+			if id > 2 {
+				id = 2
+			}
+			w.material = append(w.material, id)
+		}
 		state := seed*0x100000001B3 + g*0x9E3779B97F4A7C15
 		var u [40]float64
 		for k := 0; k < 40; k++ {
@@ -272,10 +305,11 @@ func main() {
 	nPlanes := argInt(5, 2)
 	extent := 1.8
 	height := 6.0
-	if len(os.Args) > 6 { // one large world: spread out
+	if argInt(6, 0) > 0 { // one large world: spread out
 		extent = 5.0
 		height = 9.0
 	}
+	matSeed := argInt(7, 0) // > 0: per-pair surface materials with ids drawn from this seed
 	planes := []*cubez.CollisionPlane{cubez.NewCollisionPlane(m.Vector3{0.0, 1.0, 0.0}, 0.0)}
 	if nPlanes >= 2 {
 		planes = append(planes, cubez.NewCollisionPlane(m.Vector3{1.0, 0.0, 0.0}, m.Real(-(extent + 1.2))))
@@ -287,11 +321,11 @@ func main() {
 	for k := 0; k < nWorlds; k++ {
 		w := new(world)
 		w.index = make(map[*cubez.RigidBody]int)
-		build(w, k*perWorld, perWorld, uint64(seed), extent, height)
+		build(w, k*perWorld, perWorld, uint64(seed), extent, height, matSeed)
 		worlds = append(worlds, w)
 	}
 	dt := m.Real(1.0 / 60.0)
-	fmt.Printf("cubez-dump v2 scene=random_worlds worlds=%d bodies=%d steps=%d seed=%d planes=%d\n", nWorlds, nWorlds*perWorld, steps, seed, nPlanes)
+	fmt.Printf("cubez-dump v2 scene=random_worlds worlds=%d bodies=%d steps=%d seed=%d planes=%d big=%d materials=%d\n", nWorlds, nWorlds*perWorld, steps, seed, nPlanes, argInt(6, 0), matSeed)
 	start := time.Now()
 	for s := 0; s < steps; s++ {
 		var pairs uint64

@@ -21,11 +21,12 @@ CASES = {   # name -> (binary, args)          scene builder of the same case: te
     "pile216_120": ("pile_headless", ["120", "6"]),
     "pile4096_80": ("pile_headless", ["80", "16"]),
     "free65536_16": ("integrate_bench_headless", ["16", "65536"]),
-    # the fuzz scene (scenes.random_worlds): <steps> <worlds> <bodies per world> <seed> <planes> [big]
+    # the fuzz scene (scenes.random_worlds): <steps> <worlds> <bodies per world> <seed> <planes> [big 0|1] [material seed]
     "random8x8_120": ("random_headless", ["120", "8", "8", "11", "2"]),
     "random6x13_3planes_150": ("random_headless", ["150", "6", "13", "23", "3"]),
     "random4x24_100": ("random_headless", ["100", "4", "24", "5", "1"]),
-    "random1x300_big_40": ("random_headless", ["40", "1", "300", "7", "3", "big"]),
+    "random1x300_big_40": ("random_headless", ["40", "1", "300", "7", "3", "1"]),
+    "random8x10_materials_150": ("random_headless", ["150", "8", "10", "31", "2", "0", "5"]),   # + per-pair surface materials painted by the host
 }
 
 if __name__ == "__main__":

@@ -23,6 +23,9 @@ REF_CASES = {
     "random6x13_3planes_150": (lambda: scenes.random_worlds(n_worlds=6, bodies_per_world=13, seed=23, n_planes=3), 150),
     "random4x24_100": (lambda: scenes.random_worlds(n_worlds=4, bodies_per_world=24, seed=5, n_planes=1), 100),
     "random1x300_big_40": (lambda: scenes.random_worlds(n_worlds=1, bodies_per_world=300, seed=7, n_planes=3, extent=5.0, height=9.0), 40),
+    # ... and with per-pair surface materials: the harness paints Friction / Restitution onto the contacts each check
+    # appends, as a host of the reference would; the library does it through cz_world_set_materials
+    "random8x10_materials_150": (lambda: scenes.with_materials(scenes.random_worlds(n_worlds=8, bodies_per_world=10, seed=31, n_planes=2), seed=5), 150),
 }
 
 

@@ -48,9 +48,11 @@ def main():
         scene = scenes.free_bodies(n=bodies)
     elif name == "random_worlds":
         worlds = int(header.get("worlds", 1))
-        big = worlds == 1 and bodies >= 100        # the harness's sixth argument: one large world, spread out
+        big = int(header.get("big", 0)) > 0        # the harness's sixth argument: one large world, spread out
         scene = scenes.random_worlds(n_worlds=worlds, bodies_per_world=bodies // worlds, seed=int(header.get("seed", 11)), n_planes=int(header.get("planes", 2)),
                                      **({"extent": 5.0, "height": 9.0} if big else {}))
+        if int(header.get("materials", 0)) > 0:
+            scene = scenes.with_materials(scene, seed=int(header["materials"]))
     else:
         raise SystemExit(f"unknown scene in the dump header: {header}")
     if a.gpu:
