@@ -15,13 +15,18 @@
 //     them, so the pins are dumps PRINTED BY THE TRANSLATED REFERENCE (tests/golden/ref/*.txt, made by
 //     oracle/make_ref_golden.py): this restatement reproduces them bit for bit — per frame the contact count, the
 //     (body, body) sequence, the as-generated contact geometry and the raw bits of every body's state — on
-//     cubedrop (600 frames), ballistic-64 (600), piles of 27 / 216 bodies, 256 batched perturbed worlds (600) and
-//     65 536 free bodies (tests/test_oracle_vs_reference_dump.py); the 4 096-body pile (80 frames) is checked from the GPU side.
+//     cubedrop (600 frames), ballistic-64 (600), piles of 27 / 216 bodies, 256 batched perturbed worlds (600),
+//     65 536 free bodies and five runs of a fuzz scene (random shapes, sizes, masses, collider Offsets, several planes,
+//     host-painted surface materials) (tests/test_oracle_vs_reference_dump.py); the 4 096-body pile (80 frames) is
+//     checked from the GPU side;
+//   * float32: the reference's own switch is the one-line edit `type Real float64` -> float32 (math/math.go:23);
+//     go2cpp.py --real=float32 applies it to the text it reads and gives untyped constants the type of the operand they
+//     meet (rounded once from the exact value, as Go does).  The float32 instantiation of this restatement reproduces
+//     the seven float32 dumps bit for bit as well.
 // What is not covered: the Go compiler itself (the harnesses are ready for it: tools/compare_go_dump.py) and math.Pow,
 // which is C pow() here and in the translation (<= 1 ulp from Go's; the library takes the Pow factors as host inputs).
 // The restatement keeps the Go source's expression order (left to right, one IEEE rounding per operation, no FMA
-// contraction: build with -ffp-contract=off).  The float32 instantiation has no translated counterpart (the reference
-// does not compile as float32 without edits): it is pinned only through the shared template.
+// contraction: build with -ffp-contract=off).
 //
 // Every function cites the reference file:line (paths relative to /root/reference) it
 // restates.  The structures keep the reference's AoS layout and the per-contact heap

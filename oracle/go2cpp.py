@@ -147,7 +147,31 @@ def const_cpp(c):
     f = float(v)    # Fraction -> float is correctly rounded (round-half-even), like Go's conversion of the exact constant
     if f != f or f in (float("inf"), float("-inf")):
         raise ValueError("constant overflows float64")
-    return f.hex() if f == f else "NAN"
+    # An untyped constant has no type until it meets a typed operand: `0.3 < x` is a float32 comparison when x is float32
+    # and the constant is then the exact value rounded ONCE to float32.  C++ would promote to double instead, so the
+    # literal carries both roundings and picks by the type it meets (struct gouf in the prelude).
+    return f"gouf({f.hex()}, {frac_to_f32(v).hex()}f)"
+
+
+def frac_to_f32(v):
+    """The float32 nearest to the exact rational v (round-half-even), returned as a Python float holding exactly that value."""
+    v = Fraction(v)
+    if v == 0:
+        return 0.0
+    sign, a = (-1.0 if v < 0 else 1.0), abs(v)
+    e = a.numerator.bit_length() - a.denominator.bit_length()      # 2^(e-1) < a < 2^(e+1)
+    if Fraction(2) ** e > a:
+        e -= 1                                                      # now 2^e <= a < 2^(e+1)
+    q_exp = max(e - 23, -149)                                       # spacing of float32 at this magnitude (subnormals: 2^-149)
+    scaled = a / (Fraction(2) ** q_exp)
+    q = scaled.numerator // scaled.denominator
+    rem = scaled - q
+    if rem > Fraction(1, 2) or (rem == Fraction(1, 2) and (q & 1)):
+        q += 1
+    r = Fraction(q) * (Fraction(2) ** q_exp)
+    if r >= Fraction(2) ** 128:
+        raise ValueError("constant overflows float32")
+    return sign * float(r)      # exact: q has at most 25 bits
 
 
 class Package:
@@ -1056,7 +1080,7 @@ class Translator:
 
     def translate_file(self, path):
         self.fname = path
-        self.toks, self.p = lex(open(path).read(), path), 0
+        self.toks, self.p = lex(read_source(path), path), 0
         self.imports = {}
         self.scopes = [set()]
         self.skip_semis()
@@ -1129,7 +1153,7 @@ class Translator:
         self.packages[path] = self.pkg
         for f in files:
             self.fname = f
-            self.prescan_types(lex(open(f).read(), f))
+            self.prescan_types(lex(read_source(f), f))
         for f in files:
             self.translate_file(f)
         return self.emit_package()
@@ -1197,6 +1221,7 @@ PRELUDE = r'''// GENERATED by oracle/go2cpp.py from the reference's Go sources â
 #include <tuple>
 #include <unordered_map>
 #include <vector>
+#include <type_traits>
 
 // ---- Go value / pointer plumbing ----------------------------------------------------------------
 template <class T> inline T &D(T *p) { return *p; }                 // Go's implicit dereference in selectors and indexing
@@ -1249,6 +1274,23 @@ template <class To, class From> inline To goconv(const From &v) {
 [[noreturn]] inline void gopanic(const std::string &m) { std::fprintf(stderr, "panic: %s\n", m.c_str()); std::abort(); }
 
 // ---- the slices of the Go standard library the sources use ------------------------------------------
+// An untyped Go float constant: takes the type of the operand it meets (see const_cpp in go2cpp.py).
+struct gouf {
+    double d; float f;
+    constexpr gouf(double d_, float f_) : d(d_), f(f_) {}
+    constexpr operator double() const { return d; }
+    constexpr operator float() const { return f; }
+    template <class T> constexpr T as() const { if constexpr (std::is_same<T, float>::value) return f; else return (T)d; }
+};
+#define GOUF_BIN(OP) \
+    template <class T, class = typename std::enable_if<std::is_arithmetic<T>::value>::type> constexpr auto operator OP(gouf c, T x) -> decltype(x OP x) { return c.as<T>() OP x; } \
+    template <class T, class = typename std::enable_if<std::is_arithmetic<T>::value>::type> constexpr auto operator OP(T x, gouf c) -> decltype(x OP x) { return x OP c.as<T>(); }
+GOUF_BIN(+) GOUF_BIN(-) GOUF_BIN(*) GOUF_BIN(/) GOUF_BIN(<) GOUF_BIN(>) GOUF_BIN(<=) GOUF_BIN(>=) GOUF_BIN(==) GOUF_BIN(!=)
+#undef GOUF_BIN
+#define GOUF_ASSIGN(OP) template <class T, class = typename std::enable_if<std::is_arithmetic<T>::value>::type> inline T &operator OP(T &x, gouf c) { return x OP c.as<T>(); }
+GOUF_ASSIGN(+=) GOUF_ASSIGN(-=) GOUF_ASSIGN(*=) GOUF_ASSIGN(/=)
+#undef GOUF_ASSIGN
+
 namespace gomath {
 const double MaxFloat64 = std::numeric_limits<double>::max();
 const double SmallestNonzeroFloat64 = std::numeric_limits<double>::denorm_min();
@@ -1328,7 +1370,21 @@ template <class... A> inline void Println(A... a) { std::vector<Arg> v{mk(a)...}
 '''
 
 
+# --real=float32: the reference's own switch for single precision is a one-line source edit ("type Real float64",
+# math/math.go:23).  The translator applies that edit to the text it reads â€” nothing else changes.
+REAL_EDIT = None
+
+
+def read_source(path):
+    text = open(path).read()
+    if REAL_EDIT and path.endswith(os.path.join("math", "math.go")):
+        assert "type Real float64" in text, "math.go no longer declares `type Real float64`"
+        text = text.replace("type Real float64", "type Real " + REAL_EDIT, 1)
+    return text
+
+
 def main(argv):
+    global REAL_EDIT
     out = None
     specs = []
     run_tests = None
@@ -1337,6 +1393,9 @@ def main(argv):
         if argv[i] == "-o":
             out = argv[i + 1]
             i += 2
+        elif argv[i].startswith("--real="):
+            REAL_EDIT = argv[i].split("=", 1)[1]
+            i += 1
         elif argv[i].startswith("--run-tests="):      # translate <pkg>'s *_test.go too and emit a main that runs every Test* function
             run_tests = argv[i].split("=", 1)[1]
             i += 1

@@ -27,6 +27,14 @@ CASES = {   # name -> (binary, args)          scene builder of the same case: te
     "random4x24_100": ("random_headless", ["100", "4", "24", "5", "1"]),
     "random1x300_big_40": ("random_headless", ["40", "1", "300", "7", "3", "1"]),
     "random8x10_materials_150": ("random_headless", ["150", "8", "10", "31", "2", "0", "5"]),   # + per-pair surface materials painted by the host
+    # the reference in SINGLE precision (`type Real float32`, math/math.go:23 — go2cpp.py --real=float32)
+    "cubedrop_f32_600": ("cubedrop_headless_f32", ["600"]),
+    "batched64_f32_300": ("cubedrop_headless_f32", ["300", "64", "0"]),
+    "ballistic16_f32_300": ("ballistic_headless_f32", ["300", "16"]),
+    "pile216_f32_100": ("pile_headless_f32", ["100", "6"]),
+    "free65536_f32_16": ("integrate_bench_headless_f32", ["16", "65536"]),
+    "random8x8_f32_120": ("random_headless_f32", ["120", "8", "8", "11", "2"]),
+    "random8x10_materials_f32_150": ("random_headless_f32", ["150", "8", "10", "31", "2", "0", "5"]),
 }
 
 if __name__ == "__main__":

@@ -3,6 +3,7 @@ reference's own Go sources, mechanically translated — see oracle/go2cpp.py).  
 import os
 
 from cubez_b200 import scenes
+from cubez_b200._abi import F32
 
 REF_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref")
 REF_CASES = {
@@ -26,6 +27,15 @@ REF_CASES = {
     # ... and with per-pair surface materials: the harness paints Friction / Restitution onto the contacts each check
     # appends, as a host of the reference would; the library does it through cz_world_set_materials
     "random8x10_materials_150": (lambda: scenes.with_materials(scenes.random_worlds(n_worlds=8, bodies_per_world=10, seed=31, n_planes=2), seed=5), 150),
+    # the reference in SINGLE precision: `type Real float64` -> float32 (math/math.go:23), the reference's own switch, applied by
+    # the translator to the text it reads (oracle/go2cpp.py --real=float32).  The float32 library and oracle must print the same.
+    "cubedrop_f32_600": (lambda: scenes.cubedrop(F32), 600),
+    "batched64_f32_300": (lambda: scenes.batched_cubedrop(F32, n_worlds=64), 300),
+    "ballistic16_f32_300": (lambda: scenes.ballistic(F32, n_bullets=16), 300),
+    "pile216_f32_100": (lambda: scenes.pile(F32, side=6), 100),
+    "free65536_f32_16": (lambda: scenes.free_bodies(F32, n=65536), 16),
+    "random8x8_f32_120": (lambda: scenes.random_worlds(F32, n_worlds=8, bodies_per_world=8, seed=11, n_planes=2), 120),
+    "random8x10_materials_f32_150": (lambda: scenes.with_materials(scenes.random_worlds(F32, n_worlds=8, bodies_per_world=10, seed=31, n_planes=2), seed=5), 150),
 }
 
 

@@ -13,7 +13,7 @@ pytestmark = pytest.mark.gpu
 
 
 def _flags(name):
-    if name.startswith("pile4096") or name.startswith("pile216") or name.startswith("random1x300"):
+    if name.startswith("pile4096") or name.startswith("pile216") or name.startswith("random1x300"):     # (pile216_f32 too)
         return _abi.WORLD_BROADPHASE
     return 0
 

@@ -5,7 +5,8 @@ math/*.go, read where they lie under /root/reference — translated statement by
 driven by the headless harness mains of go/harness/ (oracle/Makefile target `ref`, oracle/make_ref_golden.py).  The
 translator knows Go syntax, not physics, so agreement here is not a shared reading of the source by one author: every
 frame's contact count, (body, body) sequence, as-generated contact geometry and the raw bits of every body's state
-must be identical.  What remains outside: the Go compiler itself, and math.Pow (C pow() on both sides; the library
+must be identical — in float64 and, through the reference's own `type Real float32` switch (math/math.go:23, applied
+by go2cpp.py --real=float32), in float32.  What remains outside: the Go compiler itself, and math.Pow (C pow() on both sides; the library
 takes the Pow factors as host inputs)."""
 import os
 import subprocess
