@@ -185,3 +185,26 @@ def test_pipelined_rl_step_equals_the_synchronous_one(n_worlds):
     with pytest.raises(CubezError):
         b.rl_wait(tickets[-1])                    # nothing in flight any more
     a.close(); b.close()
+
+
+def test_step_rl_with_pageable_host_arrays():
+    """Ordinary (pageable) numpy arrays for the actions and the observations: the batched page-locked copy path does not
+    apply, the step falls back to one plain copy per field — same values."""
+    from cubez_b200._abi import Bodies
+    sc = scenes.batched_cubedrop(n_worlds=200)
+    gpu = BatchedWorld.from_scene(sc, contacts_per_world=64)
+    cpu = OracleWorld.from_scene(sc)
+    nb = 200 * 8
+    rng = np.random.default_rng(3)
+    obs = Bodies(nb, gpu.prec, fields=BatchedWorld.OBS_FIELDS)
+    for it, n in enumerate((1, 30, 2, 50)):
+        a = np.ascontiguousarray(rng.uniform(-0.3, 0.3, (nb, 3)) * (rng.uniform(0, 1, (nb, 1)) < 0.2))
+        gs = gpu.step_rl(a, None, obs, sc.dt, n)
+        oracle_apply(cpu, a, None)
+        cs = cpu.step(sc.dt, n, n_threads=8)
+        for k in ("contacts", "pos_iterations", "vel_iterations"):
+            assert gs[k] == cs[k], (it, k)
+        c = cpu.download()
+        for f in BatchedWorld.OBS_FIELDS:
+            assert np.array_equal(getattr(obs, f), getattr(c, f)), (it, f)
+    gpu.close()
